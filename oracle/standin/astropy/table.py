@@ -59,6 +59,17 @@ class Column(np.ndarray):
         return arr
 
 
+class TableColumns(OrderedDict):
+    """OrderedDict that also takes int / slice keys like astropy's."""
+
+    def __getitem__(self, item):
+        if isinstance(item, (int, np.integer)):
+            return list(self.values())[item]
+        if isinstance(item, slice):
+            return TableColumns(list(self.items())[item])
+        return OrderedDict.__getitem__(self, item)
+
+
 class MaskedColumn(Column):
     pass
 
@@ -86,7 +97,7 @@ class Row:
 class Table:
     def __init__(self, data=None, names=None, meta=None, rows=None, copy=True,
                  dtype=None):
-        self.columns = OrderedDict()
+        self.columns = TableColumns()
         self.meta = OrderedDict() if meta is None else meta
         if isinstance(data, Row):
             t = data._table
@@ -174,7 +185,7 @@ class Table:
         del self.columns[name]
 
     def rename_column(self, old, new):
-        self.columns = OrderedDict((new if k == old else k, v)
+        self.columns = TableColumns((new if k == old else k, v)
                                    for k, v in self.columns.items())
         self.columns[new].name = new
 

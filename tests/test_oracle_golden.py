@@ -1,0 +1,365 @@
+"""Pin the numpy oracle against the reference.
+
+``tests/golden/*.npz`` were produced by running the UNMODIFIED reference
+(``oracle/gen_golden.py``); the known-answer cases are transcribed from the
+reference's own tests (file:line in each docstring).  CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import marxs_oracle as mo
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+RTOL = 2e-13   # reference = BLAS/einsum summation order; oracle = left-to-right
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False))
+
+
+def table_from(g, prefix):
+    t = mo.PhotonTable()
+    for k in ('pos', 'dir', 'energy', 'polarization', 'probability'):
+        if prefix + 'in_' + k in g:
+            t[k] = g[prefix + 'in_' + k].copy()
+    return t
+
+
+def assert_cols(out, g, prefix, exact=(), skip=(), rtol=RTOL, atol=1e-13):
+    names = [k[len(prefix) + 4:] for k in g if k.startswith(prefix + 'out_')]
+    assert names
+    for c in names:
+        if c in skip:
+            continue
+        ref = g[prefix + 'out_' + c]
+        assert c in out, 'missing column ' + c
+        got = np.asarray(out[c])
+        if c in exact:
+            np.testing.assert_array_equal(np.nan_to_num(got, nan=-999), np.nan_to_num(ref, nan=-999), err_msg=c)
+        else:
+            np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol, equal_nan=True, err_msg=c)
+    assert set(names) - set(skip) <= set(out.colnames)
+
+
+# ---------------------------------------------------------------------------
+# known-answer vectors transcribed from the reference tests
+# ---------------------------------------------------------------------------
+def test_intersect_known_answers():
+    """math/tests/test_geometry.py:11-56"""
+    pos4d = mo.compose([-50., 0., 0.], np.eye(3), [1., 1., 1.])
+    g = mo.PlaneConsts(pos4d)
+    # photon hitting the plane head-on at origin of the plane
+    pos = np.array([[0., 0., 0., 1.], [0., 0.1, 0.2, 1.], [0., 5., 0., 1.], [-100., 0., 0., 1.]])
+    dir = np.array([[-1., 0., 0., 0.]] * 4)
+    hit, ipos, loc = mo.plane_intersect(g, dir, pos)
+    assert list(hit) == [True, True, False, False]
+    np.testing.assert_array_equal(ipos[0], [-50., 0., 0., 1.])
+    np.testing.assert_array_equal(ipos[1], [-50., 0.1, 0.2, 1.])
+    np.testing.assert_array_equal(loc[1], [0.1, 0.2])
+    assert np.all(np.isnan(ipos[2, :3])) and np.all(np.isnan(loc[2]))
+    # ray parallel to the plane never hits
+    hit, _, _ = mo.plane_intersect(g, np.array([[0., 1., 0., 0.]]), np.array([[-50., 0., 0., 1.]]))
+    assert not hit[0]
+
+
+def test_grating_equation():
+    """optics/tests/test_grating.py:65-92: sin(alpha) = sin(beta) + m lambda / d"""
+    n = 5
+    for order in (-2, -1, 0, 1, 3):
+        p = mo.generate_test_photons(n)
+        angle = 0.3
+        p['dir'] = np.tile(np.array([-np.cos(angle), np.sin(angle), 0., 0.]), (n, 1))
+        g = mo.FlatGrating(d=1e-3, order_selector=mo.OrderSelector([order]), zoom=20)
+        mo.assign_slots(g)
+        p = g(p, mo.Draws([np.full(n, 0.5)]))
+        lam = mo.energy2wave / 1.0
+        # grooves along z: dispersion in y
+        sin_out = p['dir'][:, 1] / np.sqrt((p['dir'][:, :3] ** 2).sum(axis=1))
+        np.testing.assert_allclose(np.abs(sin_out - np.sin(angle)), abs(order) * lam / 1e-3, rtol=1e-9, atol=1e-15)
+        assert np.all(p['order'] == order)
+        np.testing.assert_allclose(p['dir'][:, 2], 0., atol=1e-16)
+
+
+def test_zero_order_and_miss():
+    """test_grating.py:16-46 (zero order passes straight), :285-294 (misses -> NaN / -1)"""
+    p = mo.generate_test_photons(3)
+    p['pos'][2, 1] = 50.   # misses the 1x1 grating
+    g = mo.FlatGrating(d=1e-3, order_selector=mo.OrderSelector([0]), id_col='facet', id_num=7)
+    mo.assign_slots(g)
+    out = g(p.copy(), mo.Draws([np.zeros(3)]))
+    np.testing.assert_allclose(out['dir'][:2], p['dir'][:2], atol=1e-16)
+    assert np.all(out['order'][:2] == 0) and np.isnan(out['order'][2])
+    assert list(out['facet']) == [7, 7, -1]
+    assert np.isnan(out['grat_y'][2])
+    np.testing.assert_array_equal(out['pos'][2], p['pos'][2])
+
+
+def test_cat_sign_convention():
+    """test_grating.py:179-223: FlatGrating vs CATGrating order sign."""
+    n = 2
+    dirs = np.array([[-1., 0.1, 0., 0.], [-1., -0.1, 0., 0.]])
+    res = {}
+    for cls in (mo.FlatGrating, mo.CATGrating):
+        p = mo.generate_test_photons(n)
+        p['dir'] = dirs.copy()
+        g = cls(d=1e-3, order_selector=mo.OrderSelector([1]), zoom=5)
+        mo.assign_slots(g)
+        res[cls] = g(p, mo.Draws([np.zeros(n)]))['dir']
+    # flat: both photons displaced the same way; CAT: opposite ways
+    dy_flat = res[mo.FlatGrating][:, 1] / -res[mo.FlatGrating][:, 0] - dirs[:, 1]
+    dy_cat = res[mo.CATGrating][:, 1] / -res[mo.CATGrating][:, 0] - dirs[:, 1]
+    assert np.sign(dy_flat[0]) == np.sign(dy_flat[1])
+    assert np.sign(dy_cat[0]) == -np.sign(dy_cat[1])
+
+
+def test_detector_pixels():
+    """optics/tests/test_detector.py:16-35"""
+    det = mo.FlatDetector(zoom=100., pixsize=0.5)
+    assert det.npix == [400, 400]
+    assert det.centerpix == [199.5, 199.5]
+    p = mo.generate_test_photons(2)
+    p['pos'][1, 1:3] = [0.25, -0.25]
+    out = det(p)
+    np.testing.assert_allclose(out['detpix_x'], [199.5, 200.0])
+    np.testing.assert_allclose(out['detpix_y'], [199.5, 199.0])
+    np.testing.assert_allclose(out['det_x'], [0., 0.25])
+
+
+def test_multilayer_known_answers():
+    """optics/tests/test_mlMirror.py:14-78 transcribed (testFile_mirror.txt values inline)."""
+    g = load('mlmirror')
+    pos = np.tile([1., 0., 0., 1.], (4, 1))
+    dir = np.array([[-1., -1.5, 0., 0], [-1., 1.5, 0., 0], [-1., -0.5, 13., 0], [-1., -1.5, 0., 0]])
+    pol = np.array([[0., 0., 1., 0], [1., 0., 0., 0], [1., 0., 0., 0],
+                    [1. / np.sqrt(2.), 0., 1. / np.sqrt(2.), 0.]])
+    pol[1, 0:3] = np.cross(dir[1, 0:3], pol[0, 0:3])
+    pol[1, 0:3] /= np.linalg.norm(pol[1, 0:3])
+    t = mo.PhotonTable(pos=pos, dir=dir,
+                       energy=np.array([1.23984282 / 3.02, 1.23984282 / 6, 0.4, 1.23984282 / 3.02]),
+                       polarization=pol, probability=np.ones(4))
+    refl = dict(x_mm=[22., 24., 26.], peak=[5.41, 6.21, 0.42], peak_lambda=[2., 4., 6.],
+                fwhm=[0.0706446, 0.0235482, 0.0941928])
+    polf = dict(energy_ev=g['ml_pol_energy_ev'], pol=g['ml_pol'])
+    out = mo.MultiLayerMirror(refl=refl, pol=polf, zoom=[1, 24.5, 12])(t)
+    expected_dir = mo.normalize3(np.array([[1., -1.5, 0.], [1., 1.5, 0.], [-1., -0.5, 13.], [1., -1.5, 0.]]))
+    np.testing.assert_allclose(mo.normalize3(out['dir']), expected_dir, atol=1e-12)
+    tested = np.interp(1.23984282 / 3.02, g['ml_pol_energy_ev'] / 1000, g['ml_pol'])
+    expected_prob = np.array([0.0581 * np.exp(-0.5) / tested, 0., 1., 0.5 * 0.0581 * np.exp(-0.5) / tested])
+    assert np.allclose(out['probability'], expected_prob)
+    sim = mo.normalize3(out['polarization'])
+    for i in [0, 3]:
+        assert np.allclose(np.abs(sim[i]), [0., 0., 1.])
+    assert np.all(np.isnan(sim[1]))
+
+
+@pytest.mark.parametrize("angle,avgpol", [(0., 0.5), (np.pi / 2, 0.)])
+def test_double_brewster(angle, avgpol):
+    """test_mlMirror.py:138-166 (euler2mat 'szxy'/'szyx' matrices written out)."""
+    ang = np.arange(0, 2. * np.pi, np.pi / 4)
+    t = mo.PhotonTable(pos=np.tile([1., 0., 0., 1.], (8, 1)), dir=np.tile([-1., 0., 0., 0.], (8, 1)),
+                       energy=np.ones(8),
+                       polarization=np.vstack([np.zeros(8), np.sin(ang), np.cos(ang), np.zeros(8)]).T,
+                       probability=np.ones(8))
+    c, s = np.cos(np.pi / 4), np.sin(np.pi / 4)
+    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.]])
+    ry = lambda a: np.array([[np.cos(a), 0, np.sin(a)], [0, 1., 0], [-np.sin(a), 0, np.cos(a)]])
+    ml1 = mo.FlatBrewsterMirror(orientation=rz(np.pi / 4))
+    ml2 = mo.FlatBrewsterMirror(position=[0, 1, 0], orientation=np.dot(ry(angle), rz(-np.pi / 4)))
+    out = ml2(ml1(t))
+    assert np.isclose(np.mean(out['probability']), avgpol)
+
+
+def test_baffle_known():
+    """optics/tests/test_baffle.py:8-51 (CircularHole compares absolute r <= 1.0)"""
+    b = mo.CircularBaffle(zoom=[1., 1.5, 0.3])
+    p = mo.generate_test_photons(3)
+    p['pos'][1, 1:3] = [1.49, 0.29]
+    p['pos'][2, 1:3] = [0.5, 0.1]
+    out = b(p)
+    assert list(out['probability']) == [1., 0., 1.]
+
+
+def test_parallel_numbering():
+    """simulator/tests/test_parallel.py:11-23"""
+    pos = [[0, -10.1, -10.1], [0, .1, -10.1], [0, -10.1, .1], [0, .1, .1]]
+    det = mo.Parallel(mo.FlatDetector, {'position': pos}, {'pixsize': 0.01, 'zoom': 5}, id_col='CCD_ID')
+    assert [e.id_num for e in det.elements] == [0, 1, 2, 3]
+    out = det(mo.generate_test_photons(5))
+    assert np.all(out['CCD_ID'] == 3)
+
+
+def test_choice_is_inverse_cdf():
+    g = load('order_selectors')
+    sel = mo.OrderSelector(g['sel_orders'], g['sel_p'])
+    m, p = sel.select(g['sel_u'], np.ones(len(g['sel_u'])), None, None)
+    np.testing.assert_array_equal(m, g['sel_m'])
+    np.testing.assert_allclose(p, g['sel_prob'], rtol=1e-15)
+    # and against numpy's legacy generator directly
+    np.random.seed(99)
+    ref = np.random.choice(sel.orderlist, size=500, p=sel.p / sel.p.sum())
+    np.random.seed(99)
+    u = np.random.random_sample(500)
+    np.testing.assert_array_equal(sel.select(u, np.ones(500), None, None)[0], ref)
+
+
+def test_efficiency_file_and_table():
+    g = load('order_selectors')
+    ef = mo.EfficiencyFile(g['ef_table'], g['ef_orders'])
+    m, p = ef.select(g['ef_u'], g['ef_energy'], None, None)
+    np.testing.assert_array_equal(m, g['ef_m'])
+    np.testing.assert_allclose(p, g['ef_prob'], rtol=1e-15)
+    iet = mo.InterpolateEfficiencyTable(g['iet_wave'], g['iet_theta'], g['iet_prob'], g['iet_orders'])
+    pr = iet.probabilities(g['iet_energy'], g['iet_blaze'])
+    np.testing.assert_allclose(pr, g['iet_probs'], rtol=1e-12, atol=1e-16)
+    m, tot = iet.select(g['iet_u'], g['iet_energy'], None, g['iet_blaze'])
+    np.testing.assert_array_equal(m, g['iet_m'])
+    np.testing.assert_allclose(tot, g['iet_total'], rtol=1e-12)
+
+
+def test_bilinear_equals_scipy_k1():
+    """RectBivariateSpline(kx=ky=1).ev == clamped bilinear."""
+    from scipy.interpolate import RectBivariateSpline
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 10, 12))
+    y = np.sort(rng.uniform(-1, 1, 7))
+    z = rng.normal(size=(12, 7))
+    s = RectBivariateSpline(x, y, z, kx=1, ky=1)
+    xq = rng.uniform(-2, 12, 500)
+    yq = rng.uniform(-1.5, 1.5, 500)
+    np.testing.assert_allclose(mo.interp_bilinear_clamped(x, y, z, xq, yq), s.ev(xq, yq), rtol=1e-12, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------
+# golden vectors generated from the reference itself
+# ---------------------------------------------------------------------------
+def test_golden_intersect():
+    g = load('intersect')
+    for tag, circ in (('', False), ('_circ', True)):
+        d, p = (g['circ_in_dir'], g['circ_in_pos']) if circ else (g['in_dir'], g['in_pos'])
+        hit, ipos, loc = mo.plane_intersect(mo.PlaneConsts(g['pos4d' + tag]), d, p, circ)
+        np.testing.assert_array_equal(hit, g['hit' + tag])
+        assert hit.sum() > 100 and (~hit).sum() > 100
+        np.testing.assert_allclose(ipos, g['interpos' + tag], rtol=RTOL, atol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(loc, g['loc' + tag], rtol=RTOL, atol=1e-12, equal_nan=True)
+
+
+def test_golden_parallel_transport():
+    g = load('parallel_transport')
+    out = mo.parallel_transport(g['dir_old'], g['dir_new'], g['pol_old'])
+    np.testing.assert_allclose(out, g['pol_new'], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize('tag', ['flat', 'cat', 'flat_refl'])
+def test_golden_gratings(tag):
+    g = load('gratings')
+    cls, kw = {'flat': (mo.FlatGrating, dict(d=2e-4, groove_angle=0.2)),
+               'cat': (mo.CATGrating, dict(d=2e-4, groove_angle=-0.1)),
+               'flat_refl': (mo.FlatGrating, dict(d=4e-4, transmission=False))}[tag]
+    sel = mo.OrderSelector(np.arange(-3, 4), p=np.array([.05, .1, .2, .25, .2, .1, .05]))
+    el = cls(pos4d=g[tag + '_pos4d'], order_selector=sel, **kw)
+    mo.assign_slots(el)
+    out = el(table_from(g, tag + '_'), mo.Draws([g[tag + '_u']]))
+    assert np.isfinite(out['order']).mean() > 0.3
+    assert_cols(out, g, tag + '_', exact=('order',))
+
+
+def test_golden_lens_scatter():
+    g = load('lens_scatter')
+    lens = mo.PerfectLens(focallength=250., d_center_optical_axis=7.5, pos4d=g['lens_pos4d'])
+    assert_cols(lens(table_from(g, 'lens_')), g, 'lens_')
+    sc = mo.RadialMirrorScatter(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=g['rms_pos4d'])
+    mo.assign_slots(sc)
+    assert_cols(sc(table_from(g, 'rms_'), mo.Draws([g['rms_z0'], g['rms_z1']])), g, 'rms_')
+    sg = mo.RandomGaussianScatter(scatter=1e-3, pos4d=g['rms_pos4d'])
+    mo.assign_slots(sg)
+    assert_cols(sg(table_from(g, 'rgs_'), mo.Draws([g['rgs_z0'], g['rgs_u1']])), g, 'rgs_')
+    st = mo.FlatStack(pos4d=g['stack_pos4d'],
+                      elements=[mo.PerfectLens, mo.RadialMirrorScatter, mo.EnergyFilter],
+                      keywords=[{'focallength': 300.},
+                                {'inplanescatter': 3e-4, 'perpplanescatter': 1e-4},
+                                {'filterfunc': 0.66}])
+    mo.assign_slots(st)
+    assert_cols(st(table_from(g, 'stack_'), mo.Draws([g['stack_z0'], g['stack_z1']])), g, 'stack_')
+
+
+def test_golden_detector():
+    g = load('detectors')
+    det = mo.FlatDetector(pixsize=0.024, pos4d=g['det_pos4d'])
+    assert det.npix == list(g['det_npix']) and det.centerpix == list(g['det_centerpix'])
+    out = det(table_from(g, 'det_'))
+    assert_cols(out, g, 'det_')
+    ok = np.isfinite(out['detpix_x'])
+    np.testing.assert_array_equal(np.round(out['detpix_x'][ok]), np.round(g['det_out_detpix_x'][ok]))
+
+
+def test_golden_mlmirror():
+    g = load('mlmirror')
+    m = mo.FlatBrewsterMirror(pos4d=g['brew_pos4d'])
+    assert_cols(m(table_from(g, 'brew_')), g, 'brew_', rtol=1e-12)
+    refl = dict(x_mm=g['ml_x_mm'], peak_lambda=g['ml_peak_lambda'], peak=g['ml_peak'], fwhm=g['ml_fwhm'])
+    pol = dict(energy_ev=g['ml_pol_energy_ev'], pol=g['ml_pol'])
+    mm = mo.MultiLayerMirror(refl=refl, pol=pol, pos4d=g['brew_pos4d'])
+    out = mm(table_from(g, 'mlm_'))
+    assert (out['probability'] > 0).sum() > 10
+    assert_cols(out, g, 'mlm_', rtol=1e-11, atol=1e-18)
+
+
+def test_golden_apertures_baffle():
+    g = load('apertures_baffle')
+    t = table_from(g, 'rect_')
+    ap = mo.RectangleAperture(pos4d=g['rect_pos4d'])
+    mo.assign_slots(ap)
+    assert_cols(ap(t, mo.Draws([g['rect_u0'], g['rect_u1']])), g, 'rect_')
+    t = table_from(g, 'multi_')
+    aps = [mo.CircleAperture(position=[100., 0, 0], zoom=[1, r[1], r[1]], r_inner=r[0]) for r in g['multi_radii']]
+    ma = mo.MultiAperture(aps, id_col='mirror_shell')
+    mo.assign_slots(ma)
+    out = ma(t, mo.Draws([g['multi_aperid'], g['multi_u0'], g['multi_u1']]))
+    assert_cols(out, g, 'multi_', exact=('mirror_shell',))
+    assert_cols(mo.Baffle(pos4d=g['baffle_pos4d'])(table_from(g, 'baffle_')), g, 'baffle_')
+    assert_cols(mo.CircularBaffle(pos4d=g['cbaffle_pos4d'])(table_from(g, 'cbaffle_')), g, 'cbaffle_')
+
+
+def test_golden_parallel_overlap():
+    """Sequential-loop semantics of Parallel: last hit wins."""
+    g = load('parallel_overlap')
+    pos = [[0., -4., 0.], [-3., 2., 1.], [2., 4., -3.], [-6., -1., 5.]]
+    par = mo.Parallel(mo.FlatGrating, {'position': pos},
+                      {'d': [2e-4, 3e-4, 2.5e-4, 4e-4], 'zoom': [1, 5., 6.],
+                       'order_selector': mo.OrderSelector([-1, 0, 1]),
+                       'groove_angle': [0., 0.1, -0.2, 0.05]}, id_col='facet')
+    np.testing.assert_allclose(np.array([e.pos4d for e in par.elements]), g['pos4d'], rtol=1e-15, atol=1e-15)
+    mo.assign_slots(par)
+    out = par(table_from(g, ''), mo.Draws([g['u0']]))
+    assert len(set(out['facet'])) == 5          # all four facets and -1 occur
+    assert_cols(out, g, '', exact=('facet', 'order'))
+
+
+def chandra_data():
+    from marxs_b200.missions.chandra import data as cd
+    return cd.load_hess(), cd.load_acis_corners()
+
+
+def test_golden_chandra_c2():
+    """Config 2 slice: HRMA -> HETG(336) -> ACIS-S on the reference's own output."""
+    g = load('chandra_c2')
+    hess, corners = chandra_data()
+    hrma, hetg = mo.chandra_hrma(), mo.chandra_hetg(hess)
+    acis = mo.chandra_acis(corners, [4, 5, 6, 7, 8, 9])
+    np.testing.assert_allclose(np.array([e.pos4d for e in hetg.elements]), g['hetg_pos4d'], rtol=1e-14, atol=1e-12)
+    np.testing.assert_allclose(np.array([e.groove_angle for e in hetg.elements]), g['hetg_groove'], rtol=1e-14)
+    np.testing.assert_allclose(np.array([e.pos4d for e in acis.elements]), g['acis_pos4d'], rtol=1e-14, atol=1e-12)
+    np.testing.assert_array_equal([e.id_num for e in acis.elements], g['acis_id'])
+    inst = mo.Sequence([hrma, hetg, acis])
+    kinds = mo.assign_slots(inst)
+    assert kinds == ['normal', 'normal', 'uniform']
+    t = table_from(g, '')
+    t.meta['ROLL_PNT'] = (0., 'roll')
+    out = inst(t, mo.Draws([g['z0'], g['z1'], g['u2']]))
+    assert (out['facet'] >= 0).mean() > 0.8 and (out['CCD_ID'] >= 0).mean() > 0.5
+    assert_cols(out, g, '', exact=('facet', 'order', 'CCD_ID'), rtol=1e-11, atol=1e-9)
+    ok = out['CCD_ID'] >= 0
+    for c in ('chipx', 'chipy', 'tdetx', 'tdety'):
+        np.testing.assert_array_equal(np.round(out[c][ok]), np.round(g['out_' + c][ok]), err_msg=c)
