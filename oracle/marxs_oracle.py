@@ -236,11 +236,14 @@ def plane_intersect(g, dir, pos, circular=False):
         loc[:, 1] = v[:, 0] * ez[0] + v[:, 1] * ez[1] + v[:, 2] * ez[2]
         hit = (~is_parallel & forward & (np.abs(loc[:, 0]) <= g.L_y)
                & (np.abs(loc[:, 1]) <= g.L_z))
-        if circular:
-            r = np.sqrt(loc[:, 0] * loc[:, 0] + loc[:, 1] * loc[:, 1])
-            hit &= r <= 1.0
     interpos[~hit, :3] = np.nan
     loc[~hit, :] = np.nan
+    if circular:
+        # CircularHole.intersect (:376-380) narrows the mask AFTER the NaN fill:
+        # photons inside the rectangle but outside r <= 1.0 keep finite values.
+        with np.errstate(invalid='ignore'):
+            r = np.sqrt(loc[:, 0] * loc[:, 0] + loc[:, 1] * loc[:, 1])
+            hit = hit & (r <= 1.0)
     return hit, interpos, loc
 
 
