@@ -1,0 +1,136 @@
+"""Flat geometries: ray x plane intersection on the device.
+
+API of the reference's marxs/math/geometry.py (Geometry :98-198, FinitePlane
+:201-281, RectangleHole/CircularHole :335-380); ``intersect`` runs the
+``mxb_plane_intersect`` kernel instead of numpy."""
+import ctypes
+from copy import copy
+
+import numpy as np
+import torch
+
+from . import _lib
+from .base import _parse_position_keywords
+from .program import geom14
+
+__all__ = ['NoGeometry', 'Geometry', 'FinitePlane', 'PlaneWithHole', 'RectangleHole', 'CircularHole']
+
+
+class NoGeometry:
+    _geometry = {}
+    shape = 'none'
+
+    def __init__(self, kwargs={}):
+        self.geometry = self
+
+
+class Geometry(NoGeometry):
+
+    def __init__(self, kwargs={}):
+        self.pos4d = _parse_position_keywords(kwargs)
+        self._geometry = copy(self._geometry)
+        super().__init__(kwargs=kwargs)
+
+    def __getitem__(self, key):
+        """Named access to the pos4d columns: center, v_x/y/z, e_x/y/z (unit)."""
+        if key == 'center':
+            return self.pos4d[:, 3]
+        elif key in ['v_x', 'e_x']:
+            val = self.pos4d[:, 0]
+        elif key in ['v_y', 'e_y']:
+            val = self.pos4d[:, 1]
+        elif key in ['v_z', 'e_z']:
+            val = self.pos4d[:, 2]
+        elif key == 'plane':
+            c, n = self['center'], self['e_x']
+            return np.array([n[0], n[1], n[2], -np.dot(n[:3], c[:3])])
+        else:
+            val = self._geometry[key]
+            if isinstance(val, np.ndarray) and (val.shape[-1] == 4):
+                val = np.dot(self.pos4d, val)
+        if key[:2] == 'e_':
+            return val / np.linalg.norm(val)
+        return val
+
+    def intersect(self, dir, pos):
+        raise NotImplementedError
+
+    def get_local_euklid_bases(self, interpos_local):
+        raise NotImplementedError
+
+
+def _planes(t):
+    """(N, 4) tensor (any strides) -> (3, N) contiguous component planes."""
+    t = t.as_subclass(torch.Tensor)
+    if t.dim() != 2 or t.shape[1] < 3:
+        raise ValueError('expected an (N, 4) array of homogeneous vectors')
+    return t[:, :3].T.contiguous().to(torch.float64)
+
+
+class FinitePlane(Geometry):
+    """Rectangle spanned by +-v_y, +-v_z around center, normal e_x."""
+
+    shape = 'box'
+    loc_coos_name = ['y', 'z']
+    circular = False
+
+    def intersect(self, dir, pos):
+        """-> (intersect bool (N,), interpos (N, 4), interpos_local (N, 2)), NaN on miss."""
+        if not isinstance(dir, torch.Tensor):
+            dev = 'cuda' if torch.cuda.is_available() else None
+            if dev is None:
+                raise _lib.MxbError('Geometry.intersect needs a CUDA device (no CPU fallback)')
+            dir = torch.as_tensor(np.asarray(dir), device=dev)
+            pos = torch.as_tensor(np.asarray(pos), device=dev)
+        if dir.device.type != 'cuda':
+            raise _lib.MxbError('Geometry.intersect needs CUDA tensors (no CPU fallback)')
+        lib = _lib.load()
+        n = dir.shape[0]
+        d, p = _planes(dir), _planes(pos)
+        hit = torch.empty(n, dtype=torch.uint8, device=dir.device)
+        ipos = torch.empty((4, n), dtype=torch.float64, device=dir.device)
+        ipos[3] = pos.as_subclass(torch.Tensor)[:, 3]
+        loc = torch.empty((2, n), dtype=torch.float64, device=dir.device)
+        g = np.ascontiguousarray(geom14(self.pos4d))
+        vp3 = ctypes.c_void_p * 3
+        vp2 = ctypes.c_void_p * 2
+        dd = vp3(*[d.data_ptr() + k * n * 8 for k in range(3)])
+        pp = vp3(*[p.data_ptr() + k * n * 8 for k in range(3)])
+        ii = vp3(*[ipos.data_ptr() + k * n * 8 for k in range(3)])
+        ll = vp2(*[loc.data_ptr() + k * n * 8 for k in range(2)])
+        with torch.cuda.device(dir.device):
+            rc = lib.mxb_plane_intersect(g.ctypes.data, 1 if self.circular else 0, dd, pp, hit.data_ptr(),
+                                         ii, ll, n, torch.cuda.current_stream(dir.device).cuda_stream)
+        _lib.check(lib, rc, 'mxb_plane_intersect')
+        return hit.bool(), ipos.T, loc.T
+
+    def get_local_euklid_bases(self, interpos_local):
+        n = interpos_local.shape[0]
+        return (np.tile(self['e_y'], (n, 1)), np.tile(self['e_z'], (n, 1)), np.tile(self['e_x'], (n, 1)))
+
+
+class PlaneWithHole(FinitePlane):
+    shape = 'triangulation'
+
+    def __init__(self, kwargs):
+        self._geometry['r_inner'] = kwargs.pop('r_inner', 0.)
+        super().__init__(kwargs)
+
+
+class RectangleHole(PlaneWithHole):
+    pass
+
+
+class CircularHole(PlaneWithHole):
+    circular = True
+
+    def __init__(self, kwargs):
+        phi = kwargs.pop('phi', [0, 2. * np.pi])
+        if np.max(np.abs(phi)) > 10:
+            raise ValueError('Input angles >> 2 pi. Did you use degrees (radian expected)?')
+        if phi[0] > phi[1]:
+            raise ValueError('phi[1] must be greater than phi[0].')
+        if (phi[1] - phi[0]) > (2 * np.pi + 1e-6):
+            raise ValueError('phi[1] - phi[0] must be less than 2 pi.')
+        self.phi = phi
+        super().__init__(kwargs)

@@ -1,0 +1,500 @@
+"""GPU parity: the CUDA path (through the C ABI) against the numpy oracle on the
+same seeded inputs and injected draws, and against the golden vectors produced
+by the reference itself.  Run with ``pytest -m gpu`` on a B200.
+
+Bars (BASELINE.json north_star):
+  * facet / order / CCD / pixel indices: bit-exact;
+  * pos, dir, polarization, probability: 1e-12 relative (fp64);
+  * in the strict build (``libmxb_strict.so``, -fmad=false) every value that does
+    not pass through a libm call (sin/cos/acos/exp) is bit-identical to the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import marxs_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+SEED = 20261017
+
+
+def _mb():
+    import marxs_b200
+    return marxs_b200
+
+
+@pytest.fixture(params=['fast', 'strict'])
+def mode(request):
+    from marxs_b200 import _lib
+    _lib.set_strict(request.param == 'strict')
+    yield request.param
+    _lib.set_strict(False)
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False))
+
+
+def rand_pos4d(rng, zoom=(1., 8., 5.), shift=4.):
+    a, b, c = rng.uniform(-0.4, 0.4, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return mo.compose(rng.uniform(-shift, shift, 3), Rz @ Ry @ Rx, zoom)
+
+
+def make_photons(rng, n, spread=0.05, x0=60., lateral=8., e_lo=0.3, e_hi=8.):
+    pos = np.ones((n, 4))
+    pos[:, 0] = x0 + rng.uniform(-5, 5, n)
+    pos[:, 1:3] = rng.uniform(-lateral, lateral, (n, 2))
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    d[:, 1:3] = rng.normal(0, spread, (n, 2))
+    d[:, :3] *= rng.uniform(0.5, 2., n)[:, None]
+    v = rng.normal(size=(n, 3))
+    u = d[:, :3] / np.linalg.norm(d[:, :3], axis=1)[:, None]
+    v -= u * np.einsum('ij,ij->i', v, u)[:, None]
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    pol = np.zeros((n, 4))
+    pol[:, :3] = v
+    return mo.PhotonTable(pos=pos, dir=d, energy=rng.uniform(e_lo, e_hi, n), polarization=pol,
+                          probability=rng.uniform(0.2, 1., n))
+
+
+INDEX_COLS = ('facet', 'order', 'CCD_ID', 'mirror_shell', 'aperture', 'element')
+PIXEL_COLS = ('detpix_x', 'detpix_y', 'chipx', 'chipy', 'tdetx', 'tdety')
+SCALE = {'pos': 1e4, 'x': 1e4, 'y': 1e4, 'detx': 1e4, 'dety': 1e4, 'tdetx': 1e4, 'tdety': 1e4,
+         'chipx': 1e3, 'chipy': 1e3, 'detpix_x': 1e3, 'detpix_y': 1e3}
+
+
+def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=()):
+    """got_batch: PhotonBatch, want: oracle PhotonTable."""
+    got = got_batch.to_numpy()
+    assert set(want.colnames) - set(skip) <= set(got.keys()), (want.colnames, list(got.keys()))
+    assert set(got.keys()) <= set(want.colnames), 'extra columns: {0}'.format(set(got) - set(want.colnames))
+    for c in want.colnames:
+        if c in skip:
+            continue
+        w, g = np.asarray(want[c]), got[c]
+        assert g.shape == w.shape, c
+        if c in INDEX_COLS:
+            np.testing.assert_array_equal(np.nan_to_num(g.astype(float), nan=-99),
+                                          np.nan_to_num(w.astype(float), nan=-99), err_msg=c)
+            continue
+        np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg='NaN pattern of ' + c)
+        if c in PIXEL_COLS:
+            ok = np.isfinite(w)
+            np.testing.assert_array_equal(np.round(g[ok]), np.round(w[ok]), err_msg='pixel index ' + c)
+        if exact_float:
+            ok = ~np.isnan(w)
+            assert np.array_equal(g[ok], w[ok]), '{0}: {1} values differ, max |d| {2}'.format(
+                c, (g[ok] != w[ok]).sum(), np.abs(g[ok] - w[ok]).max())
+        else:
+            np.testing.assert_allclose(g, w, rtol=rtol, atol=rtol * SCALE.get(c, 1.), equal_nan=True, err_msg=c)
+
+
+def run_pair(prod, orac, table, draws=None, **cmp):
+    mb = _mb()
+    kinds = mo.assign_slots(orac)
+    want = orac(table.copy(), mo.Draws(draws) if draws is not None else None)
+    batch = mb.PhotonBatch(table, device='cuda')
+    if draws is not None:
+        assert len(draws) == len(kinds)
+        with mb.inject_draws(draws):
+            got = prod(batch)
+    else:
+        got = prod(batch)
+    compare(got, want, **cmp)
+    return got, want
+
+
+# ---------------------------------------------------------------------------
+def test_library_loaded_is_native():
+    from marxs_b200 import _lib
+    lib = _lib.load(False)
+    assert lib.mxb_version() == _lib.MXB_ABI_VERSION
+    assert b'sm_100a' in lib.mxb_build_info()
+    assert lib.mxb_device_count() >= 1
+    assert b'strict' in _lib.load(True).mxb_build_info()
+
+
+def test_intersect_golden(mode):
+    from marxs_b200.geometry import FinitePlane, CircularHole
+    g = load('intersect')
+    for tag, cls in (('', FinitePlane), ('_circ', CircularHole)):
+        d, p = (g['circ_in_dir'], g['circ_in_pos']) if tag else (g['in_dir'], g['in_pos'])
+        geo = cls({'pos4d': g['pos4d' + tag]})
+        hit, ipos, loc = geo.intersect(torch.tensor(d, device='cuda'), torch.tensor(p, device='cuda'))
+        np.testing.assert_array_equal(hit.cpu().numpy(), g['hit' + tag])
+        np.testing.assert_allclose(ipos.cpu().numpy(), g['interpos' + tag], rtol=2e-13, atol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(loc.cpu().numpy(), g['loc' + tag], rtol=2e-13, atol=1e-12, equal_nan=True)
+        # and bit-exact against the oracle in the strict build
+        h2, i2, l2 = mo.plane_intersect(mo.PlaneConsts(g['pos4d' + tag]), d, p, bool(tag))
+        if mode == 'strict':
+            assert np.array_equal(ipos.cpu().numpy(), i2, equal_nan=True)
+            assert np.array_equal(loc.cpu().numpy(), l2, equal_nan=True)
+
+
+def test_parallel_transport_golden(mode):
+    from marxs_b200.polarization import parallel_transport
+    g = load('parallel_transport')
+    out = parallel_transport(*[torch.tensor(g[k], device='cuda') for k in ('dir_old', 'dir_new', 'pol_old')])
+    np.testing.assert_allclose(out.cpu().numpy(), g['pol_new'], rtol=1e-12, atol=1e-14)
+    if mode == 'strict':
+        assert np.array_equal(out.cpu().numpy(), mo.parallel_transport(g['dir_old'], g['dir_new'], g['pol_old']))
+
+
+@pytest.mark.parametrize('kind', ['flat', 'cat', 'refl', 'nonparallel'])
+def test_grating_vs_oracle(mode, kind):
+    from marxs_b200 import optics
+    from marxs_b200.missions.mitsnl import NonParallelCATGrating
+    rng = np.random.default_rng(SEED + 1)
+    n = 20000
+    pos4d = rand_pos4d(rng, zoom=(1., 9., 7.))
+    p = np.array([.05, .1, .2, .25, .2, .1, .05])
+    kw = dict(d=2e-4, groove_angle=0.2, pos4d=pos4d, id_col='facet', id_num=3)
+    pc, oc = {'flat': (optics.FlatGrating, mo.FlatGrating), 'cat': (optics.CATGrating, mo.CATGrating),
+              'refl': (optics.FlatGrating, mo.FlatGrating),
+              'nonparallel': (NonParallelCATGrating, mo.NonParallelCATGrating)}[kind]
+    if kind == 'refl':
+        kw['transmission'] = False
+    if kind == 'nonparallel':
+        kw.update(d_blaze_mm=1e-3, blaze_center=0.01)
+    prod = pc(order_selector=optics.OrderSelector(np.arange(-3, 4), p), **kw)
+    orac = oc(order_selector=mo.OrderSelector(np.arange(-3, 4), p), **kw)
+    table = make_photons(rng, n, e_lo=0.3, e_hi=3.)
+    got, want = run_pair(prod, orac, table, [rng.random(n)], exact_float=(mode == 'strict'), skip=('blaze',))
+    np.testing.assert_allclose(got.to_numpy()['blaze'], want['blaze'], rtol=1e-12, atol=1e-15, equal_nan=True)
+    assert 0.2 < np.isfinite(want['order']).mean() < 0.99
+
+
+def test_grating_golden(mode):
+    from marxs_b200 import optics
+    g = load('gratings')
+    sel = optics.OrderSelector(np.arange(-3, 4), p=np.array([.05, .1, .2, .25, .2, .1, .05]))
+    for tag, cls, kw in (('flat', optics.FlatGrating, dict(d=2e-4, groove_angle=0.2)),
+                         ('cat', optics.CATGrating, dict(d=2e-4, groove_angle=-0.1)),
+                         ('flat_refl', optics.FlatGrating, dict(d=4e-4, transmission=False))):
+        mb = _mb()
+        t = mo.PhotonTable((k, g[tag + '_in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+        el = cls(pos4d=g[tag + '_pos4d'], order_selector=sel, **kw)
+        with mb.inject_draws([g[tag + '_u']]):
+            out = el(mb.PhotonBatch(t, device='cuda')).to_numpy()
+        for c in ('pos', 'dir', 'polarization', 'probability', 'order', 'blaze', 'grat_y', 'grat_z'):
+            ref = g[tag + '_out_' + c]
+            if c == 'order':
+                np.testing.assert_array_equal(np.nan_to_num(out[c], nan=-99), np.nan_to_num(ref, nan=-99))
+            else:
+                np.testing.assert_allclose(out[c], ref, rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=tag + c)
+
+
+def test_selectors_vs_oracle(mode):
+    """EfficiencyFile and InterpolateEfficiencyTable order selection on the device."""
+    from marxs_b200 import optics
+    from marxs_b200.missions.mitsnl import InterpolateEfficiencyTable
+    rng = np.random.default_rng(SEED + 2)
+    n = 20000
+    pos4d = rand_pos4d(rng, zoom=(1., 9., 7.))
+    en = np.array([0.3, 0.5, 1.0, 2.0, 4.0, 8.0])
+    tab = np.hstack([en[:, None], rng.uniform(0.01, 0.18, (6, 5))])
+    table = make_photons(rng, n, e_lo=0.2, e_hi=9.)
+    prod = optics.FlatGrating(d=3e-4, pos4d=pos4d, order_selector=optics.EfficiencyFile(tab, [-2, -1, 0, 1, 2]))
+    orac = mo.FlatGrating(d=3e-4, pos4d=pos4d, order_selector=mo.EfficiencyFile(tab, [-2, -1, 0, 1, 2]))
+    run_pair(prod, orac, table, [rng.random(n)], exact_float=(mode == 'strict'), skip=('blaze',))
+    wave = np.array([0.1, 0.2, 0.35, 0.6, 1.0, 1.7, 2.5, 4.0])
+    theta = np.deg2rad(np.array([0.5, 1.0, 1.5, 2.0, 3.0, 6.0]))
+    orders = np.array([2, 1, 0, -1, -2, -3, -4])
+    prob = rng.uniform(0.0, 0.12, (len(wave), len(theta), len(orders)))
+    kw = dict(d=2e-4, pos4d=pos4d)
+    prod = optics.CATGrating(order_selector=InterpolateEfficiencyTable(wave, theta, prob, orders), **kw)
+    orac = mo.CATGrating(order_selector=mo.InterpolateEfficiencyTable(wave, theta, prob, orders), **kw)
+    table = make_photons(rng, n, e_lo=0.25, e_hi=14.)
+    got, want = run_pair(prod, orac, table, [rng.random(n)], skip=('blaze',))
+    assert len(set(want['order'][np.isfinite(want['order'])])) >= 5
+
+
+def test_lens_scatter_stack_vs_oracle(mode):
+    from marxs_b200 import optics
+    rng = np.random.default_rng(SEED + 3)
+    n = 20000
+    pos4d = rand_pos4d(rng, zoom=(1., 65., 65.), shift=1.)
+    table = make_photons(rng, n, spread=0.003, x0=400., lateral=60.)
+    lens_p = optics.PerfectLens(focallength=250., d_center_optical_axis=7.5, pos4d=pos4d)
+    lens_o = mo.PerfectLens(focallength=250., d_center_optical_axis=7.5, pos4d=pos4d)
+    run_pair(lens_p, lens_o, table, exact_float=(mode == 'strict'))
+    kw = dict(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=pos4d)
+    run_pair(optics.RadialMirrorScatter(**kw), mo.RadialMirrorScatter(**kw), table,
+             [rng.standard_normal(n), rng.standard_normal(n)])
+    kw = dict(inplanescatter=2e-3, pos4d=pos4d)       # perp scatter off: column of zeros
+    run_pair(optics.RadialMirrorScatter(**kw), mo.RadialMirrorScatter(**kw), table,
+             [rng.standard_normal(n), rng.standard_normal(n)])
+    run_pair(optics.RandomGaussianScatter(scatter=1e-3, pos4d=pos4d), mo.RandomGaussianScatter(scatter=1e-3, pos4d=pos4d),
+             table, [rng.standard_normal(n), rng.random(n)])
+    layers_p = [optics.PerfectLens, optics.RadialMirrorScatter, optics.EnergyFilter]
+    layers_o = [mo.PerfectLens, mo.RadialMirrorScatter, mo.EnergyFilter]
+    x = np.array([0.1, 0.5, 1., 2., 5., 9.])
+    y = np.array([.1, .5, .9, .9, .5, .2])
+    kws = lambda f: [{'focallength': 300.}, {'inplanescatter': 3e-4, 'perpplanescatter': 1e-4}, {'filterfunc': f}]
+    run_pair(optics.FlatStack(pos4d=pos4d, elements=layers_p, keywords=kws(optics.Tabulated1D(x, y))),
+             mo.FlatStack(pos4d=pos4d, elements=layers_o, keywords=kws(mo.Tabulated1D(x, y))),
+             table, [rng.standard_normal(n), rng.standard_normal(n)])
+
+
+def test_lens_scatter_golden(mode):
+    from marxs_b200 import optics
+    mb = _mb()
+    g = load('lens_scatter')
+
+    def check(prefix, el, draws=None):
+        t = mo.PhotonTable((k, g[prefix + 'in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+        b = mb.PhotonBatch(t, device='cuda')
+        if draws:
+            with mb.inject_draws(draws):
+                out = el(b).to_numpy()
+        else:
+            out = el(b).to_numpy()
+        names = [k[len(prefix) + 4:] for k in g if k.startswith(prefix + 'out_')]
+        assert set(names) == set(out.keys())
+        for c in names:
+            np.testing.assert_allclose(out[c], g[prefix + 'out_' + c], rtol=1e-12, atol=1e-11, equal_nan=True, err_msg=prefix + c)
+
+    check('lens_', optics.PerfectLens(focallength=250., d_center_optical_axis=7.5, pos4d=g['lens_pos4d']))
+    check('rms_', optics.RadialMirrorScatter(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=g['rms_pos4d']),
+          [g['rms_z0'], g['rms_z1']])
+    check('rgs_', optics.RandomGaussianScatter(scatter=1e-3, pos4d=g['rms_pos4d']), [g['rgs_z0'], g['rgs_u1']])
+    check('stack_', optics.FlatStack(pos4d=g['stack_pos4d'],
+                                     elements=[optics.PerfectLens, optics.RadialMirrorScatter, optics.EnergyFilter],
+                                     keywords=[{'focallength': 300.},
+                                               {'inplanescatter': 3e-4, 'perpplanescatter': 1e-4},
+                                               {'filterfunc': 0.66}]), [g['stack_z0'], g['stack_z1']])
+
+
+def test_detector_baffle_vs_oracle(mode):
+    from marxs_b200 import optics
+    rng = np.random.default_rng(SEED + 4)
+    n = 20000
+    pos4d = rand_pos4d(rng, zoom=(1., 12.288, 6.144))
+    table = make_photons(rng, n, spread=0.1)
+    run_pair(optics.FlatDetector(pixsize=0.024, pos4d=pos4d), mo.FlatDetector(pixsize=0.024, pos4d=pos4d),
+             table, exact_float=(mode == 'strict'))
+    run_pair(optics.Baffle(pos4d=pos4d), mo.Baffle(pos4d=pos4d), table, exact_float=(mode == 'strict'))
+    pos4d = rand_pos4d(rng, zoom=(1., 6., 0.9), shift=.4)
+    table = make_photons(rng, n, spread=0.01, lateral=1.6, x0=30.)
+    run_pair(optics.CircularBaffle(pos4d=pos4d), mo.CircularBaffle(pos4d=pos4d), table, exact_float=(mode == 'strict'))
+
+
+def test_mlmirror_vs_oracle_and_golden(mode):
+    from marxs_b200 import optics
+    mb = _mb()
+    g = load('mlmirror')
+    refl_o = dict(x_mm=g['ml_x_mm'], peak_lambda=g['ml_peak_lambda'], peak=g['ml_peak'], fwhm=g['ml_fwhm'])
+    pol_o = dict(energy_ev=g['ml_pol_energy_ev'], pol=g['ml_pol'])
+    refl_p = {'X(mm)': g['ml_x_mm'], 'Peak lambda': g['ml_peak_lambda'], 'Peak': g['ml_peak'], 'FWHM(nm)': g['ml_fwhm']}
+    pol_p = {'Photon energy': g['ml_pol_energy_ev'], 'Polarization': g['ml_pol']}
+    pos4d = g['brew_pos4d']
+    rng = np.random.default_rng(SEED + 5)
+    table = make_photons(rng, 20000, spread=0.02, x0=60., lateral=5., e_lo=0.25, e_hi=0.45)
+    run_pair(optics.FlatBrewsterMirror(pos4d=pos4d), mo.FlatBrewsterMirror(pos4d=pos4d), table,
+             exact_float=(mode == 'strict'))
+    run_pair(optics.MultiLayerMirror(reflFile=refl_p, testedPolarization=pol_p, pos4d=pos4d),
+             mo.MultiLayerMirror(refl=refl_o, pol=pol_o, pos4d=pos4d), table, rtol=1e-11)
+    t = mo.PhotonTable((k, g['mlm_in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+    out = optics.MultiLayerMirror(reflFile=refl_p, testedPolarization=pol_p, pos4d=pos4d)(
+        mb.PhotonBatch(t, device='cuda')).to_numpy()
+    for c in ('pos', 'dir', 'polarization', 'probability', 'y', 'z'):
+        np.testing.assert_allclose(out[c], g['mlm_out_' + c], rtol=1e-11, atol=1e-12, equal_nan=True, err_msg=c)
+
+
+def test_apertures_vs_oracle(mode):
+    from marxs_b200 import optics
+    mb = _mb()
+    rng = np.random.default_rng(SEED + 6)
+    n = 20000
+
+    def src():
+        d = np.zeros((n, 4))
+        d[:, 0] = -1.
+        d[:, 1:3] = rng.normal(0, 0.01, (n, 2))
+        pol = np.zeros((n, 4))
+        pol[:, 1] = 1.
+        return mo.PhotonTable(dir=d, energy=rng.uniform(0.5, 2, n), polarization=pol, probability=np.ones(n))
+    pos4d = rand_pos4d(rng, zoom=(1., 4., 2.), shift=5.)
+    run_pair(optics.RectangleAperture(pos4d=pos4d), mo.RectangleAperture(pos4d=pos4d), src(),
+             [rng.random(n), rng.random(n)], exact_float=(mode == 'strict'))
+    radii = np.array([[59.8, 61.0], [48.1, 49.1], [42.4, 43.3]])
+    ap_p = optics.MultiAperture(elements=[optics.CircleAperture(position=[100., 0, 0], zoom=[1, r[1], r[1]], r_inner=r[0])
+                                          for r in radii], id_col='mirror_shell')
+    ap_o = mo.MultiAperture([mo.CircleAperture(position=[100., 0, 0], zoom=[1, r[1], r[1]], r_inner=r[0])
+                             for r in radii], id_col='mirror_shell')
+    aperid = rng.integers(0, 3, n).astype(float)
+    run_pair(ap_p, ap_o, src(), [aperid, rng.random(n), rng.random(n)])
+    # device RNG: area-weighted choice of the opening and uniform filling (distributional)
+    b = mb.PhotonBatch(src(), device='cuda')
+    mb.set_seed(7)
+    out = ap_p(b).to_numpy()
+    frac = np.bincount(out['mirror_shell'], minlength=3) / n
+    area = radii[:, 1] ** 2 - radii[:, 0] ** 2
+    np.testing.assert_allclose(frac, area / area.sum(), atol=0.015)
+    r = np.hypot(out['pos'][:, 1], out['pos'][:, 2])
+    for i in range(3):
+        ri = r[out['mirror_shell'] == i]
+        assert ri.min() >= radii[i, 0] - 1e-9 and ri.max() <= radii[i, 1] + 1e-9
+
+
+def test_parallel_overlap_sequential_semantics(mode):
+    """Overlapping facets: every facet sees the photon's CURRENT state, last hit wins."""
+    from marxs_b200 import optics, simulator
+    mb = _mb()
+    g = load('parallel_overlap')
+    pos = [[0., -4., 0.], [-3., 2., 1.], [2., 4., -3.], [-6., -1., 5.]]
+    args = {'d': [2e-4, 3e-4, 2.5e-4, 4e-4], 'zoom': [1, 5., 6.], 'groove_angle': [0., 0.1, -0.2, 0.05]}
+    par = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos={'position': pos}, id_col='facet',
+                             elem_args=dict(order_selector=optics.OrderSelector([-1, 0, 1]), **args))
+    t = mo.PhotonTable((k, g['in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+    with mb.inject_draws([g['u0']]):
+        out = par(mb.PhotonBatch(t, device='cuda')).to_numpy()
+    np.testing.assert_array_equal(out['facet'], g['out_facet'])
+    np.testing.assert_array_equal(np.nan_to_num(out['order'], nan=-99), np.nan_to_num(g['out_order'], nan=-99))
+    for c in ('pos', 'dir', 'polarization', 'probability', 'grat_y', 'grat_z', 'blaze'):
+        np.testing.assert_allclose(out[c], g['out_' + c], rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=c)
+    # a larger overlapping array that uses the culling grid, against the oracle's serial loop
+    rng = np.random.default_rng(SEED + 7)
+    F = 40
+    pos = np.column_stack([rng.uniform(-3, 3, F), rng.uniform(-40, 40, F), rng.uniform(-40, 40, F)]).tolist()
+    kw = {'d': 2e-4, 'zoom': [1, 6., 6.], 'groove_angle': 0.05}
+    pp = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos={'position': pos}, id_col='facet',
+                            elem_args=dict(order_selector=optics.OrderSelector([-2, -1, 0, 1, 2]), **kw))
+    po = mo.Parallel(mo.FlatGrating, {'position': pos},
+                     dict(order_selector=mo.OrderSelector([-2, -1, 0, 1, 2]), **kw), id_col='facet')
+    n = 30000
+    table = make_photons(rng, n, spread=0.03, lateral=45., x0=50., e_lo=0.3, e_hi=1.)
+    got, want = run_pair(pp, po, table, [rng.random(n)], skip=('blaze',))
+    assert (want['facet'] >= 0).mean() > 0.3
+
+
+def chandra_photons(rng, n):
+    radii = mo.HRMA_RADII
+    area = radii[:, 1] ** 2 - radii[:, 0] ** 2
+    shell = rng.choice(4, size=n, p=area / area.sum())
+    r = np.sqrt(rng.uniform(radii[shell, 0] ** 2, radii[shell, 1] ** 2))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    pos = np.ones((n, 4))
+    pos[:, 0] = 10061.65 + 100.
+    pos[:, 1] = r * np.cos(phi)
+    pos[:, 2] = r * np.sin(phi)
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    ang = rng.uniform(0, 2 * np.pi, n)
+    pol = np.zeros((n, 4))
+    pol[:, 1] = np.cos(ang)
+    pol[:, 2] = np.sin(ang)
+    t = mo.PhotonTable(pos=pos, dir=d, energy=rng.uniform(0.5, 8., n), polarization=pol, probability=np.ones(n))
+    t.meta['ROLL_PNT'] = (0., 'roll')
+    return t
+
+
+def chandra_pair():
+    from marxs_b200 import simulator
+    from marxs_b200.missions import chandra
+    from marxs_b200.missions.chandra import data as cd
+    prod = simulator.Sequence(elements=[chandra.HRMA(), chandra.HETG(),
+                                        chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])])
+    orac = mo.Sequence([mo.chandra_hrma(), mo.chandra_hetg(cd.load_hess()),
+                        mo.chandra_acis(cd.load_acis_corners(), [4, 5, 6, 7, 8, 9])])
+    return prod, orac
+
+
+def test_chandra_c2_golden(mode):
+    """BASELINE config 2 slice against the reference's own output (4000 photons)."""
+    mb = _mb()
+    g = load('chandra_c2')
+    prod, _ = chandra_pair()
+    t = mo.PhotonTable((k, g['in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+    t.meta['ROLL_PNT'] = (0., 'roll')
+    with mb.inject_draws([g['z0'], g['z1'], g['u2']]):
+        out = prod(mb.PhotonBatch(t, device='cuda')).to_numpy()
+    names = [k[4:] for k in g if k.startswith('out_')]
+    assert set(names) == set(out.keys())
+    for c in names:
+        ref = g['out_' + c]
+        if c in INDEX_COLS:
+            np.testing.assert_array_equal(np.nan_to_num(out[c].astype(float), nan=-99), np.nan_to_num(ref.astype(float), nan=-99), err_msg=c)
+        else:
+            np.testing.assert_allclose(out[c], ref, rtol=1e-11, atol=1e-9, equal_nan=True, err_msg=c)
+        if c in PIXEL_COLS:
+            ok = np.isfinite(ref)
+            np.testing.assert_array_equal(np.round(out[c][ok]), np.round(ref[ok]), err_msg=c)
+
+
+def test_chandra_c2_vs_oracle(mode):
+    """HRMA -> HETG (336 facets, culling grid) -> ACIS-S against the oracle's serial loops."""
+    rng = np.random.default_rng(SEED + 8)
+    n = 40000
+    prod, orac = chandra_pair()
+    table = chandra_photons(rng, n)
+    draws = [rng.standard_normal(n), rng.standard_normal(n), rng.random(n)]
+    got, want = run_pair(prod, orac, table, draws, rtol=1e-11)
+    assert 0.8 < (want['facet'] >= 0).mean() < 0.9
+    assert (want['CCD_ID'] >= 0).mean() > 0.5
+
+
+def test_chandra_full_size_properties():
+    """Config-2 size (1e7 photons) through size-independent properties: device RNG,
+    results independent of how the batch is split, physical invariants."""
+    mb = _mb()
+    from marxs_b200 import _lib
+    n = 10_000_000
+    prod, _ = chandra_pair()
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    radii = torch.tensor(mo.HRMA_RADII, device='cuda')
+    shell = torch.randint(0, 4, (n,), device='cuda', generator=gen)
+    u = torch.rand(n, device='cuda', generator=gen, dtype=torch.float64)
+    r = torch.sqrt(radii[shell, 0] ** 2 + u * (radii[shell, 1] ** 2 - radii[shell, 0] ** 2))
+    phi = torch.rand(n, device='cuda', generator=gen, dtype=torch.float64) * 2 * np.pi
+    b = mb.PhotonBatch(device='cuda')
+    pos = torch.ones((n, 4), device='cuda', dtype=torch.float64)
+    pos[:, 0] = 10161.65
+    pos[:, 1] = r * torch.cos(phi)
+    pos[:, 2] = r * torch.sin(phi)
+    d = torch.zeros((n, 4), device='cuda', dtype=torch.float64)
+    d[:, 0] = -1
+    pol = torch.zeros((n, 4), device='cuda', dtype=torch.float64)
+    pol[:, 1] = 1
+    b['pos'], b['dir'], b['polarization'] = pos, d, pol
+    b['energy'] = torch.rand(n, device='cuda', generator=gen, dtype=torch.float64) * 7.5 + 0.5
+    b['probability'] = torch.ones(n, device='cuda', dtype=torch.float64)
+    b.meta['ROLL_PNT'] = (0., 'roll')
+    del pos, d, pol
+    mb.set_seed(11)
+    whole = prod(b.copy())
+    # same photons in two halves with global photon ids -> identical results
+    mb.set_seed(11)
+    h1 = b[torch.arange(0, n // 2, device='cuda')]
+    h1 = prod(h1)
+    mb.set_seed(11)
+    h2 = b[torch.arange(n // 2, n, device='cuda')]
+    h2.id0 = n // 2
+    h2 = prod(h2)
+    for c in ('facet', 'CCD_ID', 'order', 'chipx', 'probability'):
+        w = whole[c]
+        assert torch.equal(torch.nan_to_num(w[:n // 2].double(), nan=-9), torch.nan_to_num(h1[c].double(), nan=-9)), c
+        assert torch.equal(torch.nan_to_num(w[n // 2:].double(), nan=-9), torch.nan_to_num(h2[c].double(), nan=-9)), c
+    facet_frac = float((whole['facet'] >= 0).double().mean())
+    assert 0.84 < facet_frac < 0.87          # SURVEY probe: 85.6 % hit a facet
+    hitccd = whole['CCD_ID'] >= 0
+    assert float(hitccd.double().mean()) > 0.5
+    dirs = whole['dir'][hitccd][:, :3]
+    pols = whole['polarization'][hitccd][:, :3]
+    ok = torch.isfinite(dirs).all(dim=1)
+    assert float((dirs[ok].norm(dim=1) - 1).abs().max()) < 1e-12          # unit directions
+    assert float((pols[ok].norm(dim=1) - 1).abs().max()) < 1e-9           # |pol| = 1
+    assert float((dirs[ok] * pols[ok]).sum(dim=1).abs().max()) < 1e-9     # pol perpendicular to dir
+    assert float(whole['probability'].max()) <= 1.0                        # probability never increases
+    orders = whole['order'][whole['facet'] >= 0]
+    counts = torch.stack([(orders == m).sum() for m in range(-3, 4)]).double()
+    assert float((counts / counts.sum() - 1 / 7).abs().max()) < 2e-3      # equal-probability orders
+    st = None
