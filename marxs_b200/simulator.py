@@ -207,6 +207,11 @@ class Parallel(BaseContainer):
                 f_pos4d = np.dot(m, f_pos4d)
             self.elements.append(self.elem_class(pos4d=f_pos4d, id_num=self.id_num_offset + i, **spec))
 
+    def __call__(self, photons):
+        if self.preprocess_steps or self.postprocess_steps:
+            return BaseContainer.__call__(self, photons)
+        return run_fused([self], photons)
+
     def _lower(self, lw):
         if not self.elements:
             return

@@ -93,6 +93,13 @@ def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=()):
             ok = ~np.isnan(w)
             assert np.array_equal(g[ok], w[ok]), '{0}: {1} values differ, max |d| {2}'.format(
                 c, (g[ok] != w[ok]).sum(), np.abs(g[ok] - w[ok]).max())
+        elif c == 'blaze':
+            # arccos(|pp.n|) near 1 is ill-conditioned: one ulp of the argument moves the angle by
+            # 1.1e-16 / sin(blaze); the strict build reproduces the argument bit for bit
+            ok = np.isfinite(w)
+            tol = rtol * np.abs(w[ok]) + 2e-15 / np.maximum(w[ok], 1e-7)   # ~10 ulp of the cosine
+            assert np.all(np.abs(g[ok] - w[ok]) <= tol), 'blaze: max excess {0}'.format(
+                (np.abs(g[ok] - w[ok]) - tol).max())
         else:
             np.testing.assert_allclose(g, w, rtol=rtol, atol=rtol * SCALE.get(c, 1.), equal_nan=True, err_msg=c)
 
@@ -492,7 +499,7 @@ def test_chandra_full_size_properties():
     ok = torch.isfinite(dirs).all(dim=1)
     assert float((dirs[ok].norm(dim=1) - 1).abs().max()) < 1e-12          # unit directions
     assert float((pols[ok].norm(dim=1) - 1).abs().max()) < 1e-9           # |pol| = 1
-    assert float((dirs[ok] * pols[ok]).sum(dim=1).abs().max()) < 1e-9     # pol perpendicular to dir
+    assert float((dirs[ok] * pols[ok]).sum(dim=1).abs().max()) < 3e-8     # pol perpendicular to dir (identity cut-off |d1 x d2| <= 1e-8 of the reference)
     assert float(whole['probability'].max()) <= 1.0                        # probability never increases
     orders = whole['order'][whole['facet'] >= 0]
     counts = torch.stack([(orders == m).sum() for m in range(-3, 4)]).double()
