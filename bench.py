@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Headline benchmark: photons/s through the full Chandra trace (BASELINE.json config 2).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --steps K --warmup W     # CPU reference arm (oracle port)
+
+One *step* = one pass of the fused trace (HRMA FlatStack -> HETG 336-facet array ->
+ACIS-S 6 chips, all 21 diagnostic columns of the reference materialised) over one
+batch of 1e7 synthetic photons per GPU, plus the detector-image accumulation that
+feeds the multi-GPU epilogue.  Inputs are resident in HBM when the timed region
+starts; every step reads a fresh input copy (the trace is in place), and one copy
+(0.88 GB read) is much larger than the 126 MB L2.  ``e2e`` is the same trace through
+``mxb_trace_host`` with pinned HOST buffers, H2D and D2H inside the timed region.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'photons/sec through full instrument trace'
+N_PER_GPU = 10_000_000
+WORKLOAD = 'C2: Chandra HRMA + HETG (336 facets) + ACIS-S (6 chips), 1e7 photons per GPU per step'
+# 15 fp64 read + 15 fp64 written per photon per fused stage + 8 B per diagnostic column
+DIAG_COLS = 21
+ALGO_BYTES_PER_PHOTON = 240 + 8 * DIAG_COLS
+CPU_PHOTONS_PER_WORKER = 20000
+
+
+# ---------------------------------------------------------------------------
+# synthetic C2 input: on-axis photons on the four HRMA annuli
+# ---------------------------------------------------------------------------
+HRMA_RADII = np.array([[598., 610.], [481, 491], [424, 433], [315, 322]])
+
+
+def synth_c2_numpy(n, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    area = HRMA_RADII[:, 1] ** 2 - HRMA_RADII[:, 0] ** 2
+    shell = rng.choice(4, size=n, p=area / area.sum())
+    r = np.sqrt(rng.uniform(HRMA_RADII[shell, 0] ** 2, HRMA_RADII[shell, 1] ** 2))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    pos = np.ones((n, 4))
+    pos[:, 0] = 10061.65 + 100.
+    pos[:, 1] = r * np.cos(phi)
+    pos[:, 2] = r * np.sin(phi)
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    ang = rng.uniform(0, 2 * np.pi, n)
+    pol = np.zeros((n, 4))
+    pol[:, 1] = np.cos(ang)
+    pol[:, 2] = np.sin(ang)
+    return dict(pos=pos, dir=d, energy=rng.uniform(0.5, 8., n), polarization=pol, probability=np.ones(n))
+
+
+def synth_c2_device(n, seed, device):
+    import torch
+    import marxs_b200 as mb
+    g = torch.Generator(device=device).manual_seed(seed)
+    radii = torch.tensor(HRMA_RADII, device=device)
+    area = radii[:, 1] ** 2 - radii[:, 0] ** 2
+    shell = torch.multinomial(area / area.sum(), n, replacement=True, generator=g)
+    u = torch.rand(n, device=device, generator=g, dtype=torch.float64)
+    r = torch.sqrt(radii[shell, 0] ** 2 + u * (radii[shell, 1] ** 2 - radii[shell, 0] ** 2))
+    phi = torch.rand(n, device=device, generator=g, dtype=torch.float64) * (2 * np.pi)
+    ang = torch.rand(n, device=device, generator=g, dtype=torch.float64) * (2 * np.pi)
+    b = mb.PhotonBatch(device=device)
+    pos = b.new_column('pos', torch.float64, vector=True)
+    pos[0] = 10161.65
+    pos[1] = r * torch.cos(phi)
+    pos[2] = r * torch.sin(phi)
+    pos[3] = 1.
+    d = b.new_column('dir', torch.float64, fill=0., vector=True)
+    d[0] = -1.
+    pol = b.new_column('polarization', torch.float64, fill=0., vector=True)
+    pol[1] = torch.cos(ang)
+    pol[2] = torch.sin(ang)
+    b.new_column('energy', torch.float64)[...] = torch.rand(n, device=device, generator=g, dtype=torch.float64) * 7.5 + 0.5
+    b.new_column('probability', torch.float64, fill=1.)
+    b.meta['ROLL_PNT'] = (0., 'roll')
+    return b
+
+
+def c2_instrument():
+    from marxs_b200 import simulator
+    from marxs_b200.missions import chandra
+    return simulator.Sequence(elements=[chandra.HRMA(), chandra.HETG(),
+                                        chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])])
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm: the oracle port (numpy restatement of the reference's own loops)
+# ---------------------------------------------------------------------------
+_worker = {}
+
+
+def _cpu_init():
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle import marxs_oracle as mo
+    from marxs_b200.missions.chandra import data as cd
+    _worker['mo'] = mo
+    _worker['inst'] = mo.Sequence([mo.chandra_hrma(), mo.chandra_hetg(cd.load_hess()),
+                                   mo.chandra_acis(cd.load_acis_corners(), [4, 5, 6, 7, 8, 9])])
+
+
+def _cpu_trace(seed):
+    mo = _worker['mo']
+    cols = synth_c2_numpy(CPU_PHOTONS_PER_WORKER, seed)
+    t = mo.PhotonTable(cols)
+    t.meta['ROLL_PNT'] = (0., 'roll')
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    out = _worker['inst'](t)          # draws=None: the legacy np.random stream, like the reference
+    dt = time.perf_counter() - t0
+    return dt, int((out['CCD_ID'] >= 0).sum())
+
+
+class CpuPool:
+    def __init__(self, procs=None):
+        import multiprocessing as mp
+        self.procs = procs or os.cpu_count() or 1
+        self.pool = mp.get_context('fork').Pool(self.procs, initializer=_cpu_init)
+        self.pool.map(_cpu_trace, range(self.procs))     # warm-up (imports, table setup)
+
+    def step(self, k):
+        """All workers trace CPU_PHOTONS_PER_WORKER photons; returns (photons, wall seconds)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_trace, [1000 * (k + 1) + i for i in range(self.procs)])
+        return self.procs * CPU_PHOTONS_PER_WORKER, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline_block(pool, steps):
+    tot_n, tot_t = 0, 0.
+    for k in range(steps):
+        n, dt = pool.step(k)
+        tot_n += n
+        tot_t += dt
+    return dict(value=tot_n / tot_t, unit='photons/s', cores=pool.procs, kind='port',
+                sample='{0} steps x {1} worker processes x {2} photons of the C2 workload through '
+                       'oracle/marxs_oracle.py (numpy restatement of the reference loops; the Python '
+                       'reference itself cannot travel to the GPU box)'.format(steps, pool.procs, CPU_PHOTONS_PER_WORKER))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    pool = CpuPool()
+    for k in range(args.warmup):
+        pool.step(100 + k)
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(args.steps):
+        n, _ = pool.step(k)
+        tot += n
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = tot / wall
+    line = dict(metric=METRIC, value=value, unit='photons/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
+                config=dict(workload=WORKLOAD, sample_per_step='{0} photons ({1} processes x {2})'.format(
+                    pool.procs * CPU_PHOTONS_PER_WORKER, pool.procs, CPU_PHOTONS_PER_WORKER)),
+                cpu_baseline=dict(value=value, unit='photons/s', cores=pool.procs, kind='port',
+                                  sample='each step traces {0} photons of the C2 workload on {1} host processes '
+                                         'through the oracle port'.format(pool.procs * CPU_PHOTONS_PER_WORKER, pool.procs)),
+                e2e=dict(value=value, unit='photons/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            # "under load": samples in the upper half of the power range
+            thr = 0.5 * (min(power) + max(power)) if power else 0
+            load = [s for s, w in zip(sm, power) if w >= thr] or sm
+            out = dict(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power) if power else None)
+        return out
+
+
+# ---------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def dram_traffic_per_photon():
+    """dram bytes per photon of the trace kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get('dram_bytes_per_photon')
+    return None
+
+
+def run_engine(args):
+    import ctypes
+    import torch
+    import marxs_b200 as mb
+    from marxs_b200 import _lib, dist as mdist, host as mhost
+    from marxs_b200.program import Lowering
+
+    rank, world, local = mdist.init_from_env('nccl' if args.gpus > 1 else None)
+    if world != args.gpus:
+        raise SystemExit('launch with torchrun --nproc-per-node {0} (WORLD_SIZE={1})'.format(args.gpus, world))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    lib = _lib.load()
+    n = args.photons
+    K, W = args.steps, args.warmup
+    inst = c2_instrument()
+
+    # one input copy per step (the trace is in place); outputs are shared
+    base = synth_c2_device(n, 20261017 + rank, device)
+    base.id0 = rank * n
+    lw = Lowering(base.colnames, meta=base.meta)
+    inst._lower(lw)
+    prog = lw.finish()
+    blob = prog.device_blob(device)
+    batches = [base] + [base.copy() for _ in range(K + W - 1)]
+    structs = []
+    for b in batches:
+        for name in prog.out_f64 + prog.out_i64:
+            if name not in b:
+                if name in batches[0]:
+                    b._store[name] = batches[0].storage(name)
+        cols, _ = prog.columns_struct(b)
+        structs.append(cols)
+    status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device=device)
+    image = torch.zeros((6, 1024, 1024), dtype=torch.float64, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    out0 = batches[0]
+
+    def step(k):
+        rc = lib.mxb_trace(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, ctypes.byref(structs[k]),
+                           n, rank * n, 1234 + k, status.data_ptr(), stream)
+        if rc:
+            raise RuntimeError(lib.mxb_last_error().decode())
+
+    def hist():
+        rc = lib.mxb_hist2d(out0.storage('chipx').data_ptr(), out0.storage('chipy').data_ptr(),
+                            out0.storage('probability').data_ptr(), out0.storage('CCD_ID').data_ptr(),
+                            4, 6, 1.0, 1.0, n, 1024, 1024, image.data_ptr(), None, stream)
+        if rc:
+            raise RuntimeError(lib.mxb_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(W):
+        step(k)
+        hist()
+    barrier()
+    image.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    ev0.record()
+    for k in range(K):
+        ka[k].record()
+        step(W + k)
+        kb[k].record()
+        # probability / chip columns of every batch alias batch 0's outputs except the core record
+        rc = lib.mxb_hist2d(out0.storage('chipx').data_ptr(), out0.storage('chipy').data_ptr(),
+                            batches[W + k].storage('probability').data_ptr(), out0.storage('CCD_ID').data_ptr(),
+                            4, 6, 1.0, 1.0, n, 1024, 1024, image.data_ptr(), None, stream)
+        if rc:
+            raise RuntimeError(lib.mxb_last_error().decode())
+    mdist.allreduce_images([image])          # the only collective: detector image over NVLink
+    ev1.record()
+    barrier()
+    total_ms = mdist.max_over_ranks(ev0.elapsed_time(ev1), device)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ka, kb)]))
+    kern_ms = mdist.max_over_ranks(kern_ms, device)
+    clocks = sampler.stop() if rank == 0 else None
+    st = status.cpu().numpy()
+    hit_ccd = float((out0['CCD_ID'] >= 0).double().mean())
+    img_sum = float(image.sum())
+
+    # ---- end to end through the host-buffer C ABI (rank-local pinned tables) ----
+    e2e = None
+    if not args.no_e2e:
+        ne = args.e2e_photons or n
+        host_in = mhost.HostPhotonTable.from_columns(synth_c2_numpy(ne, 777 + rank))
+        host_in.meta['ROLL_PNT'] = (0., 'roll')
+        host_in.id0 = rank * ne
+        host_out = mhost.HostPhotonTable(ne)
+        mhost.trace_host(inst, host_in, out=host_out, program=prog)        # warm-up (allocates + pins outputs)
+        ke = args.e2e_steps
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(ke):
+            mhost.trace_host(inst, host_in, out=host_out, program=prog, check=True)
+        barrier()
+        e2e_s = mdist.max_over_ranks(time.perf_counter() - t0, device)
+        h2d, d2h = mhost.h2d_d2h_bytes(prog, ne)
+        e2e = dict(value=world * ne * ke / e2e_s, unit='photons/s', h2d_bytes_per_step=h2d * world,
+                   d2h_bytes_per_step=d2h * world, steps=ke, photons_per_gpu_per_step=ne,
+                   ms_per_step=1e3 * e2e_s / ke,
+                   api='marxs_b200.host.trace_host -> mxb_trace_host (pinned host SoA planes, chunked 3-stream pipeline)')
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES_PER_PHOTON * n / (kern_ms * 1e-3) / 1e9
+    traffic = dram_traffic_per_photon()
+    line = dict(metric=METRIC, value=world * n * K / (total_ms * 1e-3), unit='photons/s', n_gpus=world, steps=K,
+                warmup=W, ms_per_step=total_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f64', data='synthetic',
+                config=dict(workload=WORKLOAD, photons_per_gpu_per_step=n, facets=336, chips=6,
+                            diagnostic_columns=DIAG_COLS, rng='device Philox4x32-10',
+                            l2='every step reads a fresh 0.88 GB input copy (> 126 MB L2); no flush needed',
+                            build=lib.mxb_build_info().decode(), parallelism='photon-range sharding x{0}'.format(world)),
+                roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                              traffic=(traffic * n if traffic else None), peak_source=peak_src,
+                              kernel='mxb_trace_kernel<true>', kernel_ms=kern_ms,
+                              algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
+                              note='fp64-pipe bound (see DESIGN.md): ~3.5k fp64 ops per photon'),
+                clocks=clocks, e2e=e2e, gpu_launches=2 * K,
+                checks=dict(ccd_hit_fraction=hit_ccd, image_sum=img_sum, prob_range_errors=int(st[0]),
+                            multi_hit=int(st[1]), brute_force_photons=int(st[2])))
+    if world == 1 and not args.no_cpu:
+        pool = CpuPool()
+        line['cpu_baseline'] = cpu_baseline_block(pool, args.cpu_steps)
+        pool.close()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--photons', type=int, default=N_PER_GPU, help='photons per GPU per step')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-photons', type=int, default=0)
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -148,12 +148,15 @@ int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host
               const MxbColumns* cols, int64_t n, int64_t photon_id0, uint64_t seed,
               unsigned long long* status_dev, void* stream);
 
-/* Same computation for HOST-resident columns (pinned or pageable): uploads the
- * program, streams the photons through the device in chunks (H2D, kernel, D2H
- * overlapped on three streams) and returns when the host columns are updated.
- * status_host: uint64[MXB_STATUS_WORDS] filled on return. */
-int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_cols,
-                   const unsigned char* f64_is_input, int64_t n, int64_t chunk,
+/* Same computation for HOST-resident columns (pinned for full speed, pageable works):
+ * uploads the program, streams the photons through the device in chunks of `chunk`
+ * photons (H2D, kernel, D2H overlapped on three streams, triple-buffered) and returns when
+ * the host output columns are complete.  host_in: planes to upload (the 11 core planes are
+ * required; draws optional).  host_out: planes to bring back (core planes, every output column
+ * of the program, id columns); may alias host_in (in-place, the reference's semantics:
+ * optics/base.py:168-173).  status_host: uint64[MXB_STATUS_WORDS] filled on return. */
+int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
+                   const MxbColumns* host_out, int64_t n, int64_t chunk,
                    int64_t photon_id0, uint64_t seed, unsigned long long* status_host);
 
 /* Geometry.intersect for one plane (math/geometry.py:211-261; circular != 0 adds :376-380).
@@ -169,10 +172,14 @@ int mxb_parallel_transport(const double* const dir_old[3], const double* const d
                            const double* const pol_old[3], double* const pol_new[3],
                            int64_t n, void* stream);
 
-/* Probability-weighted detector image: img[iy*nx+ix] += w for ix=round(x), iy=round(y), sel==id (or id<0: all).
- * Also counts[iy*nx+ix] += 1 when counts != NULL (bit-reproducible integer image). */
-int mxb_hist2d(const double* x, const double* y, const double* w, const long long* sel, long long id,
-               int64_t n, int nx, int ny, double* img, unsigned long long* counts, void* stream);
+/* Detector images for the multi-GPU epilogue: photon i falls into plane p = sel[i] - sel_lo
+ * (0 <= p < n_sel; sel == NULL: one plane) at pixel ix = round(x[i] - x0), iy = round(y[i] - y0)
+ * (round half to even like np.round; the reference's pixel convention, detector.py:27-32).
+ * img[(p*ny + iy)*nx + ix] += w[i] (1 if w == NULL; probability-weighted image, fp64 atomics) and
+ * counts[...] += 1 (bit-reproducible integer image).  Either output may be NULL. */
+int mxb_hist2d(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
+               int n_sel, double x0, double y0, int64_t n, int nx, int ny, double* img,
+               unsigned long long* counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,13 +61,13 @@ def load(strict=None):
     lib.mxb_trace.restype = ci
     lib.mxb_trace.argtypes = [vp, sz, vp, ctypes.POINTER(MxbColumns), i64, i64, u64, vp, vp]
     lib.mxb_trace_host.restype = ci
-    lib.mxb_trace_host.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), vp, i64, i64, i64, u64, vp]
+    lib.mxb_trace_host.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), ctypes.POINTER(MxbColumns), i64, i64, i64, u64, vp]
     lib.mxb_plane_intersect.restype = ci
     lib.mxb_plane_intersect.argtypes = [vp, ci, vp, vp, vp, vp, vp, i64, vp]
     lib.mxb_parallel_transport.restype = ci
     lib.mxb_parallel_transport.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.mxb_hist2d.restype = ci
-    lib.mxb_hist2d.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, i64, ci, ci, vp, vp, vp]
+    lib.mxb_hist2d.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, ci, ctypes.c_double, ctypes.c_double, i64, ci, ci, vp, vp, vp]
     if lib.mxb_version() != MXB_ABI_VERSION:
         raise MxbError('libmxb ABI {0} != python binding {1}: rebuild'.format(lib.mxb_version(), MXB_ABI_VERSION))
     _libs[path] = lib

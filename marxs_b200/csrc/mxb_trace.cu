@@ -723,18 +723,24 @@ parallel_transport_kernel(const double* ax, const double* ay, const double* az, 
 }
 
 __global__ void __launch_bounds__(256)
-hist2d_kernel(const double* x, const double* y, const double* w, const long long* sel, long long id,
-              long long n, int nx, int ny, double* img, unsigned long long* counts) {
+hist2d_kernel(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
+              int n_sel, double x0, double y0, long long n, int nx, int ny, double* img,
+              unsigned long long* counts) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        if (sel && id >= 0 && sel[i] != id) continue;
-        const double xv = x[i], yv = y[i];
+        long long plane = 0;
+        if (sel) {
+            plane = sel[i] - sel_lo;
+            if (plane < 0 || plane >= n_sel) continue;
+        }
+        const double xv = x[i] - x0, yv = y[i] - y0;
         if (!(xv == xv) || !(yv == yv)) continue;
         const long long ix = llrint(xv), iy = llrint(yv);   // np.round: half to even
         if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) continue;
+        const long long bin = (plane * ny + iy) * nx + ix;
         const double wv = w ? w[i] : 1.0;
-        if (wv == wv) atomicAdd(&img[iy * nx + ix], wv);
-        if (counts) atomicAdd(&counts[iy * nx + ix], 1ULL);
+        if (img && wv == wv) atomicAdd(&img[bin], wv);
+        if (counts) atomicAdd(&counts[bin], 1ULL);
     }
 }
 
@@ -863,12 +869,14 @@ int mxb_parallel_transport(const double* const dir_old[3], const double* const d
     return MXB_OK;
 }
 
-int mxb_hist2d(const double* x, const double* y, const double* w, const long long* sel, long long id,
-               int64_t n, int nx, int ny, double* img, unsigned long long* counts, void* stream) {
-    if (!x || !y || !img || nx <= 0 || ny <= 0) return fail(MXB_EINVAL, "mxb_hist2d: bad argument");
+int mxb_hist2d(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
+               int n_sel, double x0, double y0, int64_t n, int nx, int ny, double* img,
+               unsigned long long* counts, void* stream) {
+    if (!x || !y || (!img && !counts) || nx <= 0 || ny <= 0 || n_sel <= 0)
+        return fail(MXB_EINVAL, "mxb_hist2d: bad argument");
     if (n <= 0) return n == 0 ? MXB_OK : fail(MXB_EINVAL, "negative n");
-    hist2d_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, w, sel, id, n, nx, ny, img,
-                                                                         counts);
+    hist2d_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, w, sel, sel_lo, n_sel, x0, y0, n,
+                                                                         nx, ny, img, counts);
     CUDA_TRY(cudaGetLastError());
     return MXB_OK;
 }
@@ -876,15 +884,17 @@ int mxb_hist2d(const double* x, const double* y, const double* w, const long lon
 // ---------------------------------------------------------------------------
 // host-buffer entry: chunked H2D -> kernel -> D2H pipeline on three streams
 // ---------------------------------------------------------------------------
-int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_cols,
-                   const unsigned char* f64_is_input, int64_t n, int64_t chunk, int64_t photon_id0,
+int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
+                   const MxbColumns* host_out, int64_t n, int64_t chunk, int64_t photon_id0,
                    uint64_t seed, unsigned long long* status_host) {
     int n_ops = 0, stage_words = 0;
     int rc = validate_program(prog_host, prog_words, &n_ops, &stage_words);
     if (rc) return rc;
-    if (!host_cols || !status_host) return fail(MXB_EINVAL, "mxb_trace_host: null pointer");
+    if (!host_in || !host_out || !status_host) return fail(MXB_EINVAL, "mxb_trace_host: null pointer");
     if (n < 0) return fail(MXB_EINVAL, "negative n");
-    if (chunk <= 0) chunk = 1 << 22;
+    for (int k = 0; k <= MXB_COL_PROB; ++k)
+        if (!host_in->f64[k]) return fail(MXB_EINVAL, "mxb_trace_host: core photon column missing");
+    if (chunk <= 0) chunk = 1 << 21;
     if (chunk > n && n > 0) chunk = n;
     memset(status_host, 0, sizeof(unsigned long long) * MXB_STATUS_WORDS);
     if (n == 0) return MXB_OK;
@@ -892,9 +902,9 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
     constexpr int NBUF = 3;
     int nf = 0, ni = 0, nd = 0;
     int fidx[MXB_MAX_F64_COLS], iidx[MXB_MAX_I64_COLS], didx[MXB_MAX_SLOTS];
-    for (int k = 0; k < MXB_MAX_F64_COLS; ++k) if (host_cols->f64[k]) fidx[nf++] = k;
-    for (int k = 0; k < MXB_MAX_I64_COLS; ++k) if (host_cols->i64[k]) iidx[ni++] = k;
-    for (int k = 0; k < MXB_MAX_SLOTS; ++k) if (host_cols->draws[k]) didx[nd++] = k;
+    for (int k = 0; k < MXB_MAX_F64_COLS; ++k) if (host_in->f64[k] || host_out->f64[k]) fidx[nf++] = k;
+    for (int k = 0; k < MXB_MAX_I64_COLS; ++k) if (host_out->i64[k]) iidx[ni++] = k;
+    for (int k = 0; k < MXB_MAX_SLOTS; ++k) if (host_in->draws[k]) didx[nd++] = k;
     const size_t planes = (size_t)nf + ni + nd;
 
     double* dprog = nullptr;
@@ -941,8 +951,8 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             size_t p = 0;
             for (int k = 0; k < nf; ++k, ++p) {
                 dc.f64[fidx[k]] = reinterpret_cast<double*>(base + p * (size_t)chunk * 8);
-                if (!f64_is_input || f64_is_input[fidx[k]])
-                    HTRY(cudaMemcpyAsync(dc.f64[fidx[k]], host_cols->f64[fidx[k]] + off, (size_t)m * 8,
+                if (host_in->f64[fidx[k]])
+                    HTRY(cudaMemcpyAsync(dc.f64[fidx[k]], host_in->f64[fidx[k]] + off, (size_t)m * 8,
                                          cudaMemcpyHostToDevice, s_in));
             }
             for (int k = 0; k < ni; ++k, ++p)
@@ -950,7 +960,7 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             for (int k = 0; k < nd; ++k, ++p) {
                 double* d = reinterpret_cast<double*>(base + p * (size_t)chunk * 8);
                 dc.draws[didx[k]] = d;
-                HTRY(cudaMemcpyAsync(d, host_cols->draws[didx[k]] + off, (size_t)m * 8,
+                HTRY(cudaMemcpyAsync(d, host_in->draws[didx[k]] + off, (size_t)m * 8,
                                      cudaMemcpyHostToDevice, s_in));
             }
             HTRY(cudaEventRecord(ev_in[b], s_in));
@@ -960,12 +970,14 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             HTRY(cudaEventRecord(ev_k[b], s_k));
             HTRY(cudaStreamWaitEvent(s_out, ev_k[b], 0));
             for (int k = 0; k < nf; ++k) {
-                if (fidx[k] == MXB_COL_ENERGY) continue;   // never modified
-                HTRY(cudaMemcpyAsync(host_cols->f64[fidx[k]] + off, dc.f64[fidx[k]], (size_t)m * 8,
+                if (!host_out->f64[fidx[k]]) continue;
+                if (fidx[k] == MXB_COL_ENERGY && host_out->f64[fidx[k]] == host_in->f64[fidx[k]])
+                    continue;   // energy is never modified: nothing to bring back in place
+                HTRY(cudaMemcpyAsync(host_out->f64[fidx[k]] + off, dc.f64[fidx[k]], (size_t)m * 8,
                                      cudaMemcpyDeviceToHost, s_out));
             }
             for (int k = 0; k < ni; ++k)
-                HTRY(cudaMemcpyAsync(host_cols->i64[iidx[k]] + off, dc.i64[iidx[k]], (size_t)m * 8,
+                HTRY(cudaMemcpyAsync(host_out->i64[iidx[k]] + off, dc.i64[iidx[k]], (size_t)m * 8,
                                      cudaMemcpyDeviceToHost, s_out));
             HTRY(cudaEventRecord(ev_out[b], s_out));
         }
