@@ -73,7 +73,7 @@ def synth_c2_device(n, seed, device):
     phi = torch.rand(n, device=device, generator=g, dtype=torch.float64) * (2 * np.pi)
     ang = torch.rand(n, device=device, generator=g, dtype=torch.float64) * (2 * np.pi)
     b = mb.PhotonBatch(device=device)
-    pos = b.new_column('pos', torch.float64, vector=True)
+    pos = b.new_column('pos', torch.float64, vector=True, n=n)
     pos[0] = 10161.65
     pos[1] = r * torch.cos(phi)
     pos[2] = r * torch.sin(phi)

@@ -155,9 +155,11 @@ class PhotonBatch:
             raise ValueError('add_column needs a name')
         self[name] = col
 
-    def new_column(self, name, dtype=torch.float64, fill=None, vector=False):
-        """Allocate an output column (uninitialised unless ``fill`` is given)."""
-        shape = (4, len(self)) if vector else (len(self),)
+    def new_column(self, name, dtype=torch.float64, fill=None, vector=False, n=None):
+        """Allocate an output column (uninitialised unless ``fill`` is given); ``n`` is
+        only needed for the first column of an empty table."""
+        n = len(self) if n is None else int(n)
+        shape = (4, n) if vector else (n,)
         t = torch.empty(shape, dtype=dtype, device=self.device)
         if fill is not None:
             t.fill_(fill)
