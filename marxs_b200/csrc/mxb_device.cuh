@@ -26,7 +26,8 @@ MXB_DEV double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.
 MXB_DEV V3 cross(const V3& a, const V3& b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-MXB_DEV V3 ld3(const double* p) { return V3{p[0], p[1], p[2]}; }
+template <typename P>
+MXB_DEV V3 ld3(P p) { return V3{p[0], p[1], p[2]}; }
 
 // math/utils.py:150-164 norm_vector
 MXB_DEV V3 normalize(const V3& a) {
@@ -165,6 +166,18 @@ MXB_DEV double device_draw(uint64_t seed, uint64_t photon_id, int slot, int kind
     if (kind == 0) return u1;
     const double u2 = u01_from_bits(r[2], r[3]);
     return sqrt(-2.0 * log(1.0 - u1)) * cos(kTwoPi * u2);
+}
+
+// two independent standard normals from ONE Philox call (both Box-Muller branches)
+MXB_DEV void device_draw_normal_pair(uint64_t seed, uint64_t photon_id, int slot, double& z0, double& z1) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)photon_id, (uint32_t)(photon_id >> 32), (uint32_t)slot, 0u,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double rad = sqrt(-2.0 * log(1.0 - u01_from_bits(r[0], r[1])));
+    double s, c;
+    sincos(kTwoPi * u01_from_bits(r[2], r[3]), &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
 }
 
 }  // namespace mxb

@@ -80,6 +80,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------
+// program blob access: word offsets into the staged copy (shared memory, 32-bit
+// offsets -> LDS) or into the global blob when the program is too large to stage
+// ---------------------------------------------------------------------------
+extern __shared__ __align__(16) double g_smem[];
+
+template <bool STAGED>
+struct PRef {
+    const double* g;
+    int off;
+    __device__ __forceinline__ double operator[](int k) const {
+        if (STAGED) return g_smem[off + k];
+        return __ldg(g + off + k);
+    }
+    __device__ __forceinline__ PRef operator+(int k) const { return PRef{g, off + k}; }
+    __device__ __forceinline__ int i32(int k) const {  // packed int32 view of the words at off
+        if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
+        return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
+    }
+};
+
+// fused detector image: gp = nx ny sel_lo n_sel ; bin = round half to even like np.round
+template <typename PP>
+__device__ __forceinline__ void accumulate_image(double* img, PP gp, long long idn, double px, double py,
+                                                 double w) {
+    const long long nx = (long long)gp[0], ny = (long long)gp[1];
+    const long long plane = idn - (long long)gp[2];
+    if (plane < 0 || plane >= (long long)gp[3] || !(px == px) || !(py == py) || !(w == w)) return;
+    const long long ix = llrint(px), iy = llrint(py);
+    if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) return;
+    atomicAdd(&img[(plane * ny + iy) * nx + ix], w);
+}
+
+// ---------------------------------------------------------------------------
 // per-thread photon state
 // ---------------------------------------------------------------------------
 struct Photon {
@@ -151,12 +184,20 @@ __device__ __forceinline__ void op_rscatter(const Ctx& c, Photon& ph, PP p, int 
     V3 out = ph.dir;
     a = 0.0;
     b = 0.0;
+    double z0 = 0.0, z1 = 0.0;
+    const bool both = (p[3] != 0.0) && (p[4] != 0.0);
+    if (both && !c.P->cols.draws[s0] && !c.P->cols.draws[s1]) {
+        device_draw_normal_pair(c.P->seed, (unsigned long long)(c.P->id0 + c.i), s0, z0, z1);
+    } else {
+        if (p[3] != 0.0) z0 = draw(c, s0, 1);
+        if (p[4] != 0.0) z1 = draw(c, s1, 1);
+    }
     if (p[3] != 0.0) {
-        a = p[3] * draw(c, s0, 1);
+        a = p[3] * z0;
         out = axangle_rotate_T(perp, a, ph.dir);
     }
     if (p[4] != 0.0) {
-        b = p[4] * draw(c, s1, 1);
+        b = p[4] * z1;
         out = axangle_rotate_T(radial, b, out);
     }
     ph.pol = parallel_transport(ph.dir, out, ph.pol);
@@ -338,17 +379,26 @@ __device__ __forceinline__ void op_mleff(const Ctx& c, Photon& ph, PP p) {
 // ---------------------------------------------------------------------------
 // the fused program interpreter
 // ---------------------------------------------------------------------------
-struct OpI {  // decoded op (ints in smem)
-    int type, flags, pg, pf, c[8], s0, s1, w14, w15;
+struct OpHot {   // one LDS.128 per dispatch
+    int type;    // op code | kRelBit when the element params live in the current facet row
+    int flags;
+    int poff;    // word offset of the element params (relative to the facet row when kRelBit)
+    int pg;      // word offset of the global block (geometry, selector table, array header ...)
 };
+struct OpCold {
+    int c[8];
+    int s0, s1, w14, w15;
+};
+constexpr int kRelBit = 1 << 20;
 
 template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 mxb_trace_kernel(const __grid_constant__ TraceParams P) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ OpI ops[MXB_MAX_OPS];
+    __shared__ OpHot oph[MXB_MAX_OPS];
+    __shared__ OpCold opc[MXB_MAX_OPS];
     __shared__ unsigned long long st_sm[MXB_STATUS_WORDS];
     __shared__ __align__(8) uint64_t bar;
+    typedef PRef<STAGED> Ref;
 
     const int tid = threadIdx.x;
     // ---- stage the program: TMA bulk copy of the hot part of the blob ----
@@ -361,7 +411,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             uint32_t off = 0;
             while (off < bytes) {
                 const uint32_t chunk = min(bytes - off, 32768u);
-                bulk_g2s(reinterpret_cast<char*>(smem) + off, reinterpret_cast<const char*>(P.prog) + off,
+                bulk_g2s(reinterpret_cast<char*>(g_smem) + off, reinterpret_cast<const char*>(P.prog) + off,
                          chunk, &bar);
                 off += chunk;
             }
@@ -369,9 +419,24 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     }
     for (int k = tid; k < MXB_STATUS_WORDS; k += kThreads) st_sm[k] = 0ULL;
     if (STAGED) mbar_wait(&bar, 0);
-    const double* B = STAGED ? smem : P.prog;   // parameter base
-    for (int k = tid; k < P.n_ops * MXB_OP_WORDS; k += kThreads) {
-        reinterpret_cast<int*>(ops)[k] = (int)B[MXB_HEADER_WORDS + k];
+    const Ref B{P.prog, 0};
+    for (int k = tid; k < P.n_ops; k += kThreads) {
+        const Ref w = B + (MXB_HEADER_WORDS + k * MXB_OP_WORDS);
+        const int pg = (int)w[2], pf = (int)w[3];
+        OpHot h;
+        h.type = (int)w[0] | (pf >= 0 ? kRelBit : 0);
+        h.flags = (int)w[1];
+        h.poff = pf >= 0 ? pf : (pg >= 0 ? pg : 0);
+        h.pg = pg >= 0 ? pg : 0;
+        oph[k] = h;
+        OpCold c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c.c[j] = (int)w[4 + j];
+        c.s0 = (int)w[12];
+        c.s1 = (int)w[13];
+        c.w14 = (int)w[14];
+        c.w15 = (int)w[15];
+        opc[k] = c;
     }
     __syncthreads();
 
@@ -381,6 +446,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
     const long long stride = (long long)gridDim.x * kThreads;
     const long long n_round = ((P.n + kThreads - 1) / kThreads) * kThreads;  // keep warps whole
+    const bool lane0 = (tid & 31) == 0;
 
     for (long long i = (long long)blockIdx.x * kThreads + tid; i < n_round; i += stride) {
         ctx.i = i;
@@ -404,38 +470,59 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         // array iteration state
         int arr_cur = 0, arr_end = 0, arr_nhit = 0, arr_pc = -1;
         bool arr_brute = false;
-        const double* row = B;   // current facet row (params with pf >= 0 are relative to it)
-        const double* geom = B;  // current geometry block
+        int row = 0;    // word offset of the current facet row (0 = the blob itself outside arrays)
+        int geom = 0;   // word offset of the current geometry block
+
+        // leave the array at op `bpc`: photons that hit no facet initialise the columns the array creates
+        auto array_exit = [&](int bpc) {
+            const OpCold& ac = opc[bpc];
+            if (ctx.active && arr_nhit == 0) {
+                const Ref init = B + ac.s1;
+                for (int k = 0; k < ac.s0; ++k) {
+                    const int cr = init.i32(k);
+                    if (cr >= 0) P.cols.f64[cr][i] = kNaN; else P.cols.i64[-cr - 2][i] = -1LL;
+                }
+            }
+            arr_pc = -1;
+            row = 0;
+            ph.hit = false;
+        };
 
         int pc = 0;
         while (pc < P.n_ops) {
-            const OpI& op = ops[pc];
-            const int hit_pc = pc;
-            const double* pr = (op.pf >= 0) ? (row + op.pf) : (B + (op.pg >= 0 ? op.pg : 0));
-            switch (op.type) {
+            const OpHot op = oph[pc];
+            const Ref pr = B + (((op.type & kRelBit) ? row : 0) + op.poff);
+            switch (op.type & (kRelBit - 1)) {
             case MXB_OP_PLANE: {
-                geom = B + op.pg;
-                bool rect;
-                ph.hit = plane_intersect(geom, ph.pos, ph.dir, op.flags & 1, ph.ip, ph.l0, ph.l1, &rect) && ctx.active;
+                geom = op.pg;
+                ph.hit = plane_intersect(B + geom, ph.pos, ph.dir, op.flags & 1, ph.ip, ph.l0, ph.l1) && ctx.active;
+                const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
+                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
                 break;
             }
             case MXB_OP_LOADHIT: {
-                geom = B + op.pg;
+                const OpCold& c = opc[pc];
+                geom = op.pg;
                 ph.hit = false;
                 if (ctx.active) {
                     const MxbColumns& C = P.cols;
-                    ph.hit = C.f64[op.c[0]][i] != 0.0;
-                    ph.ip = V3{C.f64[op.c[1]][i], C.f64[op.c[2]][i], C.f64[op.c[3]][i]};
-                    ph.l0 = C.f64[op.c[4]][i];
-                    ph.l1 = C.f64[op.c[5]][i];
+                    ph.hit = C.f64[c.c[0]][i] != 0.0;
+                    ph.ip = V3{C.f64[c.c[1]][i], C.f64[c.c[2]][i], C.f64[c.c[3]][i]};
+                    ph.l0 = C.f64[c.c[4]][i];
+                    ph.l1 = C.f64[c.c[5]][i];
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
+                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
                 break;
             }
             case MXB_OP_COMMIT: {
-                put(ctx, op.c[0], ph.hit, ph.l0);
-                put(ctx, op.c[1], ph.hit, ph.l1);
-                const long long idn = (op.flags & 1) ? (long long)row[op.w15] : (long long)op.w14;
-                put_id(ctx, op.c[2], ph.hit, idn);
+                const OpCold& c = opc[pc];
+                put(ctx, c.c[0], ph.hit, ph.l0);
+                put(ctx, c.c[1], ph.hit, ph.l1);
+                if (c.c[2] >= 0) {
+                    const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
+                    put_id(ctx, c.c[2], ph.hit, idn);
+                }
                 if (ph.hit) ph.pos = ph.ip;
                 break;
             }
@@ -448,16 +535,18 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 break;
             }
             case MXB_OP_RSCATTER: {
+                const OpCold& c = opc[pc];
                 double a = 0, b = 0;
-                if (ph.hit) op_rscatter(ctx, ph, pr, op.s0, op.s1, a, b);
-                put(ctx, op.c[0], ph.hit, a);
-                put(ctx, op.c[1], ph.hit, b);
+                if (ph.hit) op_rscatter(ctx, ph, pr, c.s0, c.s1, a, b);
+                put(ctx, c.c[0], ph.hit, a);
+                put(ctx, c.c[1], ph.hit, b);
                 break;
             }
             case MXB_OP_GSCATTER: {
+                const OpCold& c = opc[pc];
                 double a = 0;
-                if (ph.hit) op_gscatter(ctx, ph, pr, op.s0, op.s1, a);
-                put(ctx, op.c[0], ph.hit, a);
+                if (ph.hit) op_gscatter(ctx, ph, pr, c.s0, c.s1, a);
+                put(ctx, c.c[0], ph.hit, a);
                 break;
             }
             case MXB_OP_FILTER: {
@@ -469,20 +558,31 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 break;
             }
             case MXB_OP_GRATING: {
+                const OpCold& c = opc[pc];
                 double order = 0, blaze = 0;
-                if (ph.hit) op_grating(ctx, ph, pr, geom, B + op.pg, op.flags, op.s0, order, blaze);
-                put(ctx, op.c[0], ph.hit, order);
-                put(ctx, op.c[1], ph.hit, blaze);
+                if (ph.hit) op_grating(ctx, ph, pr, B + geom, B + op.pg, op.flags, c.s0, order, blaze);
+                put(ctx, c.c[0], ph.hit, order);
+                put(ctx, c.c[1], ph.hit, blaze);
                 break;
             }
             case MXB_OP_DETPIX: {
-                put(ctx, op.c[0], ph.hit, ph.l0 / pr[0] + pr[1]);
-                put(ctx, op.c[1], ph.hit, ph.l1 / pr[0] + pr[2]);
+                // detector.py:73-75; pr: pixsize cp0 cp1; optional fused image: pg: nx ny sel_lo n_sel, s0 image slot
+                const OpCold& c = opc[pc];
+                const double px = ph.l0 / pr[0] + pr[1];
+                const double py = ph.l1 / pr[0] + pr[2];
+                put(ctx, c.c[0], ph.hit, px);
+                put(ctx, c.c[1], ph.hit, py);
+                if (c.s0 >= 0 && ph.hit) {
+                    const Ref gp = B + op.pg;
+                    const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
+                    accumulate_image(P.cols.f64[c.s0], gp, idn, px, py, ph.prob);
+                }
                 break;
             }
             case MXB_OP_ACIS: {
                 // det_acis.py:31-58 ; per-facet pr: pixsize cp0 cp1 sh ct st ox oy ; global: f pixrad odet0 odet1 cosr sinr
-                const double* gp = B + op.pg;
+                const OpCold& c = opc[pc];
+                const Ref gp = B + op.pg;
                 const double chipx = ph.l0 / pr[0] + pr[1] + 1;
                 const double chipy = ph.l1 / pr[0] + pr[2] + 1;
                 const double tx = pr[3] * (pr[4] * (chipx - 0.5) + pr[5] * (chipy - 0.5)) + pr[6];
@@ -490,14 +590,19 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const double mn0 = ph.ip.x - gp[0];
                 const double x = ph.ip.y / mn0 / gp[1];
                 const double y = ph.ip.z / mn0 / gp[1];
-                put(ctx, op.c[0], ph.hit, chipx);
-                put(ctx, op.c[1], ph.hit, chipy);
-                put(ctx, op.c[2], ph.hit, tx);
-                put(ctx, op.c[3], ph.hit, ty);
-                put(ctx, op.c[4], ph.hit, gp[2] - x);
-                put(ctx, op.c[5], ph.hit, gp[3] + y);
-                put(ctx, op.c[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
-                put(ctx, op.c[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
+                put(ctx, c.c[0], ph.hit, chipx);
+                put(ctx, c.c[1], ph.hit, chipy);
+                put(ctx, c.c[2], ph.hit, tx);
+                put(ctx, c.c[3], ph.hit, ty);
+                put(ctx, c.c[4], ph.hit, gp[2] - x);
+                put(ctx, c.c[5], ph.hit, gp[3] + y);
+                put(ctx, c.c[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
+                put(ctx, c.c[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
+                if (c.s0 >= 0 && ph.hit) {
+                    // fused detector image (chip pixel convention is 1-based: det_acis.py:33-34)
+                    const long long idn = (long long)(B + row)[c.w15];
+                    accumulate_image(P.cols.f64[c.s0], gp + 6, idn, chipx - 1.0, chipy - 1.0, ph.prob);
+                }
                 break;
             }
             case MXB_OP_BREWSTER: {
@@ -509,24 +614,25 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 break;
             }
             case MXB_OP_APERTURE: {
-                // aperture.py:42-78: params c[3] vy[3] vz[3] nex[3] phi0 dphi rin2
+                // aperture.py:42-78: params c[3] vy[3] vz[3] nex[3] phi0 dphi rin2 cum_lo cum_hi
+                const OpCold& c = opc[pc];
                 bool sel = ctx.active;
-                if (op.w14 >= 0) {  // MultiAperture :201-218: injected aperture id, or area-weighted draw
-                    const double a = draw(ctx, op.w14, 0);
-                    if (P.cols.draws[op.w14]) sel = sel && ((long long)a == (long long)op.w15);
-                    else sel = sel && (a >= pr[15] && a < pr[16]);
+                if (c.w14 >= 0 && sel) {  // MultiAperture :201-218: injected aperture id, or area-weighted draw
+                    const double a = draw(ctx, c.w14, 0);
+                    if (P.cols.draws[c.w14]) sel = ((long long)a == (long long)c.w15);
+                    else sel = (a >= pr[15] && a < pr[16]);
                 }
                 ph.hit = sel;
                 if (sel) {
                     double x, y;
-                    const double u0 = draw(ctx, op.s0, 0), u1 = draw(ctx, op.s1, 0);
+                    const double u0 = draw(ctx, c.s0, 0), u1 = draw(ctx, c.s1, 0);
                     if (op.flags & 1) {  // CircleAperture :138-146
                         const double phi = pr[12] + pr[13] * u0;
                         const double r = sqrt(pr[14] + (1. - pr[14]) * u1);
-                        double s, c;
-                        sincos(phi, &s, &c);
-                        x = r * c;
-                        y = r * s;
+                        double sn, cs;
+                        sincos(phi, &sn, &cs);
+                        x = r * cs;
+                        y = r * sn;
                     } else {  // RectangleAperture :92-95
                         x = u0 * 2. - 1.;
                         y = u1 * 2. - 1.;
@@ -538,6 +644,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     const double area = ph.dir.x * pr[9] + ph.dir.y * pr[10] + ph.dir.z * pr[11];
                     mul_prob(ctx, ph, clip01(area));
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
+                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
                 break;
             }
             case MXB_OP_PROPAGATE: {
@@ -548,24 +656,15 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 // op ints: c0 F, c1 row stride, c2 rows offset, c3 mode (1 = culling grid), c4 nu, c5 nv,
                 //          c6 cell_start offset (int32), c7 candidate offset (int32), s0 n_init, s1 init offset (int32)
                 // pg doubles: O[3] nbar[3] u[3] v[3] u0 v0 inv_cell T2
-                const double* H = B + op.pg;
-                const int F = op.c[0], rstride = op.c[1];
-                const double* rows = B + op.c[2];
+                const OpCold& c = opc[pc];
+                const Ref H = B + op.pg;
                 if (arr_pc != pc) {  // first round of this array for this photon
                     arr_pc = pc;
                     arr_nhit = 0;
                     arr_brute = true;
                     arr_cur = 0;
-                    arr_end = ctx.active ? F : 0;
-                    // columns the array body creates: NaN / -1 until a facet is hit
-                    const int* init = reinterpret_cast<const int*>(B + op.s1);
-                    for (int k = 0; k < op.s0; ++k) {
-                        const int cr = init[k];
-                        if (ctx.active) {
-                            if (cr >= 0) P.cols.f64[cr][i] = kNaN; else P.cols.i64[-cr - 2][i] = -1LL;
-                        }
-                    }
-                    if (op.c[3] == 1 && ctx.active) {
+                    arr_end = ctx.active ? c.c[0] : 0;
+                    if (c.c[3] == 1 && ctx.active) {
                         const V3 nb = ld3(H + 3);
                         const double dn = dot(ph.dir, nb);
                         const double d2 = dot(ph.dir, ph.dir);
@@ -577,13 +676,12 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                             const V3 q{ph.pos.x + t * ph.dir.x - O.x, ph.pos.y + t * ph.dir.y - O.y, ph.pos.z + t * ph.dir.z - O.z};
                             const double fu = (dot(q, ld3(H + 6)) - H[12]) * H[14];
                             const double fv = (dot(q, ld3(H + 9)) - H[13]) * H[14];
-                            const int nu = op.c[4], nv = op.c[5];
                             arr_brute = false;
-                            if (fu >= 0.0 && fv >= 0.0 && fu < (double)nu && fv < (double)nv) {
-                                const int cell = (int)fv * nu + (int)fu;
-                                const int* cs = reinterpret_cast<const int*>(B + op.c[6]);
-                                arr_cur = cs[cell];
-                                arr_end = cs[cell + 1];
+                            if (fu >= 0.0 && fv >= 0.0 && fu < (double)c.c[4] && fv < (double)c.c[5]) {
+                                const int cell = (int)fv * c.c[4] + (int)fu;
+                                const Ref cs = B + c.c[6];
+                                arr_cur = cs.i32(cell);
+                                arr_end = cs.i32(cell + 1);
                             } else {
                                 arr_cur = arr_end = 0;
                             }
@@ -594,14 +692,14 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 }
                 // search the next facet (ascending index) this photon hits from its CURRENT state
                 bool found = false;
-                const int* cand = reinterpret_cast<const int*>(B + op.c[7]);
+                const Ref cand = B + c.c[7];
                 while (arr_cur < arr_end) {
-                    const int j = arr_brute ? arr_cur : cand[arr_cur];
+                    const int j = arr_brute ? arr_cur : cand.i32(arr_cur);
                     ++arr_cur;
-                    const double* r = rows + (long long)j * rstride;
+                    const int r = c.c[2] + j * c.c[1];
                     V3 ipt;
                     double a0, a1;
-                    if (plane_intersect(r, ph.pos, ph.dir, false, ipt, a0, a1)) {
+                    if (plane_intersect(B + r, ph.pos, ph.dir, false, ipt, a0, a1)) {
                         found = true;
                         row = r;
                         geom = r;
@@ -616,46 +714,46 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     ++arr_nhit;
                     if (arr_nhit == 2) atomicAdd(&st_sm[MXB_ST_MULTI_HIT], 1ULL);
                 }
-                if (!__any_sync(0xffffffffu, found)) {
-                    // no lane has work left: skip the body
-                    while (ops[pc].type != MXB_OP_ARRAY_END) ++pc;
-                    arr_pc = -1;
-                    ph.hit = false;
-                    row = B;
+                const unsigned m = __ballot_sync(0xffffffffu, found);
+                if (m == 0u) {
+                    // no lane found a facet: leave the array, skipping the body
+                    array_exit(pc);
+                    while ((oph[pc].type & (kRelBit - 1)) != MXB_OP_ARRAY_END) ++pc;
+                } else if (lane0) {
+                    atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
                 }
                 break;
             }
             case MXB_OP_ARRAY_END: {
-                // after the body: re-validate the culling cone for the NEW direction of photons that hit
-                const OpI& bop = ops[arr_pc];
-                const double* H = B + bop.pg;
+                // after the body: photons that hit re-validate the culling cone for their NEW direction
+                const int bpc = arr_pc;
+                const OpCold& c = opc[bpc];
                 if (ph.hit && !arr_brute) {
+                    const Ref H = B + oph[bpc].pg;
                     const V3 nb = ld3(H + 3);
                     const double dn = dot(ph.dir, nb);
                     const double d2 = dot(ph.dir, ph.dir);
                     // the cell list covers ONE redirection inside the cone (H t + 2 H t' <= margin);
                     // a second hit or a steep new direction falls back to brute force
                     if (arr_nhit >= 2 || (dn == dn && !(dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn))) {
-                        const double* rows = B + bop.c[2];
-                        const int j = (int)((row - rows) / bop.c[1]);
+                        const int j = (row - c.c[2]) / c.c[1];
                         arr_brute = true;
                         arr_cur = j + 1;
-                        arr_end = bop.c[0];
+                        arr_end = c.c[0];
                         atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
                     }
                 }
-                pc = arr_pc - 1;  // loop: next round of the search (pc++ below)
+                // another search round only if some lane that hit still has facets to test
+                if (__any_sync(0xffffffffu, ph.hit && arr_cur < arr_end)) {
+                    if (!ph.hit) arr_cur = arr_end;   // lanes that found nothing are done with this array
+                    pc = bpc - 1;                     // -> ARRAY_BEGIN (pc++ below)
+                } else {
+                    array_exit(bpc);
+                }
                 break;
             }
             default:
                 break;
-            }
-            // per-op hit statistics (warp-aggregated): lets the host honour "no columns are
-            // added when nothing intersects" (optics/base.py:176-177)
-            if (op.type == MXB_OP_PLANE || op.type == MXB_OP_APERTURE || op.type == MXB_OP_ARRAY_BEGIN ||
-                op.type == MXB_OP_LOADHIT) {
-                const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
-                if ((tid & 31) == 0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + hit_pc], (unsigned long long)__popc(m));
             }
             ++pc;
         }

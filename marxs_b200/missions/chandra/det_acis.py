@@ -29,11 +29,17 @@ class ACISChip(FlatDetector):
         sh = t['scale'][self.id_num] * t['handedness'][self.id_num]
         ox, oy = t['origin'][self.id_num]
         roll = np.deg2rad(lw.meta['ROLL_PNT'][0])
-        pg = lw.params([NOMINAL_FOCALLENGTH, self.pixsize_in_rad, self.ODET[0], self.ODET[1],
-                        np.cos(roll), np.sin(roll)])
+        glob = [NOMINAL_FOCALLENGTH, self.pixsize_in_rad, self.ODET[0], self.ODET[1], np.cos(roll), np.sin(roll)]
+        s0 = -1
+        if lw.image is not None:
+            # fused detector image: image[CCD_ID - sel_lo, round(chipy) - 1, round(chipx) - 1] += probability
+            img, sel_lo = lw.image
+            glob += [img.shape[2], img.shape[1], sel_lo, img.shape[0]]
+            s0 = lw.aux_ptr(img)
+        pg = lw.params(glob)
         pf = lw.eparams([self.pixsize, self.centerpix[0], self.centerpix[1], sh, np.cos(theta),
                          np.sin(theta), ox + 0.5, oy + 0.5])
-        lw.op('ACIS', pg=pg, pf=pf,
+        lw.op('ACIS', pg=pg, pf=pf, s0=s0,
               cols=[lw.fcol(n) for n in ('chipx', 'chipy', 'tdetx', 'tdety', 'detx', 'dety', 'x', 'y')])
         lw.meta_updates['ACSYS1'] = ('CHIP:AXAF-ACIS-1.0', 'reference for chip coord system')
         lw.meta_updates['ACSYS2'] = ('TDET:{0}'.format(t['version']), 'reference for tiled detector coord system')

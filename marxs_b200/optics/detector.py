@@ -37,5 +37,15 @@ class FlatDetector(FlatOpticalElement):
             self.centerpix[i] = (self.npix[i] - 1) / 2
 
     def _lower_specific(self, lw):
-        lw.op('DETPIX', pf=lw.eparams([self.pixsize, self.centerpix[0], self.centerpix[1]]),
-              cols=[lw.fcol(self.detpix_name[0]), lw.fcol(self.detpix_name[1])])
+        image = lw.image if lw.image is not None else (
+            (self.image, self.id_num) if getattr(self, 'image', None) is not None else None)
+        pg, s0 = -1, -1
+        if image is not None:
+            # detector image fused into the trace: image[id_num - sel_lo, round(detpix_y), round(detpix_x)] += probability
+            t, sel_lo = image
+            pg = lw.params([t.shape[2], t.shape[1], sel_lo, t.shape[0]])
+            s0 = lw.aux_ptr(t)
+        lw.op('DETPIX', flags=1 if lw.array is not None else 0, pg=pg,
+              pf=lw.eparams([self.pixsize, self.centerpix[0], self.centerpix[1]]),
+              cols=[lw.fcol(self.detpix_name[0]), lw.fcol(self.detpix_name[1])], s0=s0,
+              w14=self.id_num if lw.array is None else 0)

@@ -125,8 +125,7 @@ class FlatGrating(FlatOpticalElement):
         dd = -e_perp[0]
         mod = self._blaze_modifier()
         flags = (1 if self._cat else 0) | (0 if self.transmission else 2) | (4 if mod is not None else 0)
-        b0, b1 = mod if mod is not None else (0., 0.)
-        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [self._d, b0, b1]]))
+        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [self._d], list(mod) if mod is not None else []]))
         lw.op('GRATING', flags=flags, pg=lower_selector(self.order_selector, lw), pf=pf,
               cols=[lw.fcol(self.order_name), lw.fcol(self.blaze_name)], s0=lw.slot('uniform'))
 

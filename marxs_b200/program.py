@@ -76,7 +76,7 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
     The kernel checks the cone per photon and falls back to brute force outside.
     """
     F = G.shape[0]
-    if F < 8:
+    if F < 3:
         return None
     c, ex, ey, ez = G[:, 0:3], G[:, 3:6].copy(), G[:, 6:9], G[:, 9:12]
     Ly, Lz = G[:, 12], G[:, 13]
@@ -110,10 +110,12 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
     nu, nv = int(np.floor(wu / cell)) + 1, int(np.floor(wv / cell)) + 1
     inv_cell = 1.0 / cell
     lists = [[] for _ in range(nu * nv)]
-    iu0 = np.clip(np.floor((lo_u - u0) * inv_cell).astype(int) - 1, 0, nu - 1)
-    iu1 = np.clip(np.floor((hi_u - u0) * inv_cell).astype(int) + 1, 0, nu - 1)
-    iv0 = np.clip(np.floor((lo_v - v0) * inv_cell).astype(int) - 1, 0, nv - 1)
-    iv1 = np.clip(np.floor((hi_v - v0) * inv_cell).astype(int) + 1, 0, nv - 1)
+    # (the margin carries 1e-6 mm of slack, far above the rounding of this arithmetic, which the
+    #  kernel repeats in the same order: no extra ring of cells is needed)
+    iu0 = np.clip(np.floor((lo_u - u0) * inv_cell).astype(int), 0, nu - 1)
+    iu1 = np.clip(np.floor((hi_u - u0) * inv_cell).astype(int), 0, nu - 1)
+    iv0 = np.clip(np.floor((lo_v - v0) * inv_cell).astype(int), 0, nv - 1)
+    iv1 = np.clip(np.floor((hi_v - v0) * inv_cell).astype(int), 0, nv - 1)
     for j in range(F):
         for iv in range(iv0[j], iv1[j] + 1):
             base = iv * nu
@@ -155,6 +157,8 @@ class Lowering:
         self.array = None                 # active array context
         self.meta_updates = OrderedDict()
         self.needs_pos = False            # an aperture creates the pos column
+        self.aux = OrderedDict()          # name -> device tensor reached through an f64 pointer slot
+        self.image = None                 # (tensor, sel_lo) of the detector array being lowered
 
     # ---- transactions (an element that turns out not to be fusable is rolled back) ----
     def checkpoint(self):
@@ -164,7 +168,7 @@ class Lowering:
                     n_big=len(self.big), n_fix=len(self.fixups), dedupe=dict(self._dedupe),
                     f64=list(self.f64_cols), i64=list(self.i64_cols), slots=list(self.slot_kinds),
                     new_cols=OrderedDict(self.new_cols), init=set(self.initialised), creator=self.creator,
-                    meta_updates=OrderedDict(self.meta_updates))
+                    meta_updates=OrderedDict(self.meta_updates), aux=OrderedDict(self.aux))
 
     def rollback(self, cp):
         del self.ops[cp['n_ops']:]
@@ -176,6 +180,7 @@ class Lowering:
         self.f64_cols, self.i64_cols, self.slot_kinds = cp['f64'], cp['i64'], cp['slots']
         self.new_cols, self.initialised, self.creator = cp['new_cols'], cp['init'], cp['creator']
         self.meta_updates = cp['meta_updates']
+        self.aux = cp['aux']
         self.array = None
 
     # ---- parameters -------------------------------------------------------
@@ -243,6 +248,19 @@ class Lowering:
 
     def fcol(self, name):
         return self._col(name, 'f')
+
+    def aux_ptr(self, tensor):
+        """Pointer slot (in the f64 table) for a device buffer that is not a photon column,
+        e.g. a detector image accumulated by the kernel."""
+        for name, t in self.aux.items():
+            if t is tensor:
+                return self.f64_cols.index(name)
+        name = '_aux{0}'.format(len(self.aux))
+        if len(self.f64_cols) >= _lib.MXB_MAX_F64_COLS:
+            raise NotFusable('too many output columns in one program')
+        self.f64_cols.append(name)
+        self.aux[name] = tensor
+        return len(self.f64_cols) - 1
 
     def icol(self, name):
         return self._col(name, 'i')
@@ -369,7 +387,8 @@ class Lowering:
         begin['cols'] = ints
         begin['s0'], begin['s1'] = len(init), init_off
         for rec in a['body']:
-            if rec['type'] == OP['COMMIT'] and rec['flags'] & 1:
+            # ops that need the facet's id_num read it from the last word of the row
+            if (rec['type'] in (OP['COMMIT'], OP['DETPIX']) and rec['flags'] & 1) or rec['type'] == OP['ACIS']:
                 rec['w15'] = 14 + nper
         self.array = None
         self.op('ARRAY_END')
@@ -397,7 +416,8 @@ class Lowering:
             blob[w + 4:w + 12] = rec['cols']
             blob[w + 12:w + 16] = [rec['s0'], rec['s1'], rec['w14'], rec['w15']]
         return Program(blob, stage_words, list(self.ops), self.f64_cols[FIRST_OUT:], list(self.i64_cols),
-                       list(self.slot_kinds), OrderedDict(self.new_cols), self.meta_updates)
+                       list(self.slot_kinds), OrderedDict(self.new_cols), self.meta_updates,
+                       OrderedDict(self.aux))
 
 
 _status_names = {_lib.MXB_ST_PROB_RANGE: 'probability factor outside [0, 1]'}
@@ -406,7 +426,9 @@ _status_names = {_lib.MXB_ST_PROB_RANGE: 'probability factor outside [0, 1]'}
 class Program:
     """A lowered element tree: device blob + column/slot layout + launcher."""
 
-    def __init__(self, blob, stage_words, ops, out_f64, out_i64, slot_kinds, new_cols, meta_updates):
+    def __init__(self, blob, stage_words, ops, out_f64, out_i64, slot_kinds, new_cols, meta_updates,
+                 aux=None):
+        self.aux = aux or OrderedDict()
         self.blob = np.ascontiguousarray(blob, dtype=np.float64)
         self.stage_words = stage_words
         self.ops = ops
@@ -446,6 +468,12 @@ class Program:
                 raise ValueError('column {0} must be contiguous float64'.format(name))
             cols.f64[idx] = st.data_ptr()
         for k, name in enumerate(self.out_f64):
+            if name in self.aux:
+                t = self.aux[name]
+                if t.device != photons.device or t.dtype != torch.float64 or not t.is_contiguous():
+                    raise ValueError('auxiliary buffer must be a contiguous float64 tensor on the photon device')
+                cols.f64[FIRST_OUT + k] = t.data_ptr()
+                continue
             if name not in photons:
                 photons.new_column(name, torch.float64)
             st = photons.storage(name)

@@ -217,12 +217,19 @@ class Parallel(BaseContainer):
             return
         if not all(_lowerable(e) for e in self.elements):
             raise NotFusable('Parallel holds elements that cannot be lowered')
+        image = getattr(self, 'image', None)
+        if image is not None:
+            # fused detector image (n_planes, ny, nx): plane = id_num - image_sel_lo
+            lw.image = (image, getattr(self, 'image_sel_lo', min(e.id_num for e in self.elements)))
         lw.begin_array()
-        for e in self.elements:
-            lw.begin_facet()
-            e._lower(lw)
-            lw.end_facet()
-        lw.end_array()
+        try:
+            for e in self.elements:
+                lw.begin_facet()
+                e._lower(lw)
+                lw.end_facet()
+            lw.end_array()
+        finally:
+            lw.image = None
 
 
 class ParallelCalculated(Parallel):

@@ -449,6 +449,33 @@ def test_chandra_c2_vs_oracle(mode):
     assert (want['CCD_ID'] >= 0).mean() > 0.5
 
 
+def test_fused_detector_image():
+    """The image accumulated inside the trace kernel == mxb_hist2d on the output columns == numpy."""
+    mb = _mb()
+    from marxs_b200.image import detector_image
+    rng = np.random.default_rng(SEED + 9)
+    n = 200000
+    prod, _ = chandra_pair()
+    img = torch.zeros((6, 1024, 1024), dtype=torch.float64, device='cuda')
+    prod.elements[2].image = img
+    mb.set_seed(3)
+    out = prod(mb.PhotonBatch(chandra_photons(rng, n), device='cuda'))
+    img2, cnt2 = detector_image(out, 'chipx', 'chipy', 1024, 1024, weight='probability', sel='CCD_ID',
+                                sel_lo=4, n_sel=6, x0=1., y0=1., want_counts=True)
+    o = out.to_numpy()
+    ok = o['CCD_ID'] >= 0
+    ix = np.round(o['chipx'][ok] - 1).astype(int)
+    iy = np.round(o['chipy'][ok] - 1).astype(int)
+    inside = (ix >= 0) & (ix < 1024) & (iy >= 0) & (iy < 1024)
+    flat = ((o['CCD_ID'][ok] - 4) * 1024 + iy) * 1024 + ix
+    ref_counts = np.bincount(flat[inside], minlength=6 * 1024 * 1024).reshape(6, 1024, 1024)
+    ref_img = np.bincount(flat[inside], weights=o['probability'][ok][inside], minlength=6 * 1024 * 1024).reshape(6, 1024, 1024)
+    assert np.array_equal(cnt2.cpu().numpy(), ref_counts)                      # integer image: bit-exact
+    np.testing.assert_allclose(img2.cpu().numpy(), ref_img, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(img.cpu().numpy(), ref_img, rtol=1e-12, atol=1e-12)
+    assert ref_counts.sum() > 0.9 * ok.sum()
+
+
 def test_chandra_full_size_properties():
     """Config-2 size (1e7 photons) through size-independent properties: device RNG,
     results independent of how the batch is split, physical invariants."""
