@@ -41,6 +41,8 @@ def set_strict(flag):
 def lib_path(strict=None):
     if strict is None:
         strict = _default_strict[0]
+    if os.environ.get('MXB_LIB_PATH') and not strict:      # kernel-variant experiments
+        return os.environ['MXB_LIB_PATH']
     return os.path.join(_HERE, 'libmxb_strict.so' if strict else 'libmxb.so')
 
 

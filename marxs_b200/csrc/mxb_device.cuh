@@ -22,6 +22,42 @@ struct V3 {
     double x, y, z;
 };
 
+// ---- division / sqrt -----------------------------------------------------------------
+// strict build: IEEE-754 correctly rounded operators (bit parity with numpy).
+// fast build: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) + two Newton steps: <= 1 ulp
+// typical, no denormal / special-case slow path (inputs here are lengths and dot products of
+// unit-scale vectors; zero still yields inf/NaN like the IEEE forms do).
+MXB_DEV double fast_rcp(double x) {
+#ifdef MXB_FAST
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+MXB_DEV double fast_rsqrt(double x) {   // only used in the fast build
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-hx * r, r, 0.5);
+    return fma(r, e, r);
+}
+MXB_DEV double div(double a, double b) {
+#ifdef MXB_FAST
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);    // one correction step: faithful quotient
+#else
+    return a / b;
+#endif
+}
+
 MXB_DEV double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 MXB_DEV V3 cross(const V3& a, const V3& b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
@@ -31,13 +67,29 @@ MXB_DEV V3 ld3(P p) { return V3{p[0], p[1], p[2]}; }
 
 // math/utils.py:150-164 norm_vector
 MXB_DEV V3 normalize(const V3& a) {
-    double n = sqrt(dot(a, a));
 #ifdef MXB_FAST
-    double r = 1.0 / n;
+    const double r = fast_rsqrt(dot(a, a));
     return V3{a.x * r, a.y * r, a.z * r};
 #else
+    const double n = sqrt(dot(a, a));
     return V3{a.x / n, a.y / n, a.z / n};
 #endif
+}
+
+// sin and cos; the fast build uses the Taylor series for the tiny scatter angles (|x| < 2^-7:
+// truncation error x^10/10! < 1e-28), libm otherwise
+MXB_DEV void sincos_small(double x, double* s, double* c) {
+#ifdef MXB_FAST
+    if (fabs(x) < 0.0078125) {
+        const double x2 = x * x;
+        *s = x * fma(x2, fma(x2, fma(x2, fma(x2, 2.7557319223985893e-06, -1.9841269841269841e-04),
+                                     8.3333333333333332e-03), -1.6666666666666666e-01), 1.0);
+        *c = fma(x2, fma(x2, fma(x2, fma(x2, 2.4801587301587302e-05, -1.3888888888888889e-03),
+                                 4.1666666666666664e-02), -0.5), 1.0);
+        return;
+    }
+#endif
+    sincos(x, s, c);
 }
 
 MXB_DEV double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }  // NaN propagates like np.clip
@@ -54,7 +106,7 @@ MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V
     const double ex = g[3], ey = g[4], ez = g[5];
     const double k_num = (cx - pos.x) * ex + (cy - pos.y) * ey + (cz - pos.z) * ez;
     const double k_den = dir.x * ex + dir.y * ey + dir.z * ez;
-    const double k = k_num / k_den;
+    const double k = div(k_num, k_den);
     ip.x = pos.x + k * dir.x;
     ip.y = pos.y + k * dir.y;
     ip.z = pos.z + k * dir.z;
@@ -74,12 +126,14 @@ MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& po
     const V3 d1 = normalize(dir_old);
     const V3 d2 = normalize(dir_new);
     V3 s = cross(d1, d2);
-    const double ns = sqrt(dot(s, s));
-    if (fabs(ns) <= 1e-8) return pol;
 #ifdef MXB_FAST
-    const double r = 1.0 / ns;
+    const double ns2 = dot(s, s);
+    if (!(ns2 > 1e-16)) { if (ns2 == ns2) return pol; }   // |ns| <= 1e-8 -> identity; NaN falls through
+    const double r = fast_rsqrt(ns2);
     s = V3{s.x * r, s.y * r, s.z * r};
 #else
+    const double ns = sqrt(dot(s, s));
+    if (fabs(ns) <= 1e-8) return pol;
     s = V3{s.x / ns, s.y / ns, s.z / ns};
 #endif
     const V3 p_in = cross(d1, s);
@@ -93,7 +147,7 @@ MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& po
 MXB_DEV V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
     const V3 a = normalize(axis);  // axes / np.linalg.norm(axes): true division in strict build
     double s, c;
-    sincos(angle, &s, &c);
+    sincos_small(angle, &s, &c);
     const double C = 1 - c;
     const double x = a.x, y = a.y, z = a.z;
     const double xs = x * s, ys = y * s, zs = z * s;

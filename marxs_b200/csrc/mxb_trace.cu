@@ -34,7 +34,10 @@ int fail(int code, const std::string& msg) {
             return fail(MXB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
     } while (0)
 
-constexpr int kThreads = 512;   // one persistent CTA per SM: 16 warps share one staged program
+#ifndef MXB_THREADS
+#define MXB_THREADS 512
+#endif
+constexpr int kThreads = MXB_THREADS;   // one persistent CTA per SM: its warps share one staged program
 constexpr int kMaxSmemStageBytes = 200 * 1024;
 
 struct TraceParams {
@@ -127,6 +130,7 @@ struct Ctx {
     const TraceParams* P;
     long long i;           // photon index in the batch
     bool active;
+    bool init_round;            // column-initialising stores are live (see put)
     unsigned long long* st_sm;  // smem status accumulators
 };
 
@@ -136,22 +140,19 @@ __device__ __forceinline__ double draw(const Ctx& c, int slot, int kind) {
     return device_draw(c.P->seed, (unsigned long long)(c.P->id0 + c.i), slot, kind);
 }
 
-// store into an f64 output column. col < 0: not materialised. col >= MXB_COL_INIT:
-// this op initialises the column (NaN on miss).
-__device__ __forceinline__ void put(const Ctx& c, int col, bool hit, double v) {
-    if (col < 0 || !c.active) return;
-    if (col >= MXB_COL_INIT) {
-        c.P->cols.f64[col - MXB_COL_INIT][c.i] = hit ? v : __longlong_as_double(0x7ff8000000000000LL);
-    } else if (hit) {
-        c.P->cols.f64[col][c.i] = v;
+// Output columns are resolved once per CTA into entries: (device pointer | 1 if this op
+// initialises the column), 0 = not materialised.  An initialising op stores NaN / -1 for
+// photons it does not touch (outside arrays, or in the first search round of an array).
+typedef unsigned long long ColEntry;
+
+__device__ __forceinline__ void put(const Ctx& c, ColEntry e, bool hit, double v) {
+    if (e != 0ULL && c.active && (hit || ((e & 1ULL) && c.init_round))) {
+        reinterpret_cast<double*>(e & ~7ULL)[c.i] = hit ? v : __longlong_as_double(0x7ff8000000000000LL);
     }
 }
-__device__ __forceinline__ void put_id(const Ctx& c, int col, bool hit, long long v) {
-    if (col < 0 || !c.active) return;
-    if (col >= MXB_COL_INIT) {
-        c.P->cols.i64[col - MXB_COL_INIT][c.i] = hit ? v : -1LL;
-    } else if (hit) {
-        c.P->cols.i64[col][c.i] = v;
+__device__ __forceinline__ void put_id(const Ctx& c, ColEntry e, bool hit, long long v) {
+    if (e != 0ULL && c.active && (hit || ((e & 1ULL) && c.init_round))) {
+        reinterpret_cast<long long*>(e & ~7ULL)[c.i] = hit ? v : -1LL;
     }
 }
 
@@ -300,7 +301,7 @@ __device__ __forceinline__ void op_grating(const Ctx& c, Photon& ph, PP p, PP ge
                                            int flags, int slot, double& order, double& blaze) {
     const V3 pn = normalize(ph.dir);
     const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
-    const double wave = kEnergy2Wave / ph.energy;
+    const double wave = div(kEnergy2Wave, ph.energy);
     const double p_l = dot(pn, l);
     const V3 pp = normalize(V3{pn.x - p_l * l.x, pn.y - p_l * l.y, pn.z - p_l * l.z});
     blaze = acos(clip01(fabs(dot(pp, n))));
@@ -310,7 +311,7 @@ __device__ __forceinline__ void op_grating(const Ctx& c, Photon& ph, PP p, PP ge
     order = select_order(sel, c.P->prog, u, ph.energy, blaze, psel);
     const double p_dd = dot(pn, dd);
     const double sign = (flags & 1) ? ((p_dd < 0.0) ? -1.0 : 1.0) : -1.0;  // CAT: grating.py:298-301
-    const double p_d = p_dd + sign * order * wave / p[6];
+    const double p_d = p_dd + div(sign * order * wave, p[6]);
     const double p_n = sqrt(1. - p_d * p_d - p_l * p_l);
     const double pdn = dot(pn, n);
     double direction = (pdn > 0.0) ? 1.0 : ((pdn < 0.0) ? -1.0 : pdn);  // np.sign
@@ -386,6 +387,7 @@ struct OpHot {   // one LDS.128 per dispatch
     int pg;      // word offset of the global block (geometry, selector table, array header ...)
 };
 struct OpCold {
+    ColEntry cp[8];   // resolved output columns (not for ARRAY_BEGIN / LOADHIT, whose c[] are plain ints)
     int c[8];
     int s0, s1, w14, w15;
 };
@@ -430,8 +432,23 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         h.pg = pg >= 0 ? pg : 0;
         oph[k] = h;
         OpCold c;
+        const int otype = (int)w[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c.c[j] = (int)w[4 + j];
+        for (int j = 0; j < 8; ++j) {
+            const int col = (int)w[4 + j];
+            c.c[j] = col;
+            ColEntry e = 0ULL;
+            if (col >= 0 && otype != MXB_OP_ARRAY_BEGIN) {
+                const int idx = col >= MXB_COL_INIT ? col - MXB_COL_INIT : col;
+                const bool is_id = (otype == MXB_OP_COMMIT && j == 2);
+                if (is_id ? idx < MXB_MAX_I64_COLS : idx < MXB_MAX_F64_COLS) {
+                    const unsigned long long p = is_id ? (unsigned long long)P.cols.i64[idx]
+                                                       : (unsigned long long)P.cols.f64[idx];
+                    e = p ? (p | (col >= MXB_COL_INIT ? 1ULL : 0ULL)) : 0ULL;
+                }
+            }
+            c.cp[j] = e;
+        }
         c.s0 = (int)w[12];
         c.s1 = (int)w[13];
         c.w14 = (int)w[14];
@@ -470,22 +487,16 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         // array iteration state
         int arr_cur = 0, arr_end = 0, arr_nhit = 0, arr_pc = -1;
         bool arr_brute = false;
+        ctx.init_round = true;
         int row = 0;    // word offset of the current facet row (0 = the blob itself outside arrays)
         int geom = 0;   // word offset of the current geometry block
 
-        // leave the array at op `bpc`: photons that hit no facet initialise the columns the array creates
-        auto array_exit = [&](int bpc) {
-            const OpCold& ac = opc[bpc];
-            if (ctx.active && arr_nhit == 0) {
-                const Ref init = B + ac.s1;
-                for (int k = 0; k < ac.s0; ++k) {
-                    const int cr = init.i32(k);
-                    if (cr >= 0) P.cols.f64[cr][i] = kNaN; else P.cols.i64[-cr - 2][i] = -1LL;
-                }
-            }
+        // leave the array whose ARRAY_BEGIN is op `bpc`
+        auto array_exit = [&]() {
             arr_pc = -1;
             row = 0;
             ph.hit = false;
+            ctx.init_round = true;
         };
 
         int pc = 0;
@@ -509,7 +520,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     ph.hit = C.f64[c.c[0]][i] != 0.0;
                     ph.ip = V3{C.f64[c.c[1]][i], C.f64[c.c[2]][i], C.f64[c.c[3]][i]};
                     ph.l0 = C.f64[c.c[4]][i];
-                    ph.l1 = C.f64[c.c[5]][i];
+                    ph.l1 = C.f64[c.c[5]][i];   // (input columns: plain indices)
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
                 if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
@@ -517,11 +528,11 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             }
             case MXB_OP_COMMIT: {
                 const OpCold& c = opc[pc];
-                put(ctx, c.c[0], ph.hit, ph.l0);
-                put(ctx, c.c[1], ph.hit, ph.l1);
-                if (c.c[2] >= 0) {
+                put(ctx, c.cp[0], ph.hit, ph.l0);
+                put(ctx, c.cp[1], ph.hit, ph.l1);
+                if (c.cp[2] != 0ULL) {
                     const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
-                    put_id(ctx, c.c[2], ph.hit, idn);
+                    put_id(ctx, c.cp[2], ph.hit, idn);
                 }
                 if (ph.hit) ph.pos = ph.ip;
                 break;
@@ -538,15 +549,15 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 double a = 0, b = 0;
                 if (ph.hit) op_rscatter(ctx, ph, pr, c.s0, c.s1, a, b);
-                put(ctx, c.c[0], ph.hit, a);
-                put(ctx, c.c[1], ph.hit, b);
+                put(ctx, c.cp[0], ph.hit, a);
+                put(ctx, c.cp[1], ph.hit, b);
                 break;
             }
             case MXB_OP_GSCATTER: {
                 const OpCold& c = opc[pc];
                 double a = 0;
                 if (ph.hit) op_gscatter(ctx, ph, pr, c.s0, c.s1, a);
-                put(ctx, c.c[0], ph.hit, a);
+                put(ctx, c.cp[0], ph.hit, a);
                 break;
             }
             case MXB_OP_FILTER: {
@@ -561,17 +572,17 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 double order = 0, blaze = 0;
                 if (ph.hit) op_grating(ctx, ph, pr, B + geom, B + op.pg, op.flags, c.s0, order, blaze);
-                put(ctx, c.c[0], ph.hit, order);
-                put(ctx, c.c[1], ph.hit, blaze);
+                put(ctx, c.cp[0], ph.hit, order);
+                put(ctx, c.cp[1], ph.hit, blaze);
                 break;
             }
             case MXB_OP_DETPIX: {
                 // detector.py:73-75; pr: pixsize cp0 cp1; optional fused image: pg: nx ny sel_lo n_sel, s0 image slot
                 const OpCold& c = opc[pc];
-                const double px = ph.l0 / pr[0] + pr[1];
-                const double py = ph.l1 / pr[0] + pr[2];
-                put(ctx, c.c[0], ph.hit, px);
-                put(ctx, c.c[1], ph.hit, py);
+                const double px = div(ph.l0, pr[0]) + pr[1];
+                const double py = div(ph.l1, pr[0]) + pr[2];
+                put(ctx, c.cp[0], ph.hit, px);
+                put(ctx, c.cp[1], ph.hit, py);
                 if (c.s0 >= 0 && ph.hit) {
                     const Ref gp = B + op.pg;
                     const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
@@ -583,21 +594,21 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 // det_acis.py:31-58 ; per-facet pr: pixsize cp0 cp1 sh ct st ox oy ; global: f pixrad odet0 odet1 cosr sinr
                 const OpCold& c = opc[pc];
                 const Ref gp = B + op.pg;
-                const double chipx = ph.l0 / pr[0] + pr[1] + 1;
-                const double chipy = ph.l1 / pr[0] + pr[2] + 1;
+                const double chipx = div(ph.l0, pr[0]) + pr[1] + 1;
+                const double chipy = div(ph.l1, pr[0]) + pr[2] + 1;
                 const double tx = pr[3] * (pr[4] * (chipx - 0.5) + pr[5] * (chipy - 0.5)) + pr[6];
                 const double ty = pr[3] * (-pr[5] * (chipx - 0.5) + pr[4] * (chipy - 0.5)) + pr[7];
                 const double mn0 = ph.ip.x - gp[0];
-                const double x = ph.ip.y / mn0 / gp[1];
-                const double y = ph.ip.z / mn0 / gp[1];
-                put(ctx, c.c[0], ph.hit, chipx);
-                put(ctx, c.c[1], ph.hit, chipy);
-                put(ctx, c.c[2], ph.hit, tx);
-                put(ctx, c.c[3], ph.hit, ty);
-                put(ctx, c.c[4], ph.hit, gp[2] - x);
-                put(ctx, c.c[5], ph.hit, gp[3] + y);
-                put(ctx, c.c[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
-                put(ctx, c.c[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
+                const double x = div(div(ph.ip.y, mn0), gp[1]);
+                const double y = div(div(ph.ip.z, mn0), gp[1]);
+                put(ctx, c.cp[0], ph.hit, chipx);
+                put(ctx, c.cp[1], ph.hit, chipy);
+                put(ctx, c.cp[2], ph.hit, tx);
+                put(ctx, c.cp[3], ph.hit, ty);
+                put(ctx, c.cp[4], ph.hit, gp[2] - x);
+                put(ctx, c.cp[5], ph.hit, gp[3] + y);
+                put(ctx, c.cp[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
+                put(ctx, c.cp[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
                 if (c.s0 >= 0 && ph.hit) {
                     // fused detector image (chip pixel convention is 1-based: det_acis.py:33-34)
                     const long long idn = (long long)(B + row)[c.w15];
@@ -660,6 +671,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const Ref H = B + op.pg;
                 if (arr_pc != pc) {  // first round of this array for this photon
                     arr_pc = pc;
+                    ctx.init_round = true;    // the body's first pass initialises the columns it creates
                     arr_nhit = 0;
                     arr_brute = true;
                     arr_cur = 0;
@@ -672,7 +684,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                             arr_end = 0;  // NaN direction can never hit (k >= 0 is false)
                         } else if (dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn) {
                             const V3 O = ld3(H);
-                            const double t = ((O.x - ph.pos.x) * nb.x + (O.y - ph.pos.y) * nb.y + (O.z - ph.pos.z) * nb.z) / dn;
+                            const double t = ((O.x - ph.pos.x) * nb.x + (O.y - ph.pos.y) * nb.y + (O.z - ph.pos.z) * nb.z) * fast_rcp(dn);
                             const V3 q{ph.pos.x + t * ph.dir.x - O.x, ph.pos.y + t * ph.dir.y - O.y, ph.pos.z + t * ph.dir.z - O.z};
                             const double fu = (dot(q, ld3(H + 6)) - H[12]) * H[14];
                             const double fv = (dot(q, ld3(H + 9)) - H[13]) * H[14];
@@ -716,9 +728,17 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, found);
                 if (m == 0u) {
-                    // no lane found a facet: leave the array, skipping the body
-                    array_exit(pc);
-                    while ((oph[pc].type & (kRelBit - 1)) != MXB_OP_ARRAY_END) ++pc;
+                    // no lane found a facet: leave the array, skipping the body (c.w14 = pc of ARRAY_END)
+                    if (ctx.init_round && ctx.active) {
+                        // the body never ran for this warp: initialise the columns it would have created
+                        const Ref init = B + c.s1;
+                        for (int k = 0; k < c.s0; ++k) {
+                            const int cr = init.i32(k);
+                            if (cr >= 0) P.cols.f64[cr][i] = kNaN; else P.cols.i64[-cr - 2][i] = -1LL;
+                        }
+                    }
+                    array_exit();
+                    pc = c.w14;
                 } else if (lane0) {
                     atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
                 }
@@ -744,11 +764,12 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     }
                 }
                 // another search round only if some lane that hit still has facets to test
+                ctx.init_round = false;               // later rounds only store for photons that hit
                 if (__any_sync(0xffffffffu, ph.hit && arr_cur < arr_end)) {
                     if (!ph.hit) arr_cur = arr_end;   // lanes that found nothing are done with this array
                     pc = bpc - 1;                     // -> ARRAY_BEGIN (pc++ below)
                 } else {
-                    array_exit(bpc);
+                    array_exit();
                 }
                 break;
             }

@@ -241,8 +241,9 @@ class Lowering:
         if name not in self.existing and name not in self.initialised:
             self.initialised.add(name)
             if self.array is not None:
+                # the body's first pass initialises the column; the list serves warps whose
+                # lanes all miss the array (the body is skipped for them)
                 self.array['init'].append(idx if kind == 'f' else -idx - 2)
-                return idx
             return idx + COL_INIT
         return idx
 
@@ -391,7 +392,7 @@ class Lowering:
             if (rec['type'] in (OP['COMMIT'], OP['DETPIX']) and rec['flags'] & 1) or rec['type'] == OP['ACIS']:
                 rec['w15'] = 14 + nper
         self.array = None
-        self.op('ARRAY_END')
+        begin['w14'] = self.op('ARRAY_END')      # where to continue when no photon of a warp hits
         self.last_grid = grid
         return grid
 
@@ -470,7 +471,7 @@ class Program:
         for k, name in enumerate(self.out_f64):
             if name in self.aux:
                 t = self.aux[name]
-                if t.device != photons.device or t.dtype != torch.float64 or not t.is_contiguous():
+                if t.device.type != photons.device.type or t.dtype != torch.float64 or not t.is_contiguous():
                     raise ValueError('auxiliary buffer must be a contiguous float64 tensor on the photon device')
                 cols.f64[FIRST_OUT + k] = t.data_ptr()
                 continue
