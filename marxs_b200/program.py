@@ -225,6 +225,18 @@ class Lowering:
 
     # ---- columns ----------------------------------------------------------------
     def _col(self, name, kind):
+        a = self.array
+        if a is not None and a['facet'] > 0:
+            # facets after the first replay the column references of the template facet
+            ref = a['colrefs'][a['col_cursor']]
+            a['col_cursor'] += 1
+            return ref
+        ref = self._col_new(name, kind)
+        if a is not None:
+            a['colrefs'].append(ref)
+        return ref
+
+    def _col_new(self, name, kind):
         if name is None:
             return -1
         table = self.f64_cols if kind == 'f' else self.i64_cols
@@ -329,7 +341,7 @@ class Lowering:
     def begin_array(self):
         if self.array is not None:
             raise NotFusable('nested Parallel containers are not fused')
-        self.array = dict(facet=-1, body=[], rows=[], geoms=[], ids=[], slots=[], init=[],
+        self.array = dict(facet=-1, body=[], rows=[], geoms=[], ids=[], slots=[], init=[], colrefs=[],
                           begin=self.op('ARRAY_BEGIN'))
         # the ARRAY_BEGIN op itself is not part of the per-facet body
         self.array['body'] = []
@@ -342,6 +354,7 @@ class Lowering:
         a['geom_taken'] = False
         a['op_cursor'] = 0
         a['slot_cursor'] = 0
+        a['col_cursor'] = 0
         a['id_num'] = -9
 
     def end_facet(self):
