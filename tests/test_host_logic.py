@@ -1,0 +1,271 @@
+"""CPU tests of the host side: table facade, element API / error behaviour,
+lowering (program encoding), culling-grid conservativeness, slot order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import marxs_b200 as mb
+from marxs_b200 import optics, simulator, program, affines
+from marxs_b200.base import _parse_position_keywords
+from marxs_b200.missions import chandra
+from marxs_b200.missions.mitsnl import InterpolateEfficiencyTable, NonParallelCATGrating
+from marxs_b200.program import Lowering, OP, COL_INIT
+from oracle import marxs_oracle as mo
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+CORE = ['pos', 'dir', 'polarization', 'energy', 'probability']
+
+
+# ---- photon table facade -------------------------------------------------------
+def test_photonbatch_table_protocol():
+    p = mb.generate_test_photons(5, device='cpu')
+    assert p.colnames == ['pos', 'dir', 'energy', 'polarization', 'probability'] and len(p) == 5
+    assert p['pos'].shape == (5, 4) and p.storage('pos').shape == (4, 5)
+    p['pos'][:, 3] = 2.                       # writes through the (N, 4) view
+    assert torch.all(p.storage('pos')[3] == 2.)
+    mask = torch.tensor([True, False, True, False, False])
+    p['probability'][mask] = 0.               # reference idiom (catgrating.py:320-323)
+    assert p['probability'].tolist() == [0., 1., 0., 1., 1.]
+    p['pos'] = p['pos'] + 3. * p['dir']       # propagate idiom (simulator.py:640)
+    assert p['pos'][0, 0] == -2.
+    p['energy'] = 2                           # scalar broadcast (tests/test_simulator.py:12-18)
+    assert torch.all(p['energy'] == 2.)
+    q = p.copy()
+    q['energy'][0] = 5.
+    assert p['energy'][0] == 2.               # copy is deep
+    sub = p[mask]
+    assert len(sub) == 2 and sub['pos'].shape == (2, 4)
+    p.meta['X'] = 1
+    assert p.copy().meta['X'] == 1
+    assert float(p['energy'].mean()) == 2. and p['energy'].copy() is not p['energy']
+    out = p.to_numpy()
+    assert out['dir'].shape == (5, 4) and out['dir'].flags['C_CONTIGUOUS']
+    with pytest.raises(ValueError):
+        p['bad'] = np.zeros(3)
+
+
+def test_add_output_cols_defaults():
+    p = mb.generate_test_photons(3, device='cpu')
+    el = optics.FlatDetector(pixsize=0.1, id_col='CCD', id_num=2)
+    el.add_output_cols(p, ['a'])
+    assert torch.isnan(p['a']).all() and p['CCD'].dtype == torch.int64 and torch.all(p['CCD'] == -1)
+
+
+# ---- constructor / error behaviour of the reference -----------------------------
+def test_position_keywords():
+    with pytest.raises(ValueError):
+        _parse_position_keywords({'zoom': [1., 0., 1.]})
+    with pytest.raises(ValueError):
+        _parse_position_keywords({'pos4d': np.eye(4), 'position': [1, 2, 3]})
+    with pytest.raises(ValueError):
+        _parse_position_keywords({'pos4d': np.zeros((4, 4))})
+    p = _parse_position_keywords({'position': [1, 2, 3], 'zoom': 2.})
+    assert np.allclose(p, mo.compose([1, 2, 3], np.eye(3), [2, 2, 2]))
+    with pytest.raises(ValueError, match='not understood'):
+        optics.FlatDetector(pixsize=1., nonsense=3)
+    with pytest.raises(ValueError, match='Grating constant'):
+        optics.FlatGrating(order_selector=optics.OrderSelector([0]))
+    with pytest.raises(ValueError):
+        optics.OrderSelector([0, 1], p=[0.7, 0.7])
+    with pytest.raises(simulator.SimulationSetupError):
+        simulator.Sequence(elements=[5])
+
+
+def test_affines_roundtrip_and_conventions():
+    """math/tests/test_utils.py:7-28, simulator/tests/test_parallel.py:87-99 conventions."""
+    rng = np.random.default_rng(0)
+    R = affines.axangle2mat([1, 2, 3], 0.7)
+    A = affines.compose([1., -2., 3.], R, [2., 3., 4.])
+    T, R2, Z, S = affines.decompose44(A)
+    assert np.allclose(T, [1, -2, 3]) and np.allclose(R, R2) and np.allclose(Z, [2, 3, 4]) and np.allclose(S, 0)
+    T, R2, Z, S = mo.decompose44(A)
+    assert np.allclose(Z, [2, 3, 4])
+    assert np.allclose(affines.ex2vec_fix([0, 0, 1.], [0, 1., 0])[:, 0], [0, 0, 1])
+
+
+def test_detector_known_answers():
+    """optics/tests/test_detector.py:16-31"""
+    det = optics.FlatDetector(zoom=100., pixsize=0.5)
+    assert det.npix == [400, 400] and det.centerpix == [199.5, 199.5]
+
+
+def test_parallel_matches_oracle_and_golden():
+    pos = [[0, -10.1, -10.1], [0, .1, -10.1], [0, -10.1, .1], [0, .1, .1]]
+    det = simulator.Parallel(elem_class=optics.FlatDetector, elem_args={'pixsize': 0.01, 'zoom': 5},
+                             elem_pos={'position': pos}, id_col='CCD_ID')
+    assert [e.id_num for e in det.elements] == [0, 1, 2, 3]          # test_parallel.py:11-23
+    odet = mo.Parallel(mo.FlatDetector, {'position': pos}, {'pixsize': 0.01, 'zoom': 5}, id_col='CCD_ID')
+    for a, b in zip(det.elements, odet.elements):
+        assert np.array_equal(a.pos4d, b.pos4d)
+    g = dict(np.load(os.path.join(GOLD, 'chandra_c2.npz')))
+    hetg = chandra.HETG()
+    assert len(hetg.elements) == 336
+    np.testing.assert_allclose(np.array([e.pos4d for e in hetg.elements]), g['hetg_pos4d'], rtol=1e-14, atol=1e-12)
+    np.testing.assert_allclose([e.geometry['groove_angle'] for e in hetg.elements], g['hetg_groove'], rtol=1e-14)
+    np.testing.assert_allclose([e._d for e in hetg.elements], g['hetg_d'])
+    acis = chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])
+    np.testing.assert_allclose(np.array([e.pos4d for e in acis.elements]), g['acis_pos4d'], rtol=1e-14, atol=1e-12)
+    assert [e.id_num for e in acis.elements] == list(g['acis_id'])
+    # geometry is mutable: uncertainty + generate_elements moves the facets (tolerancing use case)
+    before = hetg.elements[5].pos4d.copy()
+    hetg.uncertainty = affines.translation2aff([0., 1., 0.])
+    hetg.generate_elements()
+    assert np.allclose(hetg.elements[5].pos4d[:3, 3] - before[:3, 3], [0., 1., 0.])
+
+
+def test_hetg_orientation_known_answers():
+    """missions/chandra/tests/test_hetg.py:6-38"""
+    hetg = chandra.HETG()
+    h = hetg.hess
+    for i, e in enumerate(hetg.elements):
+        ex, ey, ez = (e.geometry[k][:3] for k in ('e_x', 'e_y', 'e_z'))
+        assert abs(np.dot([h['xu'][i], h['yu'][i], h['zu'][i]], ex)) > 0.99
+        assert abs(np.dot([h['xuxf'][i], h['yuxf'][i], h['zuxf'][i]], ey)) > 0.99
+        assert abs(np.dot([h['xuyf'][i], h['yuyf'][i], h['zuyf'][i]], ez)) > 0.99
+        a, c, n = e.e_groove_coos(np.zeros((1, 2)))
+        assert abs(np.dot(a[0, :3], [h['xul'][i], h['yul'][i], h['zul'][i]])) > 0.99
+        assert abs(np.dot(c[0, :3], [h['xud'][i], h['yud'][i], h['zud'][i]])) > 0.99
+
+
+# ---- lowering -----------------------------------------------------------------------
+def lower(elems, cols=CORE, meta=None):
+    lw = Lowering(cols, meta=meta or {'ROLL_PNT': (0., '')})
+    for e in elems:
+        e._lower(lw)
+    return lw, lw.finish()
+
+
+def test_program_encoding_c2():
+    lw, prog = lower([chandra.HRMA(), chandra.HETG(),
+                      chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])])
+    b = prog.blob
+    assert int(b[0]) == program.MXB_MAGIC and int(b[2]) == prog.n_ops == 16 and int(b[3]) == b.size
+    assert prog.stage_words * 8 < program.MAX_STAGE_BYTES and prog.stage_words % 2 == 0
+    types = [o['type'] for o in prog.ops]
+    assert types == [OP['PLANE'], OP['COMMIT'], OP['LENS'], OP['COMMIT'], OP['RSCATTER'], OP['COMMIT'],
+                     OP['FILTER'], OP['COMMIT'], OP['ARRAY_BEGIN'], OP['GRATING'], OP['COMMIT'], OP['ARRAY_END'],
+                     OP['ARRAY_BEGIN'], OP['ACIS'], OP['COMMIT'], OP['ARRAY_END']]
+    # the 21 diagnostic columns of the reference
+    assert len(prog.out_f64) + len(prog.out_i64) == 21
+    assert prog.slot_kinds == ['normal', 'normal', 'uniform']
+    # same slot order as the oracle
+    orac = mo.Sequence([mo.chandra_hrma()])
+    assert mo.assign_slots(orac) == ['normal', 'normal']
+    begin = prog.ops[8]
+    F, stride, rows_off = begin['cols'][:3]
+    assert F == 336 and (stride // 2) % 2 == 1 and begin['w14'] == 11
+    rows = b[rows_off:rows_off + F * stride].reshape(F, stride)
+    np.testing.assert_array_equal(rows[:, :14], np.array([program.geom14(e.pos4d) for e in chandra.HETG().elements]))
+    assert list(rows[:, prog.ops[10]['w15']].astype(int)) == list(range(336))      # facet id_num per row
+    # 'y' is first written (and initialised) by the HRMA stack, later overwritten by ACIS sky y
+    ycol = prog.out_f64.index('y') + program.FIRST_OUT
+    assert prog.ops[1]['cols'][1 - 1] == ycol + COL_INIT and prog.ops[13]['cols'][7] == ycol
+    # a second run on a table that already has the columns initialises nothing
+    lw2, prog2 = lower([chandra.HRMA()], cols=CORE + prog.out_f64)
+    assert all(c < COL_INIT for o in prog2.ops for c in o['cols'])
+
+
+def test_parallel_with_per_facet_args_and_heterogeneous_fallback():
+    pos = {'position': [[0., -4., 0.], [-3., 2., 1.], [2., 4., -3.]]}
+    sel = optics.OrderSelector([-1, 0, 1])
+    par = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos=pos, id_col='facet',
+                             elem_args={'d': [2e-4, 3e-4, 2.5e-4], 'zoom': [1, 5., 6.], 'order_selector': sel})
+    lw, prog = lower([par])
+    assert [o['type'] for o in prog.ops] == [OP['ARRAY_BEGIN'], OP['GRATING'], OP['COMMIT'], OP['ARRAY_END']]
+    assert len(prog.slot_kinds) == 1            # one slot for the whole array, not per facet
+    # different selectors per facet cannot share one body: NotFusable -> caller falls back
+    par2 = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos=pos,
+                              elem_args={'d': 2e-4, 'order_selector': [optics.OrderSelector([0]),
+                                                                       optics.OrderSelector([1]),
+                                                                       optics.OrderSelector([2])]})
+    with pytest.raises(program.NotFusable):
+        lower([par2])
+
+
+def test_user_plugin_is_not_lowered():
+    """A subclass that overrides the Python hook must not silently run the parent's kernel."""
+    class MyGrating(optics.FlatGrating):
+        def specific_process_photons(self, photons, intersect, interpos, intercoos):
+            return {'probability': torch.ones(int(intersect.sum()), dtype=torch.float64) * 0.5}
+
+    g = MyGrating(d=1e-3, order_selector=optics.OrderSelector([0]))
+    assert not g._can_lower()
+    assert optics.FlatGrating(d=1e-3, order_selector=optics.OrderSelector([0]))._can_lower()
+    with pytest.raises(program.UnsupportedCallable):
+        lower([optics.FlatGrating(d=1e-3, order_selector=lambda e, p, b: (0, 1))])
+    with pytest.raises(program.UnsupportedCallable):
+        lower([optics.FlatGrating(d=lambda ic: 1e-3, order_selector=optics.OrderSelector([0]))])
+    f = optics.EnergyFilter(filterfunc=lambda en: en * 0 + 0.5)
+    assert not f._can_lower()                   # evaluated with torch on the device instead
+    seq = simulator.Sequence(elements=[optics.FlatDetector(pixsize=1.)], postprocess_steps=[simulator.KeepCol('pos')])
+    assert not seq._can_lower()                 # KeepCol must see the table after every element
+
+
+def test_selector_tables():
+    sel = optics.OrderSelector(np.arange(-2, 3), p=[.1, .2, .3, .2, .1])
+    blk, big = sel.device_table()
+    assert big is None and int(blk[0]) == program.SEL_ORDERSELECTOR and int(blk[1]) == 5
+    np.testing.assert_allclose(blk[3:8], mo.OrderSelector(np.arange(-2, 3), [.1, .2, .3, .2, .1]).cdf())
+    wave, theta = np.array([1., 2., 3.]), np.array([0.01, 0.02])
+    prob = np.random.default_rng(0).uniform(0, .1, (3, 2, 4))
+    iet = InterpolateEfficiencyTable(wave, theta, prob, [1, 0, -1, -2])
+    g = optics.CATGrating(d=2e-4, order_selector=iet)
+    lw, prog = lower([g])
+    sel_off = prog.ops[1]['pg']
+    tab_off = int(prog.blob[sel_off + 4])
+    assert tab_off >= prog.stage_words                     # the big table stays in global memory
+    np.testing.assert_array_equal(prog.blob[tab_off:tab_off + prob.size], prob.ravel())
+    tab = {'lambda': np.repeat(wave, 2), 'theta': np.tile(np.rad2deg(theta), 3)}
+    for k, o in enumerate([1, 0, -1, -2]):
+        tab[str(o)] = prob[:, :, k].ravel()
+    iet2 = InterpolateEfficiencyTable.from_table(tab)
+    np.testing.assert_allclose(iet2.prob, prob)
+    np.testing.assert_allclose(iet2.theta, theta)
+    assert NonParallelCATGrating(d=2e-4, order_selector=iet, d_blaze_mm=1e-3)._blaze_modifier() == (0, 1e-3)
+
+
+# ---- culling grid ---------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['hetg', 'random'])
+def test_cull_grid_is_conservative(case):
+    """Every facet a ray inside the validity cone hits (oracle arithmetic) is listed in its cell."""
+    rng = np.random.default_rng(5)
+    if case == 'hetg':
+        elems = chandra.HETG().elements
+    else:
+        F = 60
+        elems = [optics.FlatDetector(position=[rng.uniform(-5, 5), rng.uniform(-60, 60), rng.uniform(-60, 60)],
+                                     orientation=affines.axangle2mat(rng.normal(size=3), rng.uniform(0, 0.08)),
+                                     zoom=[1, rng.uniform(3, 9), rng.uniform(3, 9)]) for _ in range(F)]
+    G = np.array([program.geom14(e.pos4d) for e in elems])
+    g = program.build_cull_grid(G)
+    assert g is not None
+    n = 60000
+    # rays through random points of the array, directions inside the cone around nbar
+    target = G[rng.integers(0, len(G), n), :3] + rng.uniform(-20, 20, (n, 3))
+    tmax = np.sqrt(g['T2'])
+    t = rng.uniform(0, tmax, n) * 0.999
+    phi = rng.uniform(0, 2 * np.pi, n)
+    d = -(g['nbar'] + t[:, None] * (np.cos(phi)[:, None] * g['u'] + np.sin(phi)[:, None] * g['v']))
+    pos = np.ones((n, 4))
+    pos[:, :3] = target - d * rng.uniform(500, 900, n)[:, None]
+    dirs = np.zeros((n, 4))
+    dirs[:, :3] = d * rng.uniform(0.5, 2, n)[:, None]
+    dn = dirs[:, :3] @ g['nbar']
+    tt = ((g['O'] - pos[:, :3]) @ g['nbar']) / dn
+    q = pos[:, :3] + tt[:, None] * dirs[:, :3] - g['O']
+    fu = (q @ g['u'] - g['u0']) * g['inv_cell']
+    fv = (q @ g['v'] - g['v0']) * g['inv_cell']
+    inside = (fu >= 0) & (fv >= 0) & (fu < g['nu']) & (fv < g['nv'])
+    cell = np.where(inside, fv.astype(int) * g['nu'] + fu.astype(int), 0)
+    nhit = 0
+    for j in range(len(G)):
+        hit, _, _ = mo.plane_intersect(mo.PlaneConsts(elems[j].pos4d), dirs, pos)
+        for i in np.nonzero(hit)[0]:
+            assert inside[i]
+            lst = g['cand'][g['start'][cell[i]]:g['start'][cell[i] + 1]]
+            assert j in lst
+            nhit += 1
+    assert nhit > 5000
+    assert g['mean_candidates'] < 6
