@@ -355,6 +355,9 @@ def run_engine(args):
                    ms_per_step=1e3 * e2e_s / ke,
                    api='marxs_b200.host.trace_host -> mxb_trace_host (pinned host SoA planes, chunked 3-stream pipeline)')
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -379,7 +382,7 @@ def run_engine(args):
         pool = CpuPool()
         line['cpu_baseline'] = cpu_baseline_block(pool, args.cpu_steps)
         pool.close()
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
