@@ -102,8 +102,11 @@ MXB_DEV double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); } 
 template <typename P>
 MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V3& ip, double& l0,
                              double& l1, bool* rect_ok = nullptr) {
-    const double cx = g[0], cy = g[1], cz = g[2];
-    const double ex = g[3], ey = g[4], ez = g[5];
+    // 14 doubles as seven 16-byte loads (parameter blocks and facet rows are 16-byte aligned)
+    const double2 g01 = g.ld2(0), g23 = g.ld2(1), g45 = g.ld2(2), g67 = g.ld2(3), g89 = g.ld2(4),
+                  gab = g.ld2(5), gcd = g.ld2(6);
+    const double cx = g01.x, cy = g01.y, cz = g23.x;
+    const double ex = g23.y, ey = g45.x, ez = g45.y;
     const double k_num = (cx - pos.x) * ex + (cy - pos.y) * ey + (cz - pos.z) * ez;
     const double k_den = dir.x * ex + dir.y * ey + dir.z * ez;
     const double k = div(k_num, k_den);
@@ -111,11 +114,11 @@ MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V
     ip.y = pos.y + k * dir.y;
     ip.z = pos.z + k * dir.z;
     const double vx = ip.x - cx, vy = ip.y - cy, vz = ip.z - cz;
-    l0 = vx * g[6] + vy * g[7] + vz * g[8];
-    l1 = vx * g[9] + vy * g[10] + vz * g[11];
-    bool hit = (k_den != 0.0) && (k >= 0.0) && (fabs(l0) <= g[12]) && (fabs(l1) <= g[13]);
+    l0 = vx * g67.x + vy * g67.y + vz * g89.x;
+    l1 = vx * g89.y + vy * gab.x + vz * gab.y;
+    bool hit = (k_den != 0.0) & (k >= 0.0) & (fabs(l0) <= gcd.x) & (fabs(l1) <= gcd.y);
     if (rect_ok) *rect_ok = hit;
-    if (circular) hit = hit && (sqrt(l0 * l0 + l1 * l1) <= 1.0);
+    if (circular) hit = hit & (sqrt(l0 * l0 + l1 * l1) <= 1.0);
     return hit;
 }
 

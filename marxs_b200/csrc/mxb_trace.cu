@@ -97,6 +97,10 @@ struct PRef {
         return __ldg(g + off + k);
     }
     __device__ __forceinline__ PRef operator+(int k) const { return PRef{g, off + k}; }
+    __device__ __forceinline__ double2 ld2(int k) const {  // words 2k, 2k+1 (off must be even)
+        if (STAGED) return reinterpret_cast<const double2*>(g_smem + off)[k];
+        return __ldg(reinterpret_cast<const double2*>(g + off) + k);
+    }
     __device__ __forceinline__ int i32(int k) const {  // packed int32 view of the words at off
         if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
         return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
@@ -146,14 +150,12 @@ __device__ __forceinline__ double draw(const Ctx& c, int slot, int kind) {
 typedef unsigned long long ColEntry;
 
 __device__ __forceinline__ void put(const Ctx& c, ColEntry e, bool hit, double v) {
-    if (e != 0ULL && c.active && (hit || ((e & 1ULL) && c.init_round))) {
-        reinterpret_cast<double*>(e & ~7ULL)[c.i] = hit ? v : __longlong_as_double(0x7ff8000000000000LL);
-    }
+    const bool doit = (e != 0ULL) & c.active & (hit | (((e & 1ULL) != 0ULL) & c.init_round));
+    if (doit) reinterpret_cast<double*>(e & ~7ULL)[c.i] = hit ? v : __longlong_as_double(0x7ff8000000000000LL);
 }
 __device__ __forceinline__ void put_id(const Ctx& c, ColEntry e, bool hit, long long v) {
-    if (e != 0ULL && c.active && (hit || ((e & 1ULL) && c.init_round))) {
-        reinterpret_cast<long long*>(e & ~7ULL)[c.i] = hit ? v : -1LL;
-    }
+    const bool doit = (e != 0ULL) & c.active & (hit | (((e & 1ULL) != 0ULL) & c.init_round));
+    if (doit) reinterpret_cast<long long*>(e & ~7ULL)[c.i] = hit ? v : -1LL;
 }
 
 // optics/base.py:43-47: probability factors multiply and must lie in [0,1]
@@ -392,6 +394,8 @@ struct OpCold {
     int s0, s1, w14, w15;
 };
 constexpr int kRelBit = 1 << 20;
+constexpr int kCommitBit = 256;     // flags: a COMMIT is folded into this op (columns c5..c7)
+constexpr int kCommitRowId = 512;   // flags: its id_num comes from the facet row (word w15)
 
 template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -440,7 +444,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             ColEntry e = 0ULL;
             if (col >= 0 && otype != MXB_OP_ARRAY_BEGIN) {
                 const int idx = col >= MXB_COL_INIT ? col - MXB_COL_INIT : col;
-                const bool is_id = (otype == MXB_OP_COMMIT && j == 2);
+                const bool is_id = (otype == MXB_OP_COMMIT && j == 2) || (otype != MXB_OP_COMMIT && j == 7 && (((int)w[1]) & kCommitBit));
                 if (is_id ? idx < MXB_MAX_I64_COLS : idx < MXB_MAX_F64_COLS) {
                     const unsigned long long p = is_id ? (unsigned long long)P.cols.i64[idx]
                                                        : (unsigned long long)P.cols.f64[idx];
@@ -776,6 +780,17 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             default:
                 break;
             }
+            if (op.flags & kCommitBit) {
+                // optics/base.py:201-209 folded into the element's op: c5,c6 loc-coos columns, c7 id column
+                const OpCold& c = opc[pc];
+                put(ctx, c.cp[5], ph.hit, ph.l0);
+                put(ctx, c.cp[6], ph.hit, ph.l1);
+                if (c.cp[7] != 0ULL) {
+                    const long long idn = (op.flags & kCommitRowId) ? (long long)(B + row)[c.w15] : (long long)c.w14;
+                    put_id(ctx, c.cp[7], ph.hit, idn);
+                }
+                if (ph.hit) ph.pos = ph.ip;
+            }
             ++pc;
         }
 
@@ -802,6 +817,7 @@ namespace {
 
 struct Geom14 {
     double g[14];
+    __device__ __forceinline__ double2 ld2(int k) const { return make_double2(g[2 * k], g[2 * k + 1]); }
 };
 
 __global__ void __launch_bounds__(256)
@@ -815,7 +831,7 @@ plane_intersect_kernel(const __grid_constant__ Geom14 G, int circular, const dou
         V3 ip;
         double a0, a1;
         bool rect;
-        const bool h = plane_intersect(G.g, V3{px[i], py[i], pz[i]}, V3{dx[i], dy[i], dz[i]}, circular != 0,
+        const bool h = plane_intersect(G, V3{px[i], py[i], pz[i]}, V3{dx[i], dy[i], dz[i]}, circular != 0,
                                        ip, a0, a1, &rect);
         hit[i] = h ? 1 : 0;
         // geometry.py:254-259 NaN fill uses the rectangle mask (CircularHole narrows it afterwards)

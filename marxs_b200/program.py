@@ -158,6 +158,7 @@ class Lowering:
         self.meta_updates = OrderedDict()
         self.needs_pos = False            # an aperture creates the pos column
         self.aux = OrderedDict()          # name -> device tensor reached through an f64 pointer slot
+        self._no_fold = None
         self.image = None                 # (tensor, sel_lo) of the detector array being lowered
 
     # ---- transactions (an element that turns out not to be fusable is rolled back) ----
@@ -288,8 +289,14 @@ class Lowering:
         if a is not None and a['facet'] > 0:
             tmpl = a['body'][a['op_cursor']] if a['op_cursor'] < len(a['body']) else None
             a['op_cursor'] += 1
-            cmp = dict(rec)
-            if tmpl is None or any(cmp[k] != tmpl[k] for k in ('type', 'flags', 'pg', 'pf', 'cols', 's0', 's1', 'w14')):
+            mask = ~(self.COMMIT_BIT | self.COMMIT_ROW_ID)
+            same = (tmpl is not None and rec['type'] == tmpl['type'] and rec['flags'] == (tmpl['flags'] & mask)
+                    and all(rec[k] == tmpl[k] for k in ('pg', 'pf', 's0', 's1'))
+                    and (rec['cols'][:5] == tmpl['cols'][:5]))
+            folded = tmpl is not None and bool(tmpl['flags'] & self.COMMIT_BIT)
+            if same and not folded:
+                same = rec['cols'] == tmpl['cols'] and rec['w14'] == tmpl['w14']
+            if not same:
                 raise NotFusable('facets of a Parallel differ in more than per-facet parameters')
             return -1
         if len(self.ops) >= MAX_OPS:
@@ -315,13 +322,38 @@ class Lowering:
             return
         self.op('PLANE', flags=1 if circular else 0, pg=self.params(geom14(pos4d)))
 
+    FOLDABLE = ('PLANE', 'LENS', 'RSCATTER', 'GSCATTER', 'FILTER', 'GRATING', 'DETPIX', 'BREWSTER', 'MLEFF')
+    COMMIT_BIT, COMMIT_ROW_ID = 256, 512
+
     def commit(self, loc_names, id_col, id_num):
-        """loc-coos columns, id column, pos = interpos (optics/base.py:201-209)."""
+        """loc-coos columns, id column, pos = interpos (optics/base.py:201-209).  Folded into the
+        element's own op when that op has its last three column slots free (one dispatch less)."""
         c0 = self.fcol(loc_names[0]) if loc_names is not None else -1
         c1 = self.fcol(loc_names[1]) if loc_names is not None else -1
         c2 = self.icol(id_col) if id_col is not None else -1
-        if self.array is not None:
-            self.array['id_num'] = id_num
+        a = self.array
+        if a is not None:
+            a['id_num'] = id_num
+            if a['facet'] > 0:                       # replay the template facet's decision
+                folded = a['folds'][a['fold_cursor']]
+                a['fold_cursor'] += 1
+                if not folded:
+                    self.op('COMMIT', flags=1, cols=[c0, c1, c2], w15=0)
+                return
+        prev = self.ops[-1] if self.ops else None
+        foldable = (prev is not None and prev is not self._no_fold
+                    and prev['type'] in [OP[t] for t in self.FOLDABLE]
+                    and prev['cols'][5:8] == [-1, -1, -1] and not (prev['flags'] & self.COMMIT_BIT)
+                    and (a is None or (a['body'] and a['body'][-1] is prev)))
+        if a is not None:
+            a['folds'].append(bool(foldable))
+        if foldable:
+            prev['cols'][5:8] = [c0, c1, c2]
+            prev['flags'] |= self.COMMIT_BIT | (self.COMMIT_ROW_ID if a is not None else 0)
+            if a is None:
+                prev['w14'] = id_num
+            return
+        if a is not None:
             self.op('COMMIT', flags=1, cols=[c0, c1, c2], w15=0)   # w15 patched to the row's id offset
         else:
             self.op('COMMIT', cols=[c0, c1, c2], w14=id_num)
@@ -342,7 +374,7 @@ class Lowering:
         if self.array is not None:
             raise NotFusable('nested Parallel containers are not fused')
         self.array = dict(facet=-1, body=[], rows=[], geoms=[], ids=[], slots=[], init=[], colrefs=[],
-                          begin=self.op('ARRAY_BEGIN'))
+                          folds=[], begin=self.op('ARRAY_BEGIN'))
         # the ARRAY_BEGIN op itself is not part of the per-facet body
         self.array['body'] = []
 
@@ -355,6 +387,7 @@ class Lowering:
         a['op_cursor'] = 0
         a['slot_cursor'] = 0
         a['col_cursor'] = 0
+        a['fold_cursor'] = 0
         a['id_num'] = -9
 
     def end_facet(self):
@@ -402,7 +435,8 @@ class Lowering:
         begin['s0'], begin['s1'] = len(init), init_off
         for rec in a['body']:
             # ops that need the facet's id_num read it from the last word of the row
-            if (rec['type'] in (OP['COMMIT'], OP['DETPIX']) and rec['flags'] & 1) or rec['type'] == OP['ACIS']:
+            if ((rec['type'] in (OP['COMMIT'], OP['DETPIX']) and rec['flags'] & 1) or rec['type'] == OP['ACIS']
+                    or rec['flags'] & self.COMMIT_ROW_ID):
                 rec['w15'] = 14 + nper
         self.array = None
         begin['w14'] = self.op('ARRAY_END')      # where to continue when no photon of a warp hits

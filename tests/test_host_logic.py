@@ -141,27 +141,28 @@ def test_program_encoding_c2():
     lw, prog = lower([chandra.HRMA(), chandra.HETG(),
                       chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])])
     b = prog.blob
-    assert int(b[0]) == program.MXB_MAGIC and int(b[2]) == prog.n_ops == 16 and int(b[3]) == b.size
+    assert int(b[0]) == program.MXB_MAGIC and int(b[2]) == prog.n_ops == 11 and int(b[3]) == b.size
     assert prog.stage_words * 8 < program.MAX_STAGE_BYTES and prog.stage_words % 2 == 0
     types = [o['type'] for o in prog.ops]
-    assert types == [OP['PLANE'], OP['COMMIT'], OP['LENS'], OP['COMMIT'], OP['RSCATTER'], OP['COMMIT'],
-                     OP['FILTER'], OP['COMMIT'], OP['ARRAY_BEGIN'], OP['GRATING'], OP['COMMIT'], OP['ARRAY_END'],
-                     OP['ARRAY_BEGIN'], OP['ACIS'], OP['COMMIT'], OP['ARRAY_END']]
+    # the COMMIT of each element is folded into its own op (flag 256) except after ACIS (8 columns used)
+    assert types == [OP['PLANE'], OP['LENS'], OP['RSCATTER'], OP['FILTER'], OP['ARRAY_BEGIN'], OP['GRATING'],
+                     OP['ARRAY_END'], OP['ARRAY_BEGIN'], OP['ACIS'], OP['COMMIT'], OP['ARRAY_END']]
+    assert all(prog.ops[k]['flags'] & 256 for k in (0, 1, 2, 3, 5))
     # the 21 diagnostic columns of the reference
     assert len(prog.out_f64) + len(prog.out_i64) == 21
     assert prog.slot_kinds == ['normal', 'normal', 'uniform']
     # same slot order as the oracle
     orac = mo.Sequence([mo.chandra_hrma()])
     assert mo.assign_slots(orac) == ['normal', 'normal']
-    begin = prog.ops[8]
+    begin = prog.ops[4]
     F, stride, rows_off = begin['cols'][:3]
-    assert F == 336 and (stride // 2) % 2 == 1 and begin['w14'] == 11
+    assert F == 336 and (stride // 2) % 2 == 1 and begin['w14'] == 6
     rows = b[rows_off:rows_off + F * stride].reshape(F, stride)
     np.testing.assert_array_equal(rows[:, :14], np.array([program.geom14(e.pos4d) for e in chandra.HETG().elements]))
-    assert list(rows[:, prog.ops[10]['w15']].astype(int)) == list(range(336))      # facet id_num per row
+    assert list(rows[:, prog.ops[5]['w15']].astype(int)) == list(range(336))       # facet id_num per row
     # 'y' is first written (and initialised) by the HRMA stack, later overwritten by ACIS sky y
     ycol = prog.out_f64.index('y') + program.FIRST_OUT
-    assert prog.ops[1]['cols'][1 - 1] == ycol + COL_INIT and prog.ops[13]['cols'][7] == ycol
+    assert prog.ops[0]['cols'][5] == ycol + COL_INIT and prog.ops[8]['cols'][7] == ycol
     # a second run on a table that already has the columns initialises nothing
     lw2, prog2 = lower([chandra.HRMA()], cols=CORE + prog.out_f64)
     assert all(c < COL_INIT for o in prog2.ops for c in o['cols'])
@@ -173,7 +174,7 @@ def test_parallel_with_per_facet_args_and_heterogeneous_fallback():
     par = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos=pos, id_col='facet',
                              elem_args={'d': [2e-4, 3e-4, 2.5e-4], 'zoom': [1, 5., 6.], 'order_selector': sel})
     lw, prog = lower([par])
-    assert [o['type'] for o in prog.ops] == [OP['ARRAY_BEGIN'], OP['GRATING'], OP['COMMIT'], OP['ARRAY_END']]
+    assert [o['type'] for o in prog.ops] == [OP['ARRAY_BEGIN'], OP['GRATING'], OP['ARRAY_END']]
     assert len(prog.slot_kinds) == 1            # one slot for the whole array, not per facet
     # different selectors per facet cannot share one body: NotFusable -> caller falls back
     par2 = simulator.Parallel(elem_class=optics.FlatGrating, elem_pos=pos,
@@ -213,7 +214,7 @@ def test_selector_tables():
     iet = InterpolateEfficiencyTable(wave, theta, prob, [1, 0, -1, -2])
     g = optics.CATGrating(d=2e-4, order_selector=iet)
     lw, prog = lower([g])
-    sel_off = prog.ops[1]['pg']
+    sel_off = [o for o in prog.ops if o['type'] == OP['GRATING']][0]['pg']
     tab_off = int(prog.blob[sel_off + 4])
     assert tab_off >= prog.stage_words                     # the big table stays in global memory
     np.testing.assert_array_equal(prog.blob[tab_off:tab_off + prob.size], prob.ravel())
