@@ -202,11 +202,17 @@ class Lowering:
     def params_with_table(self, values, index, table):
         """Like ``params`` but ``values[index]`` receives the absolute offset of
         ``table``, a large array kept in global memory only (patched at finish)."""
-        self.big.append(np.ascontiguousarray(table, dtype=np.float64).ravel())
+        tab = np.ascontiguousarray(table, dtype=np.float64).ravel()
         vals = np.array(values, dtype=np.float64).ravel()
+        vals[index] = -1.0
+        key = (vals.tobytes(), hash(tab.tobytes()), tab.size)
+        if key in self._dedupe:
+            return self._dedupe[key]
+        self.big.append(tab)
         vals[index] = -1000.0 - (len(self.big) - 1)      # unique placeholder keeps de-duplication honest
         off = self.params(vals)
         self.fixups.append((off + index, len(self.big) - 1))
+        self._dedupe[key] = off
         return off
 
     # ---- draw slots -----------------------------------------------------------
