@@ -138,6 +138,7 @@ int         mxb_version(void);
 const char* mxb_build_info(void);       /* "sm_100a fmad=on ..." */
 const char* mxb_last_error(void);       /* thread-local message of the last failing call */
 int         mxb_device_count(void);
+void        mxb_host_release(void);      /* free the staging buffers mxb_trace_host caches per host thread */
 
 /* Run a lowered element program over n photons resident on the current device.
  * prog_dev: device pointer to the program blob (prog_words 64-bit words).

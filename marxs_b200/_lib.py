@@ -60,6 +60,7 @@ def load(strict=None):
     lib.mxb_build_info.restype = ctypes.c_char_p
     lib.mxb_last_error.restype = ctypes.c_char_p
     lib.mxb_device_count.restype = ci
+    lib.mxb_host_release.restype = None
     lib.mxb_trace.restype = ci
     lib.mxb_trace.argtypes = [vp, sz, vp, ctypes.POINTER(MxbColumns), i64, i64, u64, vp, vp]
     lib.mxb_trace_host.restype = ci
@@ -81,5 +82,5 @@ def check(lib, rc, what):
         raise MxbError('{0} failed ({1}): {2}'.format(what, rc, lib.mxb_last_error().decode()))
 
 
-EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_trace',
+EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
                     'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d']

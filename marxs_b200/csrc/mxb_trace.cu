@@ -253,8 +253,8 @@ __device__ __forceinline__ double select_order(PP sel, const double* gprog, doub
         const int n = (int)sel[1];
         psel = sel[2];
         PP cdf = sel + 3;
-        int idx = 0;
-        while (idx < n - 1 && cdf[idx] <= u) ++idx;  // searchsorted(cdf, u, 'right')
+        int idx = 0;   // searchsorted(cdf, u, 'right') = number of entries <= u (clamped), branch-free
+        for (int k = 0; k < n - 1; ++k) idx += (cdf[k] <= u) ? 1 : 0;
         return sel[3 + n + idx];
     } else if (kind == MXB_SEL_EFFFILE) {
         const int nE = (int)sel[1], nO = (int)sel[2];
@@ -972,6 +972,38 @@ int launch_trace(const double* prog_dev, int n_ops, int stage_words, const MxbCo
     return MXB_OK;
 }
 
+// cached staging state of mxb_trace_host (one per host thread)
+struct HostStage {
+    int dev = -1;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[3] = {}, ev_k[3] = {}, ev_out[3] = {};
+    double* dprog = nullptr;
+    size_t prog_bytes = 0;
+    unsigned long long* dstatus = nullptr;
+    char* dbuf[3] = {nullptr, nullptr, nullptr};
+    size_t buf_bytes = 0;
+    void release() {
+        if (s_in) {
+            for (int b = 0; b < 3; ++b) {
+                cudaEventDestroy(ev_in[b]);
+                cudaEventDestroy(ev_k[b]);
+                cudaEventDestroy(ev_out[b]);
+            }
+            cudaStreamDestroy(s_in);
+            cudaStreamDestroy(s_k);
+            cudaStreamDestroy(s_out);
+        }
+        for (int b = 0; b < 3; ++b) if (dbuf[b]) cudaFree(dbuf[b]);
+        if (dprog) cudaFree(dprog);
+        if (dstatus) cudaFree(dstatus);
+        *this = HostStage();
+    }
+};
+HostStage& host_stage() {
+    static thread_local HostStage s;
+    return s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -987,6 +1019,8 @@ const char* mxb_build_info(void) {
 }
 
 const char* mxb_last_error(void) { return g_last_error.c_str(); }
+
+void mxb_host_release(void) { host_stage().release(); }
 
 int mxb_device_count(void) {
     int n = 0;
@@ -1075,12 +1109,9 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
     for (int k = 0; k < MXB_MAX_SLOTS; ++k) if (host_in->draws[k]) didx[nd++] = k;
     const size_t planes = (size_t)nf + ni + nd;
 
-    double* dprog = nullptr;
-    unsigned long long* dstatus = nullptr;
-    char* dbuf[NBUF] = {nullptr, nullptr, nullptr};
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[NBUF], ev_k[NBUF], ev_out[NBUF];
-    bool ev_ok = false;
+    // device staging (program copy, status block, NBUF chunk buffers, streams, events) is cached per
+    // host thread and device and only grows: repeated calls do no cudaMalloc / cudaFree
+    HostStage& S = host_stage();
     int result = MXB_OK;
 #define HTRY(expr)                                                                              \
     do {                                                                                        \
@@ -1090,32 +1121,52 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             goto cleanup;                                                                       \
         }                                                                                       \
     } while (0)
-
-    HTRY(cudaMalloc(&dprog, prog_words * 8));
-    HTRY(cudaMalloc(&dstatus, sizeof(unsigned long long) * MXB_STATUS_WORDS));
-    HTRY(cudaMemset(dstatus, 0, sizeof(unsigned long long) * MXB_STATUS_WORDS));
-    HTRY(cudaMemcpy(dprog, prog_host, prog_words * 8, cudaMemcpyHostToDevice));
-    for (int b = 0; b < NBUF; ++b) HTRY(cudaMalloc(&dbuf[b], planes * (size_t)chunk * 8));
-    HTRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    HTRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    HTRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int b = 0; b < NBUF; ++b) {
-        HTRY(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
-        HTRY(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
-        HTRY(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
-    }
-    ev_ok = true;
     {
+        int dev = 0;
+        HTRY(cudaGetDevice(&dev));
+        if (S.dev != dev) { S.release(); S.dev = dev; }
+        if (!S.s_in) {
+            HTRY(cudaStreamCreateWithFlags(&S.s_in, cudaStreamNonBlocking));
+            HTRY(cudaStreamCreateWithFlags(&S.s_k, cudaStreamNonBlocking));
+            HTRY(cudaStreamCreateWithFlags(&S.s_out, cudaStreamNonBlocking));
+            for (int b = 0; b < NBUF; ++b) {
+                HTRY(cudaEventCreateWithFlags(&S.ev_in[b], cudaEventDisableTiming));
+                HTRY(cudaEventCreateWithFlags(&S.ev_k[b], cudaEventDisableTiming));
+                HTRY(cudaEventCreateWithFlags(&S.ev_out[b], cudaEventDisableTiming));
+            }
+            HTRY(cudaMalloc(&S.dstatus, sizeof(unsigned long long) * MXB_STATUS_WORDS));
+        }
+        if (S.prog_bytes < prog_words * 8) {
+            if (S.dprog) HTRY(cudaFree(S.dprog));
+            S.dprog = nullptr;
+            HTRY(cudaMalloc(&S.dprog, prog_words * 8));
+            S.prog_bytes = prog_words * 8;
+        }
+        const size_t need = planes * (size_t)chunk * 8;
+        if (S.buf_bytes < need) {
+            for (int b = 0; b < NBUF; ++b) {
+                if (S.dbuf[b]) HTRY(cudaFree(S.dbuf[b]));
+                S.dbuf[b] = nullptr;
+            }
+            S.buf_bytes = 0;
+            for (int b = 0; b < NBUF; ++b) HTRY(cudaMalloc(&S.dbuf[b], need));
+            S.buf_bytes = need;
+        }
+        cudaStream_t s_in = S.s_in, s_k = S.s_k, s_out = S.s_out;
+        double* dprog = S.dprog;
+        unsigned long long* dstatus = S.dstatus;
+        HTRY(cudaMemsetAsync(dstatus, 0, sizeof(unsigned long long) * MXB_STATUS_WORDS, s_k));
+        HTRY(cudaMemcpyAsync(dprog, prog_host, prog_words * 8, cudaMemcpyHostToDevice, s_k));
         int64_t nchunks = (n + chunk - 1) / chunk;
         for (int64_t c = 0; c < nchunks; ++c) {
             const int b = (int)(c % NBUF);
             const int64_t off = c * chunk;
             const int64_t m = (off + chunk <= n) ? chunk : (n - off);
-            char* base = dbuf[b];
+            char* base = S.dbuf[b];
             MxbColumns dc;
             memset(&dc, 0, sizeof(dc));
             // buffer b is free once its previous D2H finished
-            if (c >= NBUF) HTRY(cudaStreamWaitEvent(s_in, ev_out[b], 0));
+            if (c >= NBUF) HTRY(cudaStreamWaitEvent(s_in, S.ev_out[b], 0));
             size_t p = 0;
             for (int k = 0; k < nf; ++k, ++p) {
                 dc.f64[fidx[k]] = reinterpret_cast<double*>(base + p * (size_t)chunk * 8);
@@ -1131,12 +1182,12 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
                 HTRY(cudaMemcpyAsync(d, host_in->draws[didx[k]] + off, (size_t)m * 8,
                                      cudaMemcpyHostToDevice, s_in));
             }
-            HTRY(cudaEventRecord(ev_in[b], s_in));
-            HTRY(cudaStreamWaitEvent(s_k, ev_in[b], 0));
+            HTRY(cudaEventRecord(S.ev_in[b], s_in));
+            HTRY(cudaStreamWaitEvent(s_k, S.ev_in[b], 0));
             rc = launch_trace(dprog, n_ops, stage_words, &dc, m, photon_id0 + off, seed, dstatus, s_k);
             if (rc) { result = rc; goto cleanup; }
-            HTRY(cudaEventRecord(ev_k[b], s_k));
-            HTRY(cudaStreamWaitEvent(s_out, ev_k[b], 0));
+            HTRY(cudaEventRecord(S.ev_k[b], s_k));
+            HTRY(cudaStreamWaitEvent(s_out, S.ev_k[b], 0));
             for (int k = 0; k < nf; ++k) {
                 if (!host_out->f64[fidx[k]]) continue;
                 if (fidx[k] == MXB_COL_ENERGY && host_out->f64[fidx[k]] == host_in->f64[fidx[k]])
@@ -1147,26 +1198,15 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             for (int k = 0; k < ni; ++k)
                 HTRY(cudaMemcpyAsync(host_out->i64[iidx[k]] + off, dc.i64[iidx[k]], (size_t)m * 8,
                                      cudaMemcpyDeviceToHost, s_out));
-            HTRY(cudaEventRecord(ev_out[b], s_out));
+            HTRY(cudaEventRecord(S.ev_out[b], s_out));
         }
         HTRY(cudaStreamSynchronize(s_out));
+        HTRY(cudaMemcpyAsync(status_host, dstatus, sizeof(unsigned long long) * MXB_STATUS_WORDS,
+                             cudaMemcpyDeviceToHost, s_k));
         HTRY(cudaStreamSynchronize(s_k));
-        HTRY(cudaMemcpy(status_host, dstatus, sizeof(unsigned long long) * MXB_STATUS_WORDS,
-                        cudaMemcpyDeviceToHost));
     }
 cleanup:
-    if (ev_ok)
-        for (int b = 0; b < NBUF; ++b) {
-            cudaEventDestroy(ev_in[b]);
-            cudaEventDestroy(ev_k[b]);
-            cudaEventDestroy(ev_out[b]);
-        }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_k) cudaStreamDestroy(s_k);
-    if (s_out) cudaStreamDestroy(s_out);
-    for (int b = 0; b < NBUF; ++b) if (dbuf[b]) cudaFree(dbuf[b]);
-    if (dprog) cudaFree(dprog);
-    if (dstatus) cudaFree(dstatus);
+    if (result != MXB_OK) { cudaDeviceSynchronize(); S.release(); }
 #undef HTRY
     return result;
 }
