@@ -122,6 +122,9 @@ def trace_host(instrument, table, out=None, draws=None, chunk=1 << 21, check=Tru
     lib = _lib.load()
     elements = instrument if isinstance(instrument, (list, tuple)) else [instrument]
     prog = program if program is not None else lower(elements, table.colnames, table.meta)
+    if prog.aux:
+        raise ValueError('fused device images (element.image) are not available on the host-buffer path: '
+                         'the image lives on the device; unset it or use the device API')
     dst = table if out is None else out
     if out is not None:
         for name in VECTORS:
