@@ -613,6 +613,40 @@ def test_config4_multilayer_polarimeter(mode):
     assert np.isfinite(want['det_x']).mean() > 0.3
 
 
+def test_host_buffer_path_matches_device_path(mode):
+    """mxb_trace_host (host SoA planes, chunked H2D / kernel / D2H pipeline, several chunks and a ragged
+    tail) gives exactly the device-resident result, with injected draws and with device Philox."""
+    mb = _mb()
+    from marxs_b200 import host as mhost
+    rng = np.random.default_rng(SEED + 14)
+    n = 50001
+    prod, orac = chandra_pair()
+    table = chandra_photons(rng, n)
+    draws = [rng.standard_normal(n), rng.standard_normal(n), rng.random(n)]
+    with mb.inject_draws(draws):
+        dev = prod(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    ht = mhost.HostPhotonTable.from_columns(table)
+    ht.meta['ROLL_PNT'] = (0., 'roll')
+    out, prog = mhost.trace_host(prod, ht, draws=draws, chunk=8192)
+    assert out is ht                                             # in place, like the reference
+    got = ht.to_numpy()
+    assert set(got.keys()) == set(dev.keys())
+    for c in dev:
+        assert np.array_equal(got[c], dev[c], equal_nan=True), c
+    # out-of-place with device RNG: same seed and global photon ids -> same photons as the device path
+    mb.set_seed(5)
+    dev2 = prod(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    mb.set_seed(5)
+    src = mhost.HostPhotonTable.from_columns(table)
+    src.meta['ROLL_PNT'] = (0., 'roll')
+    dst = mhost.HostPhotonTable(n)
+    mhost.trace_host(prod, src, out=dst, chunk=20000)
+    got2 = dst.to_numpy()
+    for c in ('facet', 'order', 'CCD_ID', 'chipx', 'dir', 'probability'):
+        assert np.array_equal(got2[c], dev2[c], equal_nan=True), c
+    assert np.array_equal(src['pos'], table['pos'])              # inputs untouched
+
+
 def test_fused_detector_image():
     """The image accumulated inside the trace kernel == mxb_hist2d on the output columns == numpy."""
     mb = _mb()
