@@ -272,7 +272,8 @@ def run_engine(args):
     inst = c2_instrument()
     # detector image fused into the trace kernel (input of the multi-GPU reduction epilogue)
     image = torch.zeros((6, 1024, 1024), dtype=torch.float64, device=device)
-    inst.elements[2].image = image
+    if not args.no_image:
+        inst.elements[2].image = image
 
     # one input copy per step (the trace is in place); outputs are shared
     base = synth_c2_device(n, 20261017 + rank, device)
@@ -322,6 +323,8 @@ def run_engine(args):
         ka[k].record()
         step(W + k)
         kb[k].record()
+        if args.isolate:
+            torch.cuda.synchronize(device)
     mdist.allreduce_images([image])          # the only collective: detector image over NVLink
     ev1.record()
     barrier()
@@ -377,7 +380,7 @@ def run_engine(args):
                               kernel='mxb_trace_kernel<true>', kernel_ms=kern_ms,
                               algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
                               note='fp64-pipe bound (see DESIGN.md): ~3.5k fp64 ops per photon'),
-                clocks=clocks, e2e=e2e, gpu_launches=K,
+                clocks=clocks, e2e=e2e, gpu_launches=K, kernel_path=lib.mxb_jit_info().decode(),
                 checks=dict(ccd_hit_fraction=hit_ccd, image_sum=img_sum, prob_range_errors=int(st[0]),
                             multi_hit=int(st[1]), brute_force_photons=int(st[2])))
     if world == 1 and not args.no_cpu:
@@ -399,6 +402,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-image', action='store_true', help='experiment: do not fuse the detector image')
+    ap.add_argument('--isolate', action='store_true', help='experiment: synchronise after every step')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 3
+#define MXB_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -40,6 +40,7 @@ extern "C" {
 #define MXB_ECUDA        -2   /* CUDA runtime error (see mxb_last_error)     */
 #define MXB_ENODEV       -3   /* no CUDA device                               */
 #define MXB_ETOOBIG      -4   /* program does not fit the staging limits      */
+#define MXB_EJIT         -5   /* kernel specialisation failed (NVRTC missing / compile error) */
 
 /* ---- fixed column slots in MxbColumns.f64 ------------------------------ */
 #define MXB_COL_POS_X   0
@@ -148,6 +149,25 @@ void        mxb_host_release(void);      /* free the staging buffers mxb_trace_h
 int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host,
               const MxbColumns* cols, int64_t n, int64_t photon_id0, uint64_t seed,
               unsigned long long* status_dev, void* stream);
+
+/* Kernel selection for mxb_trace / mxb_trace_host.  A program runs either on the op-list
+ * interpreter kernel or on a kernel specialised for the program's structure (compiled once with
+ * NVRTC for sm_100a, cached in memory and under $MXB_CACHE_DIR, default ~/.cache/marxs_b200).
+ * mode 0: interpreter only; 1 (default, "auto"): specialise launches of at least
+ * $MXB_JIT_MIN_PHOTONS photons (default 131072), interpreter below or when NVRTC is absent;
+ * 2: always specialise (errors are returned, no fallback); -1: back to $MXB_JIT (0 | auto | 1). */
+void        mxb_set_jit(int mode);
+int         mxb_get_jit(void);
+const char* mxb_jit_info(void);          /* which kernel the last mxb_trace of this thread launched */
+/* CUDA source of the specialised kernel of a program (for inspection): copies at most buf_len - 1
+ * bytes + NUL into buf and returns the full length, or a negative MXB_E* code. */
+long long   mxb_jit_source(const double* prog_host, size_t prog_words, const MxbColumns* cols,
+                           char* buf, size_t buf_len);
+
+/* Specialise and compile the kernel of a program without launching it (NVRTC only, no GPU needed):
+ * fills the on-disk kernel cache ($MXB_CACHE_DIR, default _jit_cache/ next to libmxb.so).  Only the
+ * NULL-ness of the pointers in cols matters.  Returns the cubin size or a negative MXB_E* code. */
+long long   mxb_jit_compile(const double* prog_host, size_t prog_words, const MxbColumns* cols);
 
 /* Same computation for HOST-resident columns (pinned for full speed, pageable works):
  * uploads the program, streams the photons through the device in chunks of `chunk`

@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 3
+MXB_ABI_VERSION = 4
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -71,10 +71,29 @@ def load(strict=None):
     lib.mxb_parallel_transport.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.mxb_hist2d.restype = ci
     lib.mxb_hist2d.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, ci, ctypes.c_double, ctypes.c_double, i64, ci, ci, vp, vp, vp]
+    lib.mxb_set_jit.restype = None
+    lib.mxb_set_jit.argtypes = [ci]
+    lib.mxb_get_jit.restype = ci
+    lib.mxb_jit_info.restype = ctypes.c_char_p
+    lib.mxb_jit_source.restype = ctypes.c_longlong
+    lib.mxb_jit_source.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), vp, sz]
+    lib.mxb_jit_compile.restype = ctypes.c_longlong
+    lib.mxb_jit_compile.argtypes = [vp, sz, ctypes.POINTER(MxbColumns)]
     if lib.mxb_version() != MXB_ABI_VERSION:
         raise MxbError('libmxb ABI {0} != python binding {1}: rebuild'.format(lib.mxb_version(), MXB_ABI_VERSION))
     _libs[path] = lib
     return lib
+
+
+def jit_source(program, cols, strict=None):
+    """CUDA source of the kernel libmxb specialises for ``program`` with the columns ``cols``."""
+    lib = load(strict)
+    n = lib.mxb_jit_source(program.blob.ctypes.data, program.blob.size, ctypes.byref(cols), None, 0)
+    if n < 0:
+        raise MxbError('mxb_jit_source failed ({0}): {1}'.format(n, lib.mxb_last_error().decode()))
+    buf = ctypes.create_string_buffer(n + 1)
+    lib.mxb_jit_source(program.blob.ctypes.data, program.blob.size, ctypes.byref(cols), buf, n + 1)
+    return buf.value.decode()
 
 
 def check(lib, rc, what):
@@ -83,4 +102,5 @@ def check(lib, rc, what):
 
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
-                    'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d']
+                    'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d',
+                    'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile']

@@ -6,8 +6,10 @@
 //   strict : nvcc -fmad=false              -> bit-identical to the oracle except libm calls
 //   fast   : nvcc -DMXB_FAST (fmad on)     -> FMA contraction + reciprocal-multiply normalisation
 #pragma once
-#include <cstdint>
+#include <stdint.h>      // NVRTC builds get a stand-in from mxb_jit.cpp
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 #define MXB_DEV __device__ __forceinline__
 

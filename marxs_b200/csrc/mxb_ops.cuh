@@ -1,0 +1,550 @@
+// mxb_ops.cuh — element physics and array search of the MARXS hot path, fp64, sm_100a.
+//
+// These are the op bodies.  Two kernels are built from them:
+//   * the interpreter (mxb_trace.cu: mxb_trace_kernel), which dispatches on the op list of a
+//     program blob at run time, and
+//   * the per-program specialised kernels (mxb_jit.cpp), whose straight-line driver is emitted
+//     from the same op list and compiled with NVRTC for sm_100a: offsets, flags, column
+//     presence and draw sources are compile-time constants there and single-element
+//     parameters are read from the kernel-parameter constant bank instead of shared memory.
+// Every body restates one reference routine (file:line cited), in the operation order of
+// oracle/marxs_oracle.py.  Random draws are ARGUMENTS: the caller decides between injected
+// per-photon arrays and the device Philox stream.
+#pragma once
+#ifdef __CUDACC_RTC__
+#include "mxb.h"
+#else
+#include "../../include/mxb.h"
+#endif
+#include "mxb_device.cuh"
+
+namespace mxb {
+
+// ---------------------------------------------------------------------------
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier
+// ---------------------------------------------------------------------------
+MXB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MXB_DEV void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+MXB_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+MXB_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+MXB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// parameter access.  PRef: word offsets into the staged program copy (shared memory, 32-bit
+// offsets -> LDS) or into the global blob when the program is too large to stage.
+// SRef: a block of kernel parameters (constant bank; offsets fold into the instruction).
+// ---------------------------------------------------------------------------
+extern __shared__ __align__(16) double g_smem[];
+
+template <bool STAGED>
+struct PRef {
+    const double* g;
+    int off;
+    MXB_DEV double operator[](int k) const {
+        if (STAGED) return g_smem[off + k];
+        return __ldg(g + off + k);
+    }
+    MXB_DEV PRef operator+(int k) const { return PRef{g, off + k}; }
+    MXB_DEV double2 ld2(int k) const {  // words 2k, 2k+1 (off must be even)
+        if (STAGED) return reinterpret_cast<const double2*>(g_smem + off)[k];
+        return __ldg(reinterpret_cast<const double2*>(g + off) + k);
+    }
+    MXB_DEV int i32(int k) const {  // packed int32 view of the words at off
+        if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
+        return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
+    }
+};
+
+struct SRef {
+    const double* s;
+    MXB_DEV double operator[](int k) const { return s[k]; }
+    MXB_DEV SRef operator+(int k) const { return SRef{s + k}; }
+    MXB_DEV double2 ld2(int k) const { return make_double2(s[2 * k], s[2 * k + 1]); }
+};
+
+// ---------------------------------------------------------------------------
+// per-thread photon state
+// ---------------------------------------------------------------------------
+struct Photon {
+    V3 pos, dir, pol;
+    double energy, prob;
+    V3 ip;          // intersection point of the current element
+    double l0, l1;  // local coordinates on the current element
+    bool hit;
+};
+
+MXB_DEV double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+MXB_DEV void st_global(double* p, double v) {
+    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+MXB_DEV void st_global(long long* p, long long v) {
+    asm volatile("st.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// optics/base.py:43-47: probability factors multiply and must lie in [0,1]
+MXB_DEV void mul_prob(unsigned long long* st_sm, Photon& ph, double f) {
+    if (f < 0.0 || f > 1.0) atomicAdd(&st_sm[MXB_ST_PROB_RANGE], 1ULL);
+    ph.prob *= f;
+}
+
+// draw source: injected per-photon array (tests, parity) or Philox keyed by (seed, photon id, slot)
+MXB_DEV double draw_value(const double* inj, long long i, unsigned long long seed, unsigned long long gid,
+                          int slot, int kind) {
+    if (inj) return inj[i];
+    return device_draw(seed, gid, slot, kind);
+}
+
+// ---------------------------------------------------------------------------
+// detector image accumulation.  A bright spot (zero order, a narrow line) sends a large fraction of
+// the batch into a handful of pixels; fp64 atomics on ONE address serialise in L2 (~1 ns each), which
+// costs more than the whole trace.  So: (1) lanes of a warp that hit the same pixel are summed with
+// shuffles and issue one atomic; (2) each CTA keeps a small direct-mapped cache of hot pixels in
+// shared memory - a pixel is admitted when two lanes of one warp coincide on it - and flushes it
+// once at the end of the kernel.  Cold pixels go straight to global memory.
+// ---------------------------------------------------------------------------
+#define MXB_HOT_SLOTS 512
+struct HotCache {
+    unsigned long long* keys;   // global address of the pixel, 0 = free
+    double* vals;
+};
+MXB_DEV void hot_init(HotCache hc, int tid, int nthreads) {
+    for (int k = tid; k < MXB_HOT_SLOTS; k += nthreads) {
+        hc.keys[k] = 0ULL;
+        hc.vals[k] = 0.0;
+    }
+}
+MXB_DEV void hot_flush(HotCache hc, int tid, int nthreads) {   // after a __syncthreads()
+    for (int k = tid; k < MXB_HOT_SLOTS; k += nthreads)
+        if (hc.keys[k]) atomicAdd(reinterpret_cast<double*>(hc.keys[k]), hc.vals[k]);
+}
+MXB_DEV void hot_add(HotCache hc, double* addr, double w) {
+    const unsigned long long key = (unsigned long long)addr;
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    double sum = w;
+    unsigned rest = peers & ~(1u << leader);
+    while (rest) {   // every lane of the group walks the same list
+        const int l = __ffs(rest) - 1;
+        sum += __shfl_sync(peers, w, l);
+        rest &= rest - 1;
+    }
+    if ((int)(threadIdx.x & 31) != leader) return;
+    const unsigned slot = (unsigned)(((key >> 3) * 0x9E3779B97F4A7C15ULL) >> 55) & (MXB_HOT_SLOTS - 1);
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&hc.keys[slot]);
+    if (cur == 0ULL && (peers & (peers - 1))) {   // free slot and the pixel looks hot: claim it
+        cur = atomicCAS(&hc.keys[slot], 0ULL, key);
+        if (cur == 0ULL) cur = key;
+    }
+    if (cur == key) atomicAdd(&hc.vals[slot], sum);
+    else atomicAdd(addr, sum);
+}
+
+// fused detector image: gp = nx ny sel_lo n_sel ; bin = round half to even like np.round
+template <typename PP>
+MXB_DEV void accumulate_image(HotCache hc, double* img, PP gp, long long idn, double px, double py, double w) {
+    const long long nx = (long long)gp[0], ny = (long long)gp[1];
+    const long long plane = idn - (long long)gp[2];
+    if (plane < 0 || plane >= (long long)gp[3] || !(px == px) || !(py == py) || !(w == w)) return;
+    const long long ix = llrint(px), iy = llrint(py);
+    if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) return;
+    hot_add(hc, &img[(plane * ny + iy) * nx + ix], w);
+}
+
+// ---------------------------------------------------------------------------
+// element physics (callers only invoke these for photons with ph.hit)
+// ---------------------------------------------------------------------------
+// mirror.py:53-82  params: P[3] f
+template <typename PP>
+MXB_DEV void op_lens(Photon& ph, PP p) {
+    const V3 nd = normalize(ph.dir);
+    const double f = p[3];
+    const V3 t{(p[0] + f * nd.x) - ph.ip.x, (p[1] + f * nd.y) - ph.ip.y, (p[2] + f * nd.z) - ph.ip.z};
+    const V3 nd2 = normalize(t);
+    ph.pol = parallel_transport(ph.dir, nd2, ph.pol);
+    ph.dir = nd2;
+}
+
+// scatter.py:49-77  params: center[3] sig_in sig_perp ; z0, z1 standard normal draws
+template <typename PP>
+MXB_DEV void op_rscatter(Photon& ph, PP p, double z0, double z1, double& a, double& b) {
+    const V3 radial{ph.pos.x - p[0], ph.pos.y - p[1], ph.pos.z - p[2]};
+    const V3 perp = cross(ph.dir, radial);
+    V3 out = ph.dir;
+    a = 0.0;
+    b = 0.0;
+    if (p[3] != 0.0) {
+        a = p[3] * z0;
+        out = axangle_rotate_T(perp, a, ph.dir);
+    }
+    if (p[4] != 0.0) {
+        b = p[4] * z1;
+        out = axangle_rotate_T(radial, b, out);
+    }
+    ph.pol = parallel_transport(ph.dir, out, ph.pol);
+    ph.dir = out;
+}
+// the two normals of op_rscatter: drawn only for non-zero widths; one Philox call when both come
+// from the device stream
+MXB_DEV void rscatter_draws(double sig_in, double sig_perp, const double* inj0, const double* inj1, long long i,
+                            unsigned long long seed, unsigned long long gid, int s0, int s1, double& z0,
+                            double& z1) {
+    z0 = 0.0;
+    z1 = 0.0;
+    if ((sig_in != 0.0) && (sig_perp != 0.0) && !inj0 && !inj1) {
+        device_draw_normal_pair(seed, gid, s0, z0, z1);
+    } else {
+        if (sig_in != 0.0) z0 = draw_value(inj0, i, seed, gid, s0, 1);
+        if (sig_perp != 0.0) z1 = draw_value(inj1, i, seed, gid, s1, 1);
+    }
+}
+
+// scatter.py:109-145  params: sigma ; zn standard normal, u uniform
+template <typename PP>
+MXB_DEV void op_gscatter(Photon& ph, PP p, double zn, double u, double& ang) {
+    const V3 pdir = normalize(ph.dir);
+    const V3 guess = (fabs(pdir.x) < 0.99999) ? V3{1, 0, 0} : V3{0, 1, 0};
+    const V3 perp = cross(pdir, guess);
+    ang = p[0] * zn;
+    V3 out = axangle_rotate_T(perp, ang, pdir);
+    const double ang2 = u * 2 * 3.141592653589793;
+    out = axangle_rotate_T(pdir, ang2, out);
+    ph.pol = parallel_transport(ph.dir, out, ph.pol);
+    ph.dir = out;
+}
+
+// filter.py:90-94  params: n, x[n], y[n]   (n == 0: constant y[0])
+template <typename PP>
+MXB_DEV double filter_value(unsigned long long* st_sm, PP p, double energy, int flags) {
+    const int n = (int)p[0];
+    if (n == 0) return p[1];
+    PP xp = p + 1;
+    PP fp = p + 1 + n;
+    if ((flags & 1) && (energy < xp[0] || energy > xp[n - 1]))
+        atomicAdd(&st_sm[MXB_ST_FILTER_BOUNDS], 1ULL);
+    return interp_clamped(xp, fp, n, energy);
+}
+
+// grating.py:12-57 OrderSelector with a compile-time order count (specialised kernels):
+// sel = kind n psum cdf[n] orders[n]
+template <int N, typename PP>
+MXB_DEV double select_order_fixed(PP sel, double u, double& psel) {
+    psel = sel[2];
+    int idx = 0;   // searchsorted(cdf, u, 'right'), clamped
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) idx += (sel[3 + k] <= u) ? 1 : 0;
+    double order = sel[3 + N];
+#pragma unroll
+    for (int k = 1; k < N; ++k) order = (idx == k) ? sel[3 + N + k] : order;
+    return order;
+}
+
+// grating.py:12-57, 60-96; mitsnl/catgrating.py:104-144.  Returns order, sets psel.
+template <typename PP>
+MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy, double blaze, double& psel) {
+    const int kind = (int)sel[0];
+    if (kind == MXB_SEL_ORDERSELECTOR) {
+        const int n = (int)sel[1];
+        psel = sel[2];
+        PP cdf = sel + 3;
+        int idx = 0;   // searchsorted(cdf, u, 'right') = number of entries <= u (clamped), branch-free
+        for (int k = 0; k < n - 1; ++k) idx += (cdf[k] <= u) ? 1 : 0;
+        return sel[3 + n + idx];
+    } else if (kind == MXB_SEL_EFFFILE) {
+        const int nE = (int)sel[1], nO = (int)sel[2];
+        PP en = sel + 3;
+        int ind = 0;
+        double best = fabs(en[0] - energy);
+        for (int k = 1; k < nE; ++k) {  // np.argmin: first minimum
+            const double d = fabs(en[k] - energy);
+            if (d < best) { best = d; ind = k; }
+        }
+        psel = sel[3 + nE + ind];
+        PP cum = sel + 3 + 2 * nE + nO + ind * nO;
+        int oi = 0;
+        for (int k = 0; k < nO; ++k)
+            if (cum[k] > u) { oi = k; break; }
+        return sel[3 + 2 * nE + oi];
+    } else {  // MXB_SEL_INTERPTABLE: bilinear, query clamped to the table (RectBivariateSpline k=1)
+        const int nw = (int)sel[1], nt = (int)sel[2], no = (int)sel[3];
+        const double* tab = gprog + (long long)sel[4];
+        PP wk = sel + 5;
+        PP tk = sel + 5 + nw;
+        PP ord = sel + 5 + nw + nt;
+        double xq = kHcKevNm / energy;
+        xq = fmin(fmax(xq, wk[0]), wk[nw - 1]);
+        double yq = fmin(fmax(blaze, tk[0]), tk[nt - 1]);
+        const int i = bracket(wk, nw, xq), j = bracket(tk, nt, yq);
+        const double tx = (xq - wk[i]) / (wk[i + 1] - wk[i]);
+        const double ty = (yq - tk[j]) / (tk[j + 1] - tk[j]);
+        const double* t00 = tab + ((long long)i * nt + j) * no;
+        const double* t10 = t00 + (long long)nt * no;
+        const double* t01 = t00 + no;
+        const double* t11 = t10 + no;
+        double total = 0.0;
+        for (int k = 0; k < no; ++k) {
+            const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
+            const double f0 = a00 + tx * (a10 - a00);
+            const double f1 = a01 + tx * (a11 - a01);
+            total = total + (f0 + ty * (f1 - f0));
+        }
+        psel = total;
+        double run = 0.0;
+        int oi = 0;
+        for (int k = 0; k < no; ++k) {
+            const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
+            const double f0 = a00 + tx * (a10 - a00);
+            const double f1 = a01 + tx * (a11 - a01);
+            run = run + (f0 + ty * (f1 - f0));
+            if (run / total > u) { oi = k; break; }   // argmax(cumprob > u): first True, 0 if none
+        }
+        return ord[oi];
+    }
+}
+
+// grating.py:233-277  params: l[3] dd[3] d blaze0 dblaze ; n = e_x of the geometry.
+// select(energy, blaze, psel) -> diffraction order (the caller binds the draw and the table)
+template <typename PP, typename GP, typename SELECT>
+MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, int flags, SELECT select,
+                        double& order, double& blaze) {
+    const V3 pn = normalize(ph.dir);
+    const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
+    const double wave = div(kEnergy2Wave, ph.energy);
+    const double p_l = dot(pn, l);
+    const V3 pp = normalize(V3{pn.x - p_l * l.x, pn.y - p_l * l.y, pn.z - p_l * l.z});
+    blaze = acos(clip01(fabs(dot(pp, n))));
+    if (flags & 4) blaze = blaze + (p[7] + ph.l0 * p[8]);  // NonParallelCATGrating blaze_angle_modifier
+    double psel;
+    order = select(ph.energy, blaze, psel);
+    const double p_dd = dot(pn, dd);
+    const double sign = (flags & 1) ? ((p_dd < 0.0) ? -1.0 : 1.0) : -1.0;  // CAT: grating.py:298-301
+    const double p_d = p_dd + div(sign * order * wave, p[6]);
+    const double p_n = sqrt(1. - p_d * p_d - p_l * p_l);
+    const double pdn = dot(pn, n);
+    double direction = (pdn > 0.0) ? 1.0 : ((pdn < 0.0) ? -1.0 : pdn);  // np.sign
+    if (flags & 2) direction = direction * -1;
+    const double q = direction * p_n;
+    const V3 nd{p_d * dd.x + p_l * l.x + q * n.x, p_d * dd.y + p_l * l.y + q * n.y,
+                p_d * dd.z + p_l * l.z + q * n.z};
+    ph.pol = parallel_transport(ph.dir, nd, ph.pol);
+    ph.dir = nd;
+    mul_prob(st_sm, ph, psel);
+}
+
+// multiLayerMirror.py:44-91  params: Pinv[9] P[9] ex[3]
+template <typename PP>
+MXB_DEV void op_brewster(unsigned long long* st_sm, Photon& ph, PP p) {
+    const V3 dh = normalize(ph.dir);
+    V3 loc{p[0] * dh.x + p[1] * dh.y + p[2] * dh.z, p[3] * dh.x + p[4] * dh.y + p[5] * dh.z,
+           p[6] * dh.x + p[7] * dh.y + p[8] * dh.z};
+    loc.x = loc.x * -1;
+    PP q = p + 9;
+    const V3 nd{q[0] * loc.x + q[1] * loc.y + q[2] * loc.z, q[3] * loc.x + q[4] * loc.y + q[5] * loc.z,
+                q[6] * loc.x + q[7] * loc.y + q[8] * loc.z};
+    const V3 ex = ld3(p + 18);
+    V3 v_s = cross(dh, ex);
+    const double nvs = sqrt(dot(v_s, v_s));
+    v_s = V3{v_s.x / nvs, v_s.y / nvs, v_s.z / nvs};
+    const V3 v_p = cross(dh, v_s);
+    const double pvs = dot(ph.pol, v_s), pvp = dot(ph.pol, v_p);
+    const double Es2 = 1. * (pvs * pvs), Ep2 = 0. * (pvp * pvp);
+    const double inten = Es2 + Ep2;
+    if (inten > 1.001) atomicAdd(&st_sm[MXB_ST_INTENSITY], 1ULL);
+    const V3 nvp = cross(nd, v_s);
+    const V3 np_{-Es2 * v_s.x + Ep2 * nvp.x, -Es2 * v_s.y + Ep2 * nvp.y, -Es2 * v_s.z + Ep2 * nvp.z};
+    const double nn = sqrt(dot(np_, np_));
+    ph.pol = V3{np_.x / nn, np_.y / nn, np_.z / nn};
+    ph.dir = nd;
+    mul_prob(st_sm, ph, clip01(inten));
+}
+
+// multiLayerMirror.py:132-170  params: Ly n_refl n_pol xs[nr] peak_lambda[nr] peak[nr] fwhm[nr] pol_e[np] pol[np]
+template <typename PP>
+MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
+    const double Ly = p[0];
+    const int nr = (int)p[1], npol = (int)p[2];
+    PP xs = p + 3;
+    PP pl = xs + nr;
+    PP pk = pl + nr;
+    PP fw = pk + nr;
+    PP pe = fw + nr;
+    PP pf = pe + npol;
+    const double wavelength = kHcMultilayer / ph.energy;
+    const double tested = interp_clamped(pe, pf, npol, ph.energy);
+    const double local_x = ph.l0 / Ly;
+    const double peak_w = interp_clamped(xs, pl, nr, local_x);
+    const double max_refl = interp_clamped(xs, pk, nr, local_x) / tested;
+    const double spread = interp_clamped(xs, fw, nr, local_x);
+    const double c2 = (spread * spread) / (8. * 0.6931471805599453);
+    double refl = 0.0;
+    if (c2 != 0.0) {
+        const double dw = wavelength - peak_w;
+        refl = max_refl * exp(-(dw * dw) / (2 * c2));
+    }
+    mul_prob(st_sm, ph, refl / 100);
+}
+
+// detector.py:73-75  pr: pixsize cp0 cp1
+template <typename PP>
+MXB_DEV void op_detpix(const Photon& ph, PP pr, double& px, double& py) {
+    px = div(ph.l0, pr[0]) + pr[1];
+    py = div(ph.l1, pr[0]) + pr[2];
+}
+
+// det_acis.py:31-58 + data.py:169-190 ; per-facet pr: pixsize cp0 cp1 sh ct st ox oy ;
+// global gp: f pixrad odet0 odet1 cosr sinr.  out: chipx chipy tdetx tdety detx dety x y
+template <typename PP, typename GP>
+MXB_DEV void op_acis(const Photon& ph, PP pr, GP gp, double out[8]) {
+    const double chipx = div(ph.l0, pr[0]) + pr[1] + 1;
+    const double chipy = div(ph.l1, pr[0]) + pr[2] + 1;
+    const double tx = pr[3] * (pr[4] * (chipx - 0.5) + pr[5] * (chipy - 0.5)) + pr[6];
+    const double ty = pr[3] * (-pr[5] * (chipx - 0.5) + pr[4] * (chipy - 0.5)) + pr[7];
+    const double mn0 = ph.ip.x - gp[0];
+    const double x = div(div(ph.ip.y, mn0), gp[1]);
+    const double y = div(div(ph.ip.z, mn0), gp[1]);
+    out[0] = chipx;
+    out[1] = chipy;
+    out[2] = tx;
+    out[3] = ty;
+    out[4] = gp[2] - x;
+    out[5] = gp[3] + y;
+    out[6] = gp[2] - x * gp[4] + y * gp[5];
+    out[7] = gp[3] + x * gp[5] + y * gp[4];
+}
+
+// aperture.py:42-78: params c[3] vy[3] vz[3] nex[3] phi0 dphi rin2 cum_lo cum_hi ; u0, u1 uniforms
+template <typename PP>
+MXB_DEV void op_aperture(unsigned long long* st_sm, Photon& ph, PP pr, int flags, double u0, double u1) {
+    double x, y;
+    if (flags & 1) {  // CircleAperture :138-146
+        const double phi = pr[12] + pr[13] * u0;
+        const double r = sqrt(pr[14] + (1. - pr[14]) * u1);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        x = r * cs;
+        y = r * sn;
+    } else {  // RectangleAperture :92-95
+        x = u0 * 2. - 1.;
+        y = u1 * 2. - 1.;
+    }
+    ph.l0 = x;
+    ph.l1 = y;
+    ph.ip = V3{pr[0] + x * pr[3] + y * pr[6], pr[1] + x * pr[4] + y * pr[7], pr[2] + x * pr[5] + y * pr[8]};
+    const double area = ph.dir.x * pr[9] + ph.dir.y * pr[10] + ph.dir.z * pr[11];
+    mul_prob(st_sm, ph, clip01(area));
+}
+
+// ---------------------------------------------------------------------------
+// Parallel containers: facet search with sequential ("last hit wins") semantics
+// (simulator.py:42-49 over a Parallel).  H: array header O[3] nbar[3] u[3] v[3]
+// u0 v0 inv_cell T2.
+// ---------------------------------------------------------------------------
+struct ArrayIter {
+    int cur, end;
+    bool brute;
+};
+
+// true when `dir` lies inside the cone for which the culling grid is conservative
+template <typename HP>
+MXB_DEV bool cull_cone_ok(HP H, const V3& dir, double& dn) {
+    const V3 nb = ld3(H + 3);
+    dn = dot(dir, nb);
+    const double d2 = dot(dir, dir);
+    return dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn;
+}
+
+// start the search of one photon: the candidate range of its culling cell (mode 1) or all F facets
+template <typename HP, typename IP>
+MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int nu, int nv, const Photon& ph,
+                        bool active, unsigned long long* st_sm) {
+    it.brute = true;
+    it.cur = 0;
+    it.end = active ? F : 0;
+    if (mode == 1 && active) {
+        double dn;
+        const bool ok = cull_cone_ok(H, ph.dir, dn);
+        if (!(dn == dn)) {
+            it.end = 0;  // NaN direction can never hit (k >= 0 is false)
+        } else if (ok) {
+            const V3 nb = ld3(H + 3);
+            const V3 O = ld3(H);
+            const double t = ((O.x - ph.pos.x) * nb.x + (O.y - ph.pos.y) * nb.y + (O.z - ph.pos.z) * nb.z) * fast_rcp(dn);
+            const V3 q{ph.pos.x + t * ph.dir.x - O.x, ph.pos.y + t * ph.dir.y - O.y, ph.pos.z + t * ph.dir.z - O.z};
+            const double fu = (dot(q, ld3(H + 6)) - H[12]) * H[14];
+            const double fv = (dot(q, ld3(H + 9)) - H[13]) * H[14];
+            it.brute = false;
+            if (fu >= 0.0 && fv >= 0.0 && fu < (double)nu && fv < (double)nv) {
+                const int cell = (int)fv * nu + (int)fu;
+                it.cur = cell_start.i32(cell);
+                it.end = cell_start.i32(cell + 1);
+            } else {
+                it.cur = it.end = 0;
+            }
+        } else {
+            atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
+        }
+    }
+}
+
+// next facet (ascending index) the photon hits from its CURRENT state; row = word offset of its row
+template <typename BP, typename IP>
+MXB_DEV bool array_search(ArrayIter& it, BP B, IP cand, int rows_off, int stride, Photon& ph, int& row) {
+    while (it.cur < it.end) {
+        const int j = it.brute ? it.cur : cand.i32(it.cur);
+        ++it.cur;
+        const int r = rows_off + j * stride;
+        V3 ipt;
+        double a0, a1;
+        if (plane_intersect(B + r, ph.pos, ph.dir, false, ipt, a0, a1)) {
+            row = r;
+            ph.ip = ipt;
+            ph.l0 = a0;
+            ph.l1 = a1;
+            return true;
+        }
+    }
+    return false;
+}
+
+// after the body: photons that hit re-validate the culling cone for their NEW direction.  The cell
+// list covers ONE redirection inside the cone (H t + 2 H t' <= margin); a second hit or a steep new
+// direction falls back to brute force over the remaining facets
+template <typename HP>
+MXB_DEV void array_revalidate(ArrayIter& it, HP H, const Photon& ph, int nhit, int row, int rows_off, int stride,
+                              int F, unsigned long long* st_sm) {
+    if (ph.hit && !it.brute) {
+        double dn;
+        const bool ok = cull_cone_ok(H, ph.dir, dn);
+        if (nhit >= 2 || (dn == dn && !ok)) {
+            const int j = (row - rows_off) / stride;
+            it.brute = true;
+            it.cur = j + 1;
+            it.end = F;
+            atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
+        }
+    }
+}
+
+}  // namespace mxb

@@ -15,7 +15,8 @@
 #include <vector>
 
 #include "../../include/mxb.h"
-#include "mxb_device.cuh"
+#include "mxb_ops.cuh"
+#include "mxb_jit.h"
 
 using namespace mxb;
 
@@ -51,85 +52,12 @@ struct TraceParams {
     MxbColumns cols;
 };
 
-// --- TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier ---
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-
 // ---------------------------------------------------------------------------
-// program blob access: word offsets into the staged copy (shared memory, 32-bit
-// offsets -> LDS) or into the global blob when the program is too large to stage
+// interpreter-side column stores.  Output columns are resolved once per CTA: cp[k] = device
+// pointer of the op's k-th column and a mode word (bit k: materialised, bit 8+k: this op
+// initialises the column, i.e. stores NaN / -1 for photons it does not touch - outside arrays,
+// or in the first search round).  Per op, `wmask` = the columns this lane has to store.
 // ---------------------------------------------------------------------------
-extern __shared__ __align__(16) double g_smem[];
-
-template <bool STAGED>
-struct PRef {
-    const double* g;
-    int off;
-    __device__ __forceinline__ double operator[](int k) const {
-        if (STAGED) return g_smem[off + k];
-        return __ldg(g + off + k);
-    }
-    __device__ __forceinline__ PRef operator+(int k) const { return PRef{g, off + k}; }
-    __device__ __forceinline__ double2 ld2(int k) const {  // words 2k, 2k+1 (off must be even)
-        if (STAGED) return reinterpret_cast<const double2*>(g_smem + off)[k];
-        return __ldg(reinterpret_cast<const double2*>(g + off) + k);
-    }
-    __device__ __forceinline__ int i32(int k) const {  // packed int32 view of the words at off
-        if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
-        return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
-    }
-};
-
-// fused detector image: gp = nx ny sel_lo n_sel ; bin = round half to even like np.round
-template <typename PP>
-__device__ __forceinline__ void accumulate_image(double* img, PP gp, long long idn, double px, double py,
-                                                 double w) {
-    const long long nx = (long long)gp[0], ny = (long long)gp[1];
-    const long long plane = idn - (long long)gp[2];
-    if (plane < 0 || plane >= (long long)gp[3] || !(px == px) || !(py == py) || !(w == w)) return;
-    const long long ix = llrint(px), iy = llrint(py);
-    if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) return;
-    atomicAdd(&img[(plane * ny + iy) * nx + ix], w);
-}
-
-// ---------------------------------------------------------------------------
-// per-thread photon state
-// ---------------------------------------------------------------------------
-struct Photon {
-    V3 pos, dir, pol;
-    double energy, prob;
-    V3 ip;          // intersection point of the current element
-    double l0, l1;  // local coordinates on the current element
-    bool hit;
-};
-
 struct Ctx {
     const TraceParams* P;
     long long i;           // photon index in the batch
@@ -139,255 +67,20 @@ struct Ctx {
 };
 
 __device__ __forceinline__ double draw(const Ctx& c, int slot, int kind) {
-    const double* inj = c.P->cols.draws[slot];
-    if (inj) return inj[c.i];
-    return device_draw(c.P->seed, (unsigned long long)(c.P->id0 + c.i), slot, kind);
+    return draw_value(c.P->cols.draws[slot], c.i, c.P->seed, (unsigned long long)(c.P->id0 + c.i), slot, kind);
 }
 
-// Output columns are resolved once per CTA: cp[k] = device pointer of the op's k-th column and
-// a mode word (bit k: materialised, bit 8+k: this op initialises the column, i.e. stores
-// NaN / -1 for photons it does not touch - outside arrays, or in the first search round).
-// Per op, `wmask` = the columns this lane has to store (computed once from hit / active /
-// init_round); each put is then a predicated global store.
 typedef unsigned long long ColEntry;
 
-__device__ __forceinline__ void st_global(double* p, double v) {
-    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void st_global(long long* p, long long v) {
-    asm volatile("st.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ int store_mask(const Ctx& c, int mode, bool hit) {
     const int sel = hit ? 0xff : (c.init_round ? (mode >> 8) : 0);
     return c.active ? (mode & sel) : 0;
 }
 __device__ __forceinline__ void put(const Ctx& c, int wmask, int k, ColEntry e, bool hit, double v) {
-    if (wmask & (1 << k))
-        st_global(reinterpret_cast<double*>(e) + c.i, hit ? v : __longlong_as_double(0x7ff8000000000000LL));
+    if (wmask & (1 << k)) st_global(reinterpret_cast<double*>(e) + c.i, hit ? v : nan64());
 }
 __device__ __forceinline__ void put_id(const Ctx& c, int wmask, int k, ColEntry e, bool hit, long long v) {
     if (wmask & (1 << k)) st_global(reinterpret_cast<long long*>(e) + c.i, hit ? v : -1LL);
-}
-
-// optics/base.py:43-47: probability factors multiply and must lie in [0,1]
-__device__ __forceinline__ void mul_prob(const Ctx& c, Photon& ph, double f) {
-    if (f < 0.0 || f > 1.0) atomicAdd(&c.st_sm[MXB_ST_PROB_RANGE], 1ULL);
-    ph.prob *= f;
-}
-
-// ---------------------------------------------------------------------------
-// element physics (each only touches photons with ph.hit)
-// ---------------------------------------------------------------------------
-// mirror.py:53-82  params: P[3] f
-template <typename PP>
-__device__ __forceinline__ void op_lens(Photon& ph, PP p) {
-    const V3 nd = normalize(ph.dir);
-    const double f = p[3];
-    const V3 t{(p[0] + f * nd.x) - ph.ip.x, (p[1] + f * nd.y) - ph.ip.y, (p[2] + f * nd.z) - ph.ip.z};
-    const V3 nd2 = normalize(t);
-    ph.pol = parallel_transport(ph.dir, nd2, ph.pol);
-    ph.dir = nd2;
-}
-
-// scatter.py:49-77  params: center[3] sig_in sig_perp
-template <typename PP>
-__device__ __forceinline__ void op_rscatter(const Ctx& c, Photon& ph, PP p, int s0, int s1,
-                                            double& a, double& b) {
-    const V3 radial{ph.pos.x - p[0], ph.pos.y - p[1], ph.pos.z - p[2]};
-    const V3 perp = cross(ph.dir, radial);
-    V3 out = ph.dir;
-    a = 0.0;
-    b = 0.0;
-    double z0 = 0.0, z1 = 0.0;
-    const bool both = (p[3] != 0.0) && (p[4] != 0.0);
-    if (both && !c.P->cols.draws[s0] && !c.P->cols.draws[s1]) {
-        device_draw_normal_pair(c.P->seed, (unsigned long long)(c.P->id0 + c.i), s0, z0, z1);
-    } else {
-        if (p[3] != 0.0) z0 = draw(c, s0, 1);
-        if (p[4] != 0.0) z1 = draw(c, s1, 1);
-    }
-    if (p[3] != 0.0) {
-        a = p[3] * z0;
-        out = axangle_rotate_T(perp, a, ph.dir);
-    }
-    if (p[4] != 0.0) {
-        b = p[4] * z1;
-        out = axangle_rotate_T(radial, b, out);
-    }
-    ph.pol = parallel_transport(ph.dir, out, ph.pol);
-    ph.dir = out;
-}
-
-// scatter.py:109-145  params: sigma
-template <typename PP>
-__device__ __forceinline__ void op_gscatter(const Ctx& c, Photon& ph, PP p, int s0, int s1, double& ang) {
-    const V3 pdir = normalize(ph.dir);
-    const V3 guess = (fabs(pdir.x) < 0.99999) ? V3{1, 0, 0} : V3{0, 1, 0};
-    const V3 perp = cross(pdir, guess);
-    ang = p[0] * draw(c, s0, 1);
-    V3 out = axangle_rotate_T(perp, ang, pdir);
-    const double ang2 = draw(c, s1, 0) * 2 * 3.141592653589793;
-    out = axangle_rotate_T(pdir, ang2, out);
-    ph.pol = parallel_transport(ph.dir, out, ph.pol);
-    ph.dir = out;
-}
-
-// filter.py:90-94  params: n, x[n], y[n]   (n == 0: constant y[0])
-template <typename PP>
-__device__ __forceinline__ double filter_value(const Ctx& c, PP p, double energy, int flags) {
-    const int n = (int)p[0];
-    if (n == 0) return p[1];
-    PP xp = p + 1;
-    PP fp = p + 1 + n;
-    if ((flags & 1) && (energy < xp[0] || energy > xp[n - 1]))
-        atomicAdd(&c.st_sm[MXB_ST_FILTER_BOUNDS], 1ULL);
-    return interp_clamped(xp, fp, n, energy);
-}
-
-// grating.py:12-57, 60-96; mitsnl/catgrating.py:104-144.  Returns order, sets psel.
-template <typename PP>
-__device__ __forceinline__ double select_order(PP sel, const double* gprog, double u, double energy,
-                                               double blaze, double& psel) {
-    const int kind = (int)sel[0];
-    if (kind == MXB_SEL_ORDERSELECTOR) {
-        const int n = (int)sel[1];
-        psel = sel[2];
-        PP cdf = sel + 3;
-        int idx = 0;   // searchsorted(cdf, u, 'right') = number of entries <= u (clamped), branch-free
-        for (int k = 0; k < n - 1; ++k) idx += (cdf[k] <= u) ? 1 : 0;
-        return sel[3 + n + idx];
-    } else if (kind == MXB_SEL_EFFFILE) {
-        const int nE = (int)sel[1], nO = (int)sel[2];
-        PP en = sel + 3;
-        int ind = 0;
-        double best = fabs(en[0] - energy);
-        for (int k = 1; k < nE; ++k) {  // np.argmin: first minimum
-            const double d = fabs(en[k] - energy);
-            if (d < best) { best = d; ind = k; }
-        }
-        psel = sel[3 + nE + ind];
-        PP cum = sel + 3 + 2 * nE + nO + ind * nO;
-        int oi = 0;
-        for (int k = 0; k < nO; ++k)
-            if (cum[k] > u) { oi = k; break; }
-        return sel[3 + 2 * nE + oi];
-    } else {  // MXB_SEL_INTERPTABLE: bilinear, query clamped to the table (RectBivariateSpline k=1)
-        const int nw = (int)sel[1], nt = (int)sel[2], no = (int)sel[3];
-        const double* tab = gprog + (long long)sel[4];
-        PP wk = sel + 5;
-        PP tk = sel + 5 + nw;
-        PP ord = sel + 5 + nw + nt;
-        double xq = kHcKevNm / energy;
-        xq = fmin(fmax(xq, wk[0]), wk[nw - 1]);
-        double yq = fmin(fmax(blaze, tk[0]), tk[nt - 1]);
-        const int i = bracket(wk, nw, xq), j = bracket(tk, nt, yq);
-        const double tx = (xq - wk[i]) / (wk[i + 1] - wk[i]);
-        const double ty = (yq - tk[j]) / (tk[j + 1] - tk[j]);
-        const double* t00 = tab + ((long long)i * nt + j) * no;
-        const double* t10 = t00 + (long long)nt * no;
-        const double* t01 = t00 + no;
-        const double* t11 = t10 + no;
-        double total = 0.0;
-        for (int k = 0; k < no; ++k) {
-            const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
-            const double f0 = a00 + tx * (a10 - a00);
-            const double f1 = a01 + tx * (a11 - a01);
-            total = total + (f0 + ty * (f1 - f0));
-        }
-        psel = total;
-        double run = 0.0;
-        int oi = 0;
-        for (int k = 0; k < no; ++k) {
-            const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
-            const double f0 = a00 + tx * (a10 - a00);
-            const double f1 = a01 + tx * (a11 - a01);
-            run = run + (f0 + ty * (f1 - f0));
-            if (run / total > u) { oi = k; break; }   // argmax(cumprob > u): first True, 0 if none
-        }
-        return ord[oi];
-    }
-}
-
-// grating.py:233-277  params: l[3] dd[3] d blaze0 dblaze ; n = e_x of the geometry
-template <typename PP>
-__device__ __forceinline__ void op_grating(const Ctx& c, Photon& ph, PP p, PP geom, PP sel,
-                                           int flags, int slot, double& order, double& blaze) {
-    const V3 pn = normalize(ph.dir);
-    const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
-    const double wave = div(kEnergy2Wave, ph.energy);
-    const double p_l = dot(pn, l);
-    const V3 pp = normalize(V3{pn.x - p_l * l.x, pn.y - p_l * l.y, pn.z - p_l * l.z});
-    blaze = acos(clip01(fabs(dot(pp, n))));
-    if (flags & 4) blaze = blaze + (p[7] + ph.l0 * p[8]);  // NonParallelCATGrating blaze_angle_modifier
-    const double u = draw(c, slot, 0);
-    double psel;
-    order = select_order(sel, c.P->prog, u, ph.energy, blaze, psel);
-    const double p_dd = dot(pn, dd);
-    const double sign = (flags & 1) ? ((p_dd < 0.0) ? -1.0 : 1.0) : -1.0;  // CAT: grating.py:298-301
-    const double p_d = p_dd + div(sign * order * wave, p[6]);
-    const double p_n = sqrt(1. - p_d * p_d - p_l * p_l);
-    const double pdn = dot(pn, n);
-    double direction = (pdn > 0.0) ? 1.0 : ((pdn < 0.0) ? -1.0 : pdn);  // np.sign
-    if (flags & 2) direction = direction * -1;
-    const double q = direction * p_n;
-    const V3 nd{p_d * dd.x + p_l * l.x + q * n.x, p_d * dd.y + p_l * l.y + q * n.y,
-                p_d * dd.z + p_l * l.z + q * n.z};
-    ph.pol = parallel_transport(ph.dir, nd, ph.pol);
-    ph.dir = nd;
-    mul_prob(c, ph, psel);
-}
-
-// multiLayerMirror.py:44-91  params: Pinv[9] P[9] ex[3]
-template <typename PP>
-__device__ __forceinline__ void op_brewster(const Ctx& c, Photon& ph, PP p) {
-    const V3 dh = normalize(ph.dir);
-    V3 loc{p[0] * dh.x + p[1] * dh.y + p[2] * dh.z, p[3] * dh.x + p[4] * dh.y + p[5] * dh.z,
-           p[6] * dh.x + p[7] * dh.y + p[8] * dh.z};
-    loc.x = loc.x * -1;
-    PP q = p + 9;
-    const V3 nd{q[0] * loc.x + q[1] * loc.y + q[2] * loc.z, q[3] * loc.x + q[4] * loc.y + q[5] * loc.z,
-                q[6] * loc.x + q[7] * loc.y + q[8] * loc.z};
-    const V3 ex = ld3(p + 18);
-    V3 v_s = cross(dh, ex);
-    const double nvs = sqrt(dot(v_s, v_s));
-    v_s = V3{v_s.x / nvs, v_s.y / nvs, v_s.z / nvs};
-    const V3 v_p = cross(dh, v_s);
-    const double pvs = dot(ph.pol, v_s), pvp = dot(ph.pol, v_p);
-    const double Es2 = 1. * (pvs * pvs), Ep2 = 0. * (pvp * pvp);
-    const double inten = Es2 + Ep2;
-    if (inten > 1.001) atomicAdd(&c.st_sm[MXB_ST_INTENSITY], 1ULL);
-    const V3 nvp = cross(nd, v_s);
-    const V3 np_{-Es2 * v_s.x + Ep2 * nvp.x, -Es2 * v_s.y + Ep2 * nvp.y, -Es2 * v_s.z + Ep2 * nvp.z};
-    const double nn = sqrt(dot(np_, np_));
-    ph.pol = V3{np_.x / nn, np_.y / nn, np_.z / nn};
-    ph.dir = nd;
-    mul_prob(c, ph, clip01(inten));
-}
-
-// multiLayerMirror.py:132-170  params: Ly n_refl n_pol xs[nr] peak_lambda[nr] peak[nr] fwhm[nr] pol_e[np] pol[np]
-template <typename PP>
-__device__ __forceinline__ void op_mleff(const Ctx& c, Photon& ph, PP p) {
-    const double Ly = p[0];
-    const int nr = (int)p[1], npol = (int)p[2];
-    PP xs = p + 3;
-    PP pl = xs + nr;
-    PP pk = pl + nr;
-    PP fw = pk + nr;
-    PP pe = fw + nr;
-    PP pf = pe + npol;
-    const double wavelength = kHcMultilayer / ph.energy;
-    const double tested = interp_clamped(pe, pf, npol, ph.energy);
-    const double local_x = ph.l0 / Ly;
-    const double peak_w = interp_clamped(xs, pl, nr, local_x);
-    const double max_refl = interp_clamped(xs, pk, nr, local_x) / tested;
-    const double spread = interp_clamped(xs, fw, nr, local_x);
-    const double c2 = (spread * spread) / (8. * 0.6931471805599453);
-    double refl = 0.0;
-    if (c2 != 0.0) {
-        const double dw = wavelength - peak_w;
-        refl = max_refl * exp(-(dw * dw) / (2 * c2));
-    }
-    mul_prob(c, ph, refl / 100);
 }
 
 // ---------------------------------------------------------------------------
@@ -418,6 +111,9 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ unsigned long long st_sm[MXB_STATUS_WORDS];
     __shared__ unsigned int hits_w[kThreads / 32][MXB_MAX_OPS];   // per-warp hit counters (no atomics)
     __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned long long hot_keys[MXB_HOT_SLOTS];
+    __shared__ double hot_vals[MXB_HOT_SLOTS];
+    const HotCache hot{hot_keys, hot_vals};
     typedef PRef<STAGED> Ref;
 
     const int tid = threadIdx.x;
@@ -438,6 +134,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         }
     }
     for (int k = tid; k < MXB_STATUS_WORDS; k += kThreads) st_sm[k] = 0ULL;
+    hot_init(hot, tid, kThreads);
     for (int k = tid; k < (kThreads / 32) * MXB_MAX_OPS; k += kThreads) (&hits_w[0][0])[k] = 0u;
     if (STAGED) mbar_wait(&bar, 0);
     const Ref B{P.prog, 0};
@@ -508,8 +205,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         ph.l0 = ph.l1 = kNaN;
 
         // array iteration state
-        int arr_cur = 0, arr_end = 0, arr_nhit = 0, arr_pc = -1;
-        bool arr_brute = false;
+        int arr_nhit = 0, arr_pc = -1;
+        ArrayIter arr{0, 0, false};
         ctx.init_round = true;
         int row = 0;    // word offset of the current facet row (0 = the blob itself outside arrays)
         int geom = 0;   // word offset of the current geometry block
@@ -577,7 +274,12 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 double a = 0, b = 0;
-                if (ph.hit) op_rscatter(ctx, ph, pr, c.s0, c.s1, a, b);
+                if (ph.hit) {
+                    double z0, z1;
+                    rscatter_draws(pr[3], pr[4], P.cols.draws[c.s0], P.cols.draws[c.s1], i, P.seed,
+                                   (unsigned long long)(P.id0 + i), c.s0, c.s1, z0, z1);
+                    op_rscatter(ph, pr, z0, z1, a, b);
+                }
                 put(ctx, wm, 0, c.cp[0], ph.hit, a);
                 put(ctx, wm, 1, c.cp[1], ph.hit, b);
                 break;
@@ -586,23 +288,35 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 double a = 0;
-                if (ph.hit) op_gscatter(ctx, ph, pr, c.s0, c.s1, a);
+                if (ph.hit) {
+                    const double zn = draw(ctx, c.s0, 1);
+                    const double u = draw(ctx, c.s1, 0);
+                    op_gscatter(ph, pr, zn, u, a);
+                }
                 put(ctx, wm, 0, c.cp[0], ph.hit, a);
                 break;
             }
             case MXB_OP_FILTER: {
-                if (ph.hit) mul_prob(ctx, ph, filter_value(ctx, pr, ph.energy, op.flags));
+                if (ph.hit) mul_prob(st_sm, ph, filter_value(st_sm, pr, ph.energy, op.flags));
                 break;
             }
             case MXB_OP_GFILTER: {
-                if (ctx.active) mul_prob(ctx, ph, filter_value(ctx, pr, ph.energy, op.flags));
+                if (ctx.active) mul_prob(st_sm, ph, filter_value(st_sm, pr, ph.energy, op.flags));
                 break;
             }
             case MXB_OP_GRATING: {
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 double order = 0, blaze = 0;
-                if (ph.hit) op_grating(ctx, ph, pr, B + geom, B + op.pg, op.flags, c.s0, order, blaze);
+                if (ph.hit) {
+                    const double u = draw(ctx, c.s0, 0);
+                    const Ref sel = B + op.pg;
+                    op_grating(st_sm, ph, pr, B + geom, op.flags,
+                               [&](double energy, double bl, double& psel) {
+                                   return select_order(sel, P.prog, u, energy, bl, psel);
+                               },
+                               order, blaze);
+                }
                 put(ctx, wm, 0, c.cp[0], ph.hit, order);
                 put(ctx, wm, 1, c.cp[1], ph.hit, blaze);
                 break;
@@ -611,14 +325,14 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 // detector.py:73-75; pr: pixsize cp0 cp1; optional fused image: pg: nx ny sel_lo n_sel, s0 image slot
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
-                const double px = div(ph.l0, pr[0]) + pr[1];
-                const double py = div(ph.l1, pr[0]) + pr[2];
+                double px, py;
+                op_detpix(ph, pr, px, py);
                 put(ctx, wm, 0, c.cp[0], ph.hit, px);
                 put(ctx, wm, 1, c.cp[1], ph.hit, py);
                 if (c.s0 >= 0 && ph.hit) {
                     const Ref gp = B + op.pg;
                     const long long idn = (op.flags & 1) ? (long long)(B + row)[c.w15] : (long long)c.w14;
-                    accumulate_image(P.cols.f64[c.s0], gp, idn, px, py, ph.prob);
+                    accumulate_image(hot, P.cols.f64[c.s0], gp, idn, px, py, ph.prob);
                 }
                 break;
             }
@@ -627,34 +341,24 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 const Ref gp = B + op.pg;
-                const double chipx = div(ph.l0, pr[0]) + pr[1] + 1;
-                const double chipy = div(ph.l1, pr[0]) + pr[2] + 1;
-                const double tx = pr[3] * (pr[4] * (chipx - 0.5) + pr[5] * (chipy - 0.5)) + pr[6];
-                const double ty = pr[3] * (-pr[5] * (chipx - 0.5) + pr[4] * (chipy - 0.5)) + pr[7];
-                const double mn0 = ph.ip.x - gp[0];
-                const double x = div(div(ph.ip.y, mn0), gp[1]);
-                const double y = div(div(ph.ip.z, mn0), gp[1]);
-                put(ctx, wm, 0, c.cp[0], ph.hit, chipx);
-                put(ctx, wm, 1, c.cp[1], ph.hit, chipy);
-                put(ctx, wm, 2, c.cp[2], ph.hit, tx);
-                put(ctx, wm, 3, c.cp[3], ph.hit, ty);
-                put(ctx, wm, 4, c.cp[4], ph.hit, gp[2] - x);
-                put(ctx, wm, 5, c.cp[5], ph.hit, gp[3] + y);
-                put(ctx, wm, 6, c.cp[6], ph.hit, gp[2] - x * gp[4] + y * gp[5]);
-                put(ctx, wm, 7, c.cp[7], ph.hit, gp[3] + x * gp[5] + y * gp[4]);
+                double o[8];
+                op_acis(ph, pr, gp, o);
+                const double chipx = o[0], chipy = o[1];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) put(ctx, wm, k, c.cp[k], ph.hit, o[k]);
                 if (c.s0 >= 0 && ph.hit) {
                     // fused detector image (chip pixel convention is 1-based: det_acis.py:33-34)
                     const long long idn = (long long)(B + row)[c.w15];
-                    accumulate_image(P.cols.f64[c.s0], gp + 6, idn, chipx - 1.0, chipy - 1.0, ph.prob);
+                    accumulate_image(hot, P.cols.f64[c.s0], gp + 6, idn, chipx - 1.0, chipy - 1.0, ph.prob);
                 }
                 break;
             }
             case MXB_OP_BREWSTER: {
-                if (ph.hit) op_brewster(ctx, ph, pr);
+                if (ph.hit) op_brewster(st_sm, ph, pr);
                 break;
             }
             case MXB_OP_MLEFF: {
-                if (ph.hit) op_mleff(ctx, ph, pr);
+                if (ph.hit) op_mleff(st_sm, ph, pr);
                 break;
             }
             case MXB_OP_APERTURE: {
@@ -668,25 +372,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 }
                 ph.hit = sel;
                 if (sel) {
-                    double x, y;
                     const double u0 = draw(ctx, c.s0, 0), u1 = draw(ctx, c.s1, 0);
-                    if (op.flags & 1) {  // CircleAperture :138-146
-                        const double phi = pr[12] + pr[13] * u0;
-                        const double r = sqrt(pr[14] + (1. - pr[14]) * u1);
-                        double sn, cs;
-                        sincos(phi, &sn, &cs);
-                        x = r * cs;
-                        y = r * sn;
-                    } else {  // RectangleAperture :92-95
-                        x = u0 * 2. - 1.;
-                        y = u1 * 2. - 1.;
-                    }
-                    ph.l0 = x;
-                    ph.l1 = y;
-                    ph.ip = V3{pr[0] + x * pr[3] + y * pr[6], pr[1] + x * pr[4] + y * pr[7],
-                               pr[2] + x * pr[5] + y * pr[8]};
-                    const double area = ph.dir.x * pr[9] + ph.dir.y * pr[10] + ph.dir.z * pr[11];
-                    mul_prob(ctx, ph, clip01(area));
+                    op_aperture(st_sm, ph, pr, op.flags, u0, u1);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
                 if (lane0) my_hits[pc] += __popc(m);
@@ -706,54 +393,11 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     arr_pc = pc;
                     ctx.init_round = true;    // the body's first pass initialises the columns it creates
                     arr_nhit = 0;
-                    arr_brute = true;
-                    arr_cur = 0;
-                    arr_end = ctx.active ? c.c[0] : 0;
-                    if (c.c[3] == 1 && ctx.active) {
-                        const V3 nb = ld3(H + 3);
-                        const double dn = dot(ph.dir, nb);
-                        const double d2 = dot(ph.dir, ph.dir);
-                        if (!(dn == dn)) {
-                            arr_end = 0;  // NaN direction can never hit (k >= 0 is false)
-                        } else if (dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn) {
-                            const V3 O = ld3(H);
-                            const double t = ((O.x - ph.pos.x) * nb.x + (O.y - ph.pos.y) * nb.y + (O.z - ph.pos.z) * nb.z) * fast_rcp(dn);
-                            const V3 q{ph.pos.x + t * ph.dir.x - O.x, ph.pos.y + t * ph.dir.y - O.y, ph.pos.z + t * ph.dir.z - O.z};
-                            const double fu = (dot(q, ld3(H + 6)) - H[12]) * H[14];
-                            const double fv = (dot(q, ld3(H + 9)) - H[13]) * H[14];
-                            arr_brute = false;
-                            if (fu >= 0.0 && fv >= 0.0 && fu < (double)c.c[4] && fv < (double)c.c[5]) {
-                                const int cell = (int)fv * c.c[4] + (int)fu;
-                                const Ref cs = B + c.c[6];
-                                arr_cur = cs.i32(cell);
-                                arr_end = cs.i32(cell + 1);
-                            } else {
-                                arr_cur = arr_end = 0;
-                            }
-                        } else {
-                            atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
-                        }
-                    }
+                    array_open(arr, H, B + c.c[6], c.c[0], c.c[3], c.c[4], c.c[5], ph, ctx.active, st_sm);
                 }
                 // search the next facet (ascending index) this photon hits from its CURRENT state
-                bool found = false;
-                const Ref cand = B + c.c[7];
-                while (arr_cur < arr_end) {
-                    const int j = arr_brute ? arr_cur : cand.i32(arr_cur);
-                    ++arr_cur;
-                    const int r = c.c[2] + j * c.c[1];
-                    V3 ipt;
-                    double a0, a1;
-                    if (plane_intersect(B + r, ph.pos, ph.dir, false, ipt, a0, a1)) {
-                        found = true;
-                        row = r;
-                        geom = r;
-                        ph.ip = ipt;
-                        ph.l0 = a0;
-                        ph.l1 = a1;
-                        break;
-                    }
-                }
+                const bool found = array_search(arr, B, B + c.c[7], c.c[2], c.c[1], ph, row);
+                if (found) geom = row;
                 ph.hit = found;
                 arr_nhit += found ? 1 : 0;
                 const unsigned m = __ballot_sync(0xffffffffu, found);
@@ -778,25 +422,11 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 // after the body: photons that hit re-validate the culling cone for their NEW direction
                 const int bpc = arr_pc;
                 const OpCold& c = opc[bpc];
-                if (ph.hit && !arr_brute) {
-                    const Ref H = B + oph[bpc].pg;
-                    const V3 nb = ld3(H + 3);
-                    const double dn = dot(ph.dir, nb);
-                    const double d2 = dot(ph.dir, ph.dir);
-                    // the cell list covers ONE redirection inside the cone (H t + 2 H t' <= margin);
-                    // a second hit or a steep new direction falls back to brute force
-                    if (arr_nhit >= 2 || (dn == dn && !(dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn))) {
-                        const int j = (row - c.c[2]) / c.c[1];
-                        arr_brute = true;
-                        arr_cur = j + 1;
-                        arr_end = c.c[0];
-                        atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
-                    }
-                }
+                array_revalidate(arr, B + oph[bpc].pg, ph, arr_nhit, row, c.c[2], c.c[1], c.c[0], st_sm);
                 // another search round only if some lane that hit still has facets to test
                 ctx.init_round = false;               // later rounds only store for photons that hit
-                if (__any_sync(0xffffffffu, ph.hit && arr_cur < arr_end)) {
-                    if (!ph.hit) arr_cur = arr_end;   // lanes that found nothing are done with this array
+                if (__any_sync(0xffffffffu, ph.hit && arr.cur < arr.end)) {
+                    if (!ph.hit) arr.cur = arr.end;   // lanes that found nothing are done with this array
                     pc = bpc - 1;                     // -> ARRAY_BEGIN (pc++ below)
                 } else {
                     array_exit();
@@ -832,6 +462,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
     }
 
     __syncthreads();
+    hot_flush(hot, tid, kThreads);
     for (int k = tid; k < MXB_MAX_OPS; k += kThreads) {
         unsigned long long t = 0ULL;
         for (int w = 0; w < kThreads / 32; ++w) t += hits_w[w][k];
@@ -894,6 +525,11 @@ __global__ void __launch_bounds__(256)
 hist2d_kernel(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
               int n_sel, double x0, double y0, long long n, int nx, int ny, double* img,
               unsigned long long* counts) {
+    __shared__ unsigned long long hot_keys[MXB_HOT_SLOTS];
+    __shared__ double hot_vals[MXB_HOT_SLOTS];
+    const HotCache hot{hot_keys, hot_vals};
+    hot_init(hot, threadIdx.x, blockDim.x);
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         long long plane = 0;
@@ -907,9 +543,11 @@ hist2d_kernel(const double* x, const double* y, const double* w, const long long
         if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) continue;
         const long long bin = (plane * ny + iy) * nx + ix;
         const double wv = w ? w[i] : 1.0;
-        if (img && wv == wv) atomicAdd(&img[bin], wv);
+        if (img && wv == wv) hot_add(hot, &img[bin], wv);
         if (counts) atomicAdd(&counts[bin], 1ULL);
     }
+    __syncthreads();
+    hot_flush(hot, threadIdx.x, blockDim.x);
 }
 
 int sm_count() {
@@ -944,8 +582,10 @@ int validate_program(const double* h, size_t words, int* n_ops, int* stage_words
     return MXB_OK;
 }
 
-int launch_trace(const double* prog_dev, int n_ops, int stage_words, const MxbColumns* cols, int64_t n,
-                 int64_t id0, uint64_t seed, unsigned long long* status_dev, cudaStream_t stream) {
+thread_local std::string g_kernel_info = "none";
+
+int launch_interp(const double* prog_dev, int n_ops, int stage_words, const MxbColumns* cols, int64_t n,
+                  int64_t id0, uint64_t seed, unsigned long long* status_dev, cudaStream_t stream) {
     TraceParams P;
     P.prog = prog_dev;
     P.n_ops = n_ops;
@@ -969,7 +609,34 @@ int launch_trace(const double* prog_dev, int n_ops, int stage_words, const MxbCo
         mxb_trace_kernel<false><<<grid, kThreads, 0, stream>>>(P);
     }
     CUDA_TRY(cudaGetLastError());
+    g_kernel_info = "interpreter";
     return MXB_OK;
+}
+
+#ifdef MXB_FAST
+constexpr bool kFastBuild = true;
+#else
+constexpr bool kFastBuild = false;
+#endif
+
+// kernel selection (see mxb_set_jit in mxb.h): specialised kernel or the interpreter
+int launch_trace(const double* prog_dev, const double* prog_host, size_t prog_words, int n_ops, int stage_words,
+                 const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed, unsigned long long* status_dev,
+                 cudaStream_t stream) {
+    const mxbjit::Mode mode = mxbjit::mode();
+    if (mode == mxbjit::kForce || (mode == mxbjit::kAuto && n >= mxbjit::auto_threshold())) {
+        std::string err;
+        bool unavailable = false;
+        const int rc = mxbjit::launch(prog_dev, prog_host, prog_words, n_ops, stage_words, cols, n, id0, seed,
+                                      status_dev, stream, kFastBuild, &err, &unavailable);
+        if (rc == MXB_OK) {
+            g_kernel_info = mxbjit::last_info();
+            return MXB_OK;
+        }
+        if (mode == mxbjit::kForce || !unavailable) return fail(rc, err);
+        // auto mode without NVRTC on this machine: the interpreter kernel runs the program
+    }
+    return launch_interp(prog_dev, n_ops, stage_words, cols, n, id0, seed, status_dev, stream);
 }
 
 // cached staging state of mxb_trace_host (one per host thread)
@@ -1022,6 +689,39 @@ const char* mxb_last_error(void) { return g_last_error.c_str(); }
 
 void mxb_host_release(void) { host_stage().release(); }
 
+void mxb_set_jit(int mode) { mxbjit::set_mode(mode); }
+int mxb_get_jit(void) { return (int)mxbjit::mode(); }
+const char* mxb_jit_info(void) { return g_kernel_info.c_str(); }
+
+long long mxb_jit_source(const double* prog_host, size_t prog_words, const MxbColumns* cols, char* buf,
+                         size_t buf_len) {
+    int n_ops = 0, stage_words = 0;
+    const int rc = validate_program(prog_host, prog_words, &n_ops, &stage_words);
+    if (rc) return rc;
+    if (!cols) return fail(MXB_EINVAL, "mxb_jit_source: null pointer");
+    std::string err;
+    const std::string src = mxbjit::source_for(prog_host, prog_words, cols, &err);
+    if (src.empty()) return fail(MXB_EJIT, err);
+    if (buf && buf_len) {
+        const size_t m = src.size() < buf_len - 1 ? src.size() : buf_len - 1;
+        memcpy(buf, src.data(), m);
+        buf[m] = 0;
+    }
+    return (long long)src.size();
+}
+
+long long mxb_jit_compile(const double* prog_host, size_t prog_words, const MxbColumns* cols) {
+    int n_ops = 0, stage_words = 0;
+    const int rc = validate_program(prog_host, prog_words, &n_ops, &stage_words);
+    if (rc) return rc;
+    if (!cols) return fail(MXB_EINVAL, "mxb_jit_compile: null pointer");
+    std::string err, info;
+    const long long sz = mxbjit::compile_only(prog_host, prog_words, cols, kFastBuild, &info, &err);
+    if (sz < 0) return fail((int)sz, err);
+    g_kernel_info = info;
+    return sz;
+}
+
 int mxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -1041,8 +741,8 @@ int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host
     if (n == 0) return MXB_OK;
     for (int k = 0; k <= MXB_COL_PROB; ++k)
         if (!cols->f64[k]) return fail(MXB_EINVAL, "mxb_trace: core photon column missing");
-    return launch_trace(prog_dev, n_ops, stage_words, cols, n, photon_id0, seed, status_dev,
-                        (cudaStream_t)stream);
+    return launch_trace(prog_dev, prog_host, prog_words, n_ops, stage_words, cols, n, photon_id0, seed,
+                        status_dev, (cudaStream_t)stream);
 }
 
 int mxb_plane_intersect(const double* geom14_host, int circular, const double* const dir[3],
@@ -1184,7 +884,8 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             }
             HTRY(cudaEventRecord(S.ev_in[b], s_in));
             HTRY(cudaStreamWaitEvent(s_k, S.ev_in[b], 0));
-            rc = launch_trace(dprog, n_ops, stage_words, &dc, m, photon_id0 + off, seed, dstatus, s_k);
+            rc = launch_trace(dprog, prog_host, prog_words, n_ops, stage_words, &dc, m, photon_id0 + off, seed,
+                              dstatus, s_k);
             if (rc) { result = rc; goto cleanup; }
             HTRY(cudaEventRecord(S.ev_k[b], s_k));
             HTRY(cudaStreamWaitEvent(s_out, S.ev_k[b], 0));

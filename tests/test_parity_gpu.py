@@ -27,12 +27,34 @@ def _mb():
     return marxs_b200
 
 
-@pytest.fixture(params=['fast', 'strict'])
+@pytest.fixture(params=['fast-jit', 'strict-jit', 'fast-interp', 'strict-interp'])
 def mode(request):
+    """Both builds (fast / bit-parity) x both kernels: the kernel specialised for the program
+    (NVRTC, forced here: the default `auto` policy only specialises large launches) and the
+    op-list interpreter.  Yields 'fast' or 'strict'."""
     from marxs_b200 import _lib
-    _lib.set_strict(request.param == 'strict')
-    yield request.param
+    build, kernel = request.param.split('-')
+    _lib.set_strict(build == 'strict')
+    for strict in (False, True):
+        _lib.load(strict).mxb_set_jit(2 if kernel == 'jit' else 0)
+    yield build
     _lib.set_strict(False)
+    for strict in (False, True):
+        _lib.load(strict).mxb_set_jit(-1)
+
+
+@pytest.fixture(autouse=True)
+def _jit_default_forced(request):
+    """Tests without the `mode` fixture run the specialised kernels."""
+    from marxs_b200 import _lib
+    if 'mode' in request.fixturenames:
+        yield
+        return
+    for strict in (False, True):
+        _lib.load(strict).mxb_set_jit(2)
+    yield
+    for strict in (False, True):
+        _lib.load(strict).mxb_set_jit(-1)
 
 
 def load(name):
@@ -127,6 +149,23 @@ def test_library_loaded_is_native():
     assert b'sm_100a' in lib.mxb_build_info()
     assert lib.mxb_device_count() >= 1
     assert b'strict' in _lib.load(True).mxb_build_info()
+
+
+def test_specialised_kernel_is_launched():
+    """mxb_jit_info reports which kernel ran: NVRTC-specialised when forced, interpreter when off."""
+    from marxs_b200 import _lib, optics
+    mb = _mb()
+    lib = _lib.load(False)
+    rng = np.random.default_rng(5)
+    table = make_photons(rng, 1000)
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    lib.mxb_set_jit(2)
+    det(mb.PhotonBatch(table, device='cuda'))
+    assert lib.mxb_jit_info().startswith(b'jit '), lib.mxb_jit_info()
+    lib.mxb_set_jit(0)
+    det(mb.PhotonBatch(table, device='cuda'))
+    assert lib.mxb_jit_info() == b'interpreter'
+    lib.mxb_set_jit(-1)
 
 
 def test_intersect_golden(mode):
