@@ -124,12 +124,28 @@ MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V
     return hit;
 }
 
+// Unit-length tracking (fast build only).  The reference re-normalises directions in every
+// routine; a vector this kernel has just produced by normalisation, rotation or the grating
+// equation already has |v| = 1 to rounding, and normalising it again changes it by <= 1 ulp.  The
+// fast build carries one flag per photon and skips those renormalisations; the strict build
+// (bit parity) never does.
+#ifdef MXB_FAST
+constexpr bool kTrackUnit = true;
+#else
+constexpr bool kTrackUnit = false;
+#endif
+MXB_DEV V3 normalize_unless(bool unit, const V3& a) {
+    if (kTrackUnit && unit) return a;
+    return normalize(a);
+}
+
 // ---------------------------------------------------------------------------
 // math/polarization.py:90-170 parallel_transport (identity when |d1 x d2| <= 1e-8)
 // ---------------------------------------------------------------------------
-MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol) {
-    const V3 d1 = normalize(dir_old);
-    const V3 d2 = normalize(dir_new);
+MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol, bool old_unit = false,
+                              bool new_unit = false) {
+    const V3 d1 = normalize_unless(old_unit, dir_old);
+    const V3 d2 = normalize_unless(new_unit, dir_new);
     V3 s = cross(d1, d2);
 #ifdef MXB_FAST
     const double ns2 = dot(s, s);

@@ -16,6 +16,8 @@
 #include <unordered_map>
 #include <vector>
 
+#define MXB_PIPE_BYTES_PER_WARP (11 * 32 * 8)   // mxb_ops.cuh: MXB_PIPE_WORDS_PER_WARP doubles
+
 #include "mxb_embed.inc"   // kSrcMxbH, kSrcDeviceCuh, kSrcOpsCuh : the headers, embedded at build time
 
 namespace mxbjit {
@@ -92,6 +94,8 @@ struct Gen {
     std::map<std::pair<int, int>, int> sidx;
     bool need_blob = false;       // some op reads the blob through PRef (staging needed)
     bool need_hot = false;        // a detector image is accumulated: per-CTA hot-pixel cache
+    int threads = 640;            // CTA size the kernel is compiled for
+    bool pipe_wanted = true, pipe = false;
     std::vector<Op> ops;
     // array context
     bool in_array = false;
@@ -499,15 +503,21 @@ struct Gen {
         if (!emit) return true;
         std::string body;
         body.swap(src);         // body holds the op code; src receives the preamble
-        if ((5 + fmap.size() + imap.size() + dmap.size() + smap.size()) * 8 > 32000) return fail("program has too many scalar parameters");
+        if ((6 + fmap.size() + imap.size() + dmap.size() + smap.size()) * 8 > 32000) return fail("program has too many scalar parameters");
         out("// generated by libmxb (mxb_jit.cpp): specialised driver of one element program");
         out("#include \"mxb_ops.cuh\"");
         out("using namespace mxb;");
         out("#ifndef JIT_THREADS\n#define JIT_THREADS 640\n#endif");
         out("#ifndef JIT_MINBLOCKS\n#define JIT_MINBLOCKS 1\n#endif");
+        out("#ifndef JIT_PREFETCH\n#define JIT_PREFETCH 1\n#endif");
         out("#define JIT_STAGE_WORDS %d", need_blob && staged ? stage_words : 0);
+        {   // per-warp TMA input pipeline (mxb_ops.cuh InputPipe) when its buffers fit beside the staged program
+            const long long stage_b = need_blob && staged ? (long long)stage_words * 8 : 0;
+            pipe = pipe_wanted && stage_b + (long long)(threads / 32) * MXB_PIPE_BYTES_PER_WARP <= 225 * 1024;
+            out("#define JIT_PIPE %d", pipe ? 1 : 0);
+        }
         out("struct JitParams {");
-        out("    long long n, id0;");
+        out("    long long n, id0, flags;");
         out("    unsigned long long seed;");
         out("    unsigned long long* status;");
         out("    const double* prog;");
@@ -534,6 +544,10 @@ struct Gen {
         out("                     min(bytes - off, 32768u), &bar);");
         out("    }");
         out("#endif");
+        out("#if JIT_PIPE");
+        out("    __shared__ __align__(8) uint64_t in_bar[JIT_THREADS / 32];");
+        out("    if ((tid & 31) == 0) mbar_init(&in_bar[tid >> 5], 1);");
+        out("#endif");
         out("    if (tid < MXB_ST_OPHITS) st_sm[tid] = 0ULL;");
         if (need_hot) {
             out("    __shared__ unsigned long long hot_keys[MXB_HOT_SLOTS];");
@@ -554,23 +568,32 @@ struct Gen {
         }
         out("    const double kNaN = nan64();");
         out("    const long long stride = (long long)gridDim.x * JIT_THREADS;");
-        out("    const long long n_round = ((P.n + JIT_THREADS - 1) / JIT_THREADS) * JIT_THREADS;   // keep warps whole");
-        out("    for (long long i = (long long)blockIdx.x * JIT_THREADS + tid; i < n_round; i += stride) {");
+        out("    const int lane = tid & 31;");
+        out("    const bool tma_ok = JIT_PIPE && (P.flags & 1);   // host: all 11 core planes are 16-byte aligned");
+        out("    InputPipe pipe;");
+        out("#if JIT_PIPE");
+        out("    pipe.buf = g_smem + JIT_STAGE_WORDS + (tid >> 5) * MXB_PIPE_WORDS_PER_WARP;");
+        out("    pipe.bar = &in_bar[tid >> 5];");
+        out("#else");
+        out("    pipe.buf = nullptr;");
+        out("    pipe.bar = nullptr;");
+        out("#endif");
+        out("    long long base = (long long)blockIdx.x * JIT_THREADS + (tid & ~31);   // whole warps");
+        out("    pipe_start(pipe, P.f, base, P.n, tma_ok, lane);");
+        out("    for (; base < P.n; base += stride) {");
+        out("        const long long i = base + lane;");
         out("        const bool active = i < P.n;");
         out("        const unsigned long long gid = (unsigned long long)(P.id0 + i);");
         out("        (void)gid;");
         out("        Photon ph;");
-        out("        if (active) {");
-        out("            ph.pos = V3{P.f[0][i], P.f[1][i], P.f[2][i]};");
-        out("            ph.dir = V3{P.f[3][i], P.f[4][i], P.f[5][i]};");
-        out("            ph.pol = V3{P.f[6][i], P.f[7][i], P.f[8][i]};");
-        out("            ph.energy = P.f[9][i];");
-        out("            ph.prob = P.f[10][i];");
-        out("        } else {");
-        out("            ph.pos = ph.dir = ph.pol = V3{kNaN, kNaN, kNaN};");
-        out("            ph.energy = ph.prob = kNaN;");
+        out("        pipe_load(pipe, P.f, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
+        out("        photon_loaded(ph);");
+        out("#if JIT_PREFETCH");
+        out("        if (i + stride < P.n) {   // next group's inputs -> L2 while this one is traced");
+        out("#pragma unroll");
+        out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.f[k] + i + stride));");
         out("        }");
-        out("        ph.hit = false;");
+        out("#endif");
         out("        ph.ip = V3{kNaN, kNaN, kNaN};");
         out("        ph.l0 = ph.l1 = kNaN;");
         out("        {");
@@ -598,7 +621,11 @@ struct Gen {
     }
 };
 
+int env_int(const char* name, int dflt);
+
 void init_gen(Gen& g, const double* prog_host, size_t words, const MxbColumns* cols, bool emit) {
+    g.threads = env_int("MXB_JIT_THREADS", 640);
+    g.pipe_wanted = env_int("MXB_JIT_PIPE", 0) != 0;
     g.W = prog_host;
     g.words = words;
     g.n_ops = (int)prog_host[2];
@@ -616,7 +643,8 @@ struct Kernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t fn = nullptr;
     std::vector<int> fmap, imap, dmap, smap;
-    int stage_bytes = 0, threads = 512, blocks_per_sm = 1, regs = 0;
+    int stage_bytes = 0, smem_bytes = 0, threads = 640, blocks_per_sm = 1, regs = 0;
+    bool pipe = false;
     bool need_blob = false;
     std::string hash, origin;
     int smem_attr_dev = -1;
@@ -698,13 +726,35 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
     const std::string cu_path = dir + "/mxb_jit_" + hash + ".cu";
     const char* headers[] = {kSrcMxbH, kSrcDeviceCuh, kSrcOpsCuh, kStdintStub, kStddefStub};
     const char* names[] = {"mxb.h", "mxb_device.cuh", "mxb_ops.cuh", "stdint.h", "stddef.h"};
-    nvrtcProgram prog = nullptr;
-    int rc = N.CreateProgram(&prog, source.c_str(), cu_path.c_str(), 5, headers, names);
-    if (rc) { *err = std::string("nvrtcCreateProgram: ") + N.GetErrorString(rc); return MXB_EJIT; }
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    // with the disk cache the embedded headers are written next to the kernels and included from
+    // there, so -lineinfo points at real files (ncu --import-source, cuobjdump)
+    int n_mem_headers = 5;
+    if (env_int("MXB_JIT_DISK_CACHE", 1) != 0) {
+        uint64_t hh = fnv1a(kSrcMxbH, strlen(kSrcMxbH));
+        hh = fnv1a(kSrcDeviceCuh, strlen(kSrcDeviceCuh), hh);
+        hh = fnv1a(kSrcOpsCuh, strlen(kSrcOpsCuh), hh);
+        char hs[32];
+        snprintf(hs, sizeof(hs), "%016llx", (unsigned long long)hh);
+        const std::string inc = dir + "/include_" + hs;
+        mkdirs(inc);
+        std::string probe;
+        if (!read_file(inc + "/mxb_ops.cuh", probe)) {
+            for (int k = 0; k < 5; ++k) write_file(inc + "/" + names[k], headers[k]);
+        }
+        if (read_file(inc + "/mxb_ops.cuh", probe) && probe == kSrcOpsCuh) {
+            opts.push_back("-I" + inc);
+            n_mem_headers = 0;
+        }
+    }
+    nvrtcProgram prog = nullptr;
+    int rc = N.CreateProgram(&prog, source.c_str(), cu_path.c_str(), n_mem_headers, n_mem_headers ? headers : nullptr,
+                             n_mem_headers ? names : nullptr);
+    if (rc) { *err = std::string("nvrtcCreateProgram: ") + N.GetErrorString(rc); return MXB_EJIT; }
     if (fast_build) opts.push_back("-DMXB_FAST"); else opts.push_back("--fmad=false");
     opts.push_back("-DJIT_THREADS=" + std::to_string(env_int("MXB_JIT_THREADS", 640)));
     opts.push_back("-DJIT_MINBLOCKS=" + std::to_string(env_int("MXB_JIT_MINBLOCKS", 1)));
+    opts.push_back("-DJIT_PREFETCH=" + std::to_string(env_int("MXB_JIT_PREFETCH", 1)));
     if (env_int("MXB_JIT_MAXREG", 0) > 0) opts.push_back("--maxrregcount=" + std::to_string(env_int("MXB_JIT_MAXREG", 0)));
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -729,8 +779,9 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
 
 std::string options_tag(bool fast_build) {
     char b[128];
-    snprintf(b, sizeof(b), "%s t%d b%d r%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 640),
-             env_int("MXB_JIT_MINBLOCKS", 1), env_int("MXB_JIT_MAXREG", 0));
+    snprintf(b, sizeof(b), "%s t%d b%d r%d p%d f%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 640),
+             env_int("MXB_JIT_MINBLOCKS", 1), env_int("MXB_JIT_MAXREG", 0), env_int("MXB_JIT_PIPE", 0),
+             env_int("MXB_JIT_PREFETCH", 1));
     return b;
 }
 
@@ -793,6 +844,8 @@ int get_kernel(Gen& keygen, const double* prog_host, size_t words, const MxbColu
     k->fmap = g.fmap; k->imap = g.imap; k->dmap = g.dmap; k->smap = g.smap;
     k->need_blob = g.need_blob;
     k->stage_bytes = (g.need_blob && g.staged) ? g.stage_words * 8 : 0;
+    k->pipe = g.pipe;
+    k->smem_bytes = k->stage_bytes + (g.pipe ? (g.threads / 32) * MXB_PIPE_BYTES_PER_WARP : 0);
     k->threads = env_int("MXB_JIT_THREADS", 640);
     k->hash = hs;
     k->origin = origin;
@@ -858,23 +911,27 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     if (rc) return rc;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (k->stage_bytes > 48 * 1024 && k->smem_attr_dev != dev) {
-        cudaError_t ce = cudaFuncSetAttribute((const void*)k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k->stage_bytes);
+    if (k->smem_bytes > 48 * 1024 && k->smem_attr_dev != dev) {
+        cudaError_t ce = cudaFuncSetAttribute((const void*)k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k->smem_bytes);
         if (ce != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(ce); return MXB_ECUDA; }
         k->smem_attr_dev = dev;
     }
     if (!k->occupancy_known) {
         k->occupancy_known = true;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k->fn, k->threads, k->stage_bytes) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k->fn, k->threads, k->smem_bytes) == cudaSuccess && nb > 0)
             k->blocks_per_sm = nb;
         else { cudaGetLastError(); k->blocks_per_sm = 1; }
     }
     // parameter block: n id0 seed status prog f[] i[] d[] s[]   (all 8-byte words)
     std::vector<uint64_t> pw;
-    pw.reserve(5 + k->fmap.size() + k->imap.size() + k->dmap.size() + k->smap.size() + 4);
+    pw.reserve(6 + k->fmap.size() + k->imap.size() + k->dmap.size() + k->smap.size() + 4);
     pw.push_back((uint64_t)n);
     pw.push_back((uint64_t)id0);
+    uint64_t flags = 1;   // bit 0: the 11 core planes are 16-byte aligned (TMA input pipeline)
+    for (int c = 0; c <= MXB_COL_PROB; ++c)
+        if ((uintptr_t)cols->f64[c] & 15) flags = 0;
+    pw.push_back(flags);
     pw.push_back(seed);
     pw.push_back((uint64_t)(uintptr_t)status);
     pw.push_back((uint64_t)(uintptr_t)prog_dev);
@@ -892,11 +949,12 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     if (blocks < 1) blocks = 1;
     void* args[] = {pw.data()};
     cudaError_t ce = cudaLaunchKernel((const void*)k->fn, dim3((unsigned)blocks), dim3((unsigned)k->threads), args,
-                                      (size_t)k->stage_bytes, stream);
+                                      (size_t)k->smem_bytes, stream);
     if (ce != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaLaunchKernel(jit): ") + cudaGetErrorString(ce); return MXB_ECUDA; }
     char b[256];
-    snprintf(b, sizeof(b), "jit %s (%s): %d regs, %d threads x %lld CTAs (%d/SM), %d B staged, %d scalars", k->hash.c_str(),
-             k->origin.c_str(), k->regs, k->threads, blocks, k->blocks_per_sm, k->stage_bytes, (int)k->smap.size());
+    snprintf(b, sizeof(b), "jit %s (%s): %d regs, %d threads x %lld CTAs (%d/SM), %d B staged, %d scalars, input pipe %s",
+             k->hash.c_str(), k->origin.c_str(), k->regs, k->threads, blocks, k->blocks_per_sm, k->stage_bytes,
+             (int)k->smap.size(), k->pipe ? ((flags & 1) ? "on" : "off (unaligned planes)") : "off");
     g_info = b;
     return MXB_OK;
 }

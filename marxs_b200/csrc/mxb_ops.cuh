@@ -92,7 +92,63 @@ struct Photon {
     V3 ip;          // intersection point of the current element
     double l0, l1;  // local coordinates on the current element
     bool hit;
+    bool unit;      // |dir| == 1 to rounding (fast build: see kTrackUnit in mxb_device.cuh)
 };
+MXB_DEV void photon_loaded(Photon& ph) {   // after pos/dir/pol/energy/prob are in registers
+    ph.hit = false;
+    ph.unit = kTrackUnit && (dot(ph.dir, ph.dir) == 1.0);
+}
+
+// ---------------------------------------------------------------------------
+// per-warp input pipeline.  Each warp owns 11 x 32 doubles of shared memory and one mbarrier; lane 0
+// fetches the NEXT group of 32 photons (11 core planes, 256 B each) with TMA bulk copies while the
+// warp traces the current one, so a warp never waits on DRAM latency at the top of its loop and no
+// registers are spent on double buffering.  Needs 16-byte aligned planes and a full group; anything
+// else (tail, odd plane offsets) is read with ordinary loads.
+// ---------------------------------------------------------------------------
+#define MXB_IN_PLANES 11
+#define MXB_PIPE_WORDS_PER_WARP (MXB_IN_PLANES * 32)
+struct InputPipe {
+    double* buf;      // this warp's slice
+    uint64_t* bar;    // this warp's mbarrier (count 1: lane 0's expect_tx arrive)
+    unsigned phase;
+    bool pending;     // a group is in flight / has landed in buf
+};
+MXB_DEV void pipe_issue(InputPipe& p, double* const* planes, long long base) {   // lane 0 only
+    mbar_expect_tx(p.bar, MXB_IN_PLANES * 256u);
+#pragma unroll
+    for (int k = 0; k < MXB_IN_PLANES; ++k) bulk_g2s(p.buf + 32 * k, planes[k] + base, 256u, p.bar);
+}
+MXB_DEV void pipe_start(InputPipe& p, double* const* planes, long long base, long long n, bool tma_ok, int lane) {
+    p.phase = 0u;
+    p.pending = tma_ok && (base + 32 <= n);
+    if (p.pending && lane == 0) pipe_issue(p, planes, base);
+}
+// photon `base + lane` into registers, then start fetching the group at next_base.  Lanes past the
+// end of the batch re-read the last photon (their results are never stored).
+MXB_DEV void pipe_load(InputPipe& p, double* const* planes, long long base, long long next_base, long long n,
+                       bool tma_ok, int lane, bool active, V3& pos, V3& dir, V3& pol, double& energy, double& prob) {
+    if (p.pending) {
+        mbar_wait(p.bar, p.phase);
+        p.phase ^= 1u;
+        const double* b = p.buf + lane;
+        pos = V3{b[0], b[32], b[64]};
+        dir = V3{b[96], b[128], b[160]};
+        pol = V3{b[192], b[224], b[256]};
+        energy = b[288];
+        prob = b[320];
+        __syncwarp();   // every lane has read its values before the slice is refilled
+    } else {
+        const long long il = active ? (base + lane) : (n - 1);
+        pos = V3{planes[0][il], planes[1][il], planes[2][il]};
+        dir = V3{planes[3][il], planes[4][il], planes[5][il]};
+        pol = V3{planes[6][il], planes[7][il], planes[8][il]};
+        energy = planes[9][il];
+        prob = planes[10][il];
+    }
+    p.pending = tma_ok && (next_base + 32 <= n);
+    if (p.pending && lane == 0) pipe_issue(p, planes, next_base);
+}
 
 MXB_DEV double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
 
@@ -179,12 +235,13 @@ MXB_DEV void accumulate_image(HotCache hc, double* img, PP gp, long long idn, do
 // mirror.py:53-82  params: P[3] f
 template <typename PP>
 MXB_DEV void op_lens(Photon& ph, PP p) {
-    const V3 nd = normalize(ph.dir);
+    const V3 nd = normalize_unless(ph.unit, ph.dir);
     const double f = p[3];
     const V3 t{(p[0] + f * nd.x) - ph.ip.x, (p[1] + f * nd.y) - ph.ip.y, (p[2] + f * nd.z) - ph.ip.z};
     const V3 nd2 = normalize(t);
-    ph.pol = parallel_transport(ph.dir, nd2, ph.pol);
+    ph.pol = parallel_transport(kTrackUnit ? nd : ph.dir, nd2, ph.pol, kTrackUnit, true);
     ph.dir = nd2;
+    ph.unit = true;
 }
 
 // scatter.py:49-77  params: center[3] sig_in sig_perp ; z0, z1 standard normal draws
@@ -203,7 +260,7 @@ MXB_DEV void op_rscatter(Photon& ph, PP p, double z0, double z1, double& a, doub
         b = p[4] * z1;
         out = axangle_rotate_T(radial, b, out);
     }
-    ph.pol = parallel_transport(ph.dir, out, ph.pol);
+    ph.pol = parallel_transport(ph.dir, out, ph.pol, ph.unit, ph.unit);   // rotations keep |dir|
     ph.dir = out;
 }
 // the two normals of op_rscatter: drawn only for non-zero widths; one Philox call when both come
@@ -224,15 +281,16 @@ MXB_DEV void rscatter_draws(double sig_in, double sig_perp, const double* inj0, 
 // scatter.py:109-145  params: sigma ; zn standard normal, u uniform
 template <typename PP>
 MXB_DEV void op_gscatter(Photon& ph, PP p, double zn, double u, double& ang) {
-    const V3 pdir = normalize(ph.dir);
+    const V3 pdir = normalize_unless(ph.unit, ph.dir);
     const V3 guess = (fabs(pdir.x) < 0.99999) ? V3{1, 0, 0} : V3{0, 1, 0};
     const V3 perp = cross(pdir, guess);
     ang = p[0] * zn;
     V3 out = axangle_rotate_T(perp, ang, pdir);
     const double ang2 = u * 2 * 3.141592653589793;
     out = axangle_rotate_T(pdir, ang2, out);
-    ph.pol = parallel_transport(ph.dir, out, ph.pol);
+    ph.pol = parallel_transport(kTrackUnit ? pdir : ph.dir, out, ph.pol, kTrackUnit, true);
     ph.dir = out;
+    ph.unit = true;
 }
 
 // filter.py:90-94  params: n, x[n], y[n]   (n == 0: constant y[0])
@@ -329,7 +387,7 @@ MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy
 template <typename PP, typename GP, typename SELECT>
 MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, int flags, SELECT select,
                         double& order, double& blaze) {
-    const V3 pn = normalize(ph.dir);
+    const V3 pn = normalize_unless(ph.unit, ph.dir);
     const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
     const double wave = div(kEnergy2Wave, ph.energy);
     const double p_l = dot(pn, l);
@@ -348,8 +406,10 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
     const double q = direction * p_n;
     const V3 nd{p_d * dd.x + p_l * l.x + q * n.x, p_d * dd.y + p_l * l.y + q * n.y,
                 p_d * dd.z + p_l * l.z + q * n.z};
-    ph.pol = parallel_transport(ph.dir, nd, ph.pol);
+    // nd is a unit vector by construction (p_d^2 + p_l^2 + p_n^2 = 1 in the orthonormal frame d, l, n)
+    ph.pol = parallel_transport(kTrackUnit ? pn : ph.dir, nd, ph.pol, kTrackUnit, true);
     ph.dir = nd;
+    ph.unit = true;
     mul_prob(st_sm, ph, psel);
 }
 
@@ -377,6 +437,7 @@ MXB_DEV void op_brewster(unsigned long long* st_sm, Photon& ph, PP p) {
     const double nn = sqrt(dot(np_, np_));
     ph.pol = V3{np_.x / nn, np_.y / nn, np_.z / nn};
     ph.dir = nd;
+    ph.unit = false;   // pos4d may carry zoom / shear: renormalise at the next use
     mul_prob(st_sm, ph, clip01(inten));
 }
 
@@ -468,10 +529,10 @@ struct ArrayIter {
 
 // true when `dir` lies inside the cone for which the culling grid is conservative
 template <typename HP>
-MXB_DEV bool cull_cone_ok(HP H, const V3& dir, double& dn) {
+MXB_DEV bool cull_cone_ok(HP H, const V3& dir, bool unit, double& dn) {
     const V3 nb = ld3(H + 3);
     dn = dot(dir, nb);
-    const double d2 = dot(dir, dir);
+    const double d2 = (kTrackUnit && unit) ? 1.0 : dot(dir, dir);
     return dn != 0.0 && (d2 - dn * dn) <= H[15] * dn * dn;
 }
 
@@ -484,7 +545,7 @@ MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int
     it.end = active ? F : 0;
     if (mode == 1 && active) {
         double dn;
-        const bool ok = cull_cone_ok(H, ph.dir, dn);
+        const bool ok = cull_cone_ok(H, ph.dir, ph.unit, dn);
         if (!(dn == dn)) {
             it.end = 0;  // NaN direction can never hit (k >= 0 is false)
         } else if (ok) {
@@ -515,13 +576,9 @@ MXB_DEV bool array_search(ArrayIter& it, BP B, IP cand, int rows_off, int stride
         const int j = it.brute ? it.cur : cand.i32(it.cur);
         ++it.cur;
         const int r = rows_off + j * stride;
-        V3 ipt;
-        double a0, a1;
-        if (plane_intersect(B + r, ph.pos, ph.dir, false, ipt, a0, a1)) {
+        // results go straight into the photon: after a miss ip / l0 / l1 are dead (only read under hit)
+        if (plane_intersect(B + r, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1)) {
             row = r;
-            ph.ip = ipt;
-            ph.l0 = a0;
-            ph.l1 = a1;
             return true;
         }
     }
@@ -536,7 +593,7 @@ MXB_DEV void array_revalidate(ArrayIter& it, HP H, const Photon& ph, int nhit, i
                               int F, unsigned long long* st_sm) {
     if (ph.hit && !it.brute) {
         double dn;
-        const bool ok = cull_cone_ok(H, ph.dir, dn);
+        const bool ok = cull_cone_ok(H, ph.dir, ph.unit, dn);
         if (nhit >= 2 || (dn == dn && !ok)) {
             const int j = (row - rows_off) / stride;
             it.brute = true;

@@ -200,7 +200,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             ph.pos = ph.dir = ph.pol = V3{kNaN, kNaN, kNaN};
             ph.energy = ph.prob = kNaN;
         }
-        ph.hit = false;
+        photon_loaded(ph);
         ph.ip = V3{kNaN, kNaN, kNaN};
         ph.l0 = ph.l1 = kNaN;
 

@@ -41,6 +41,13 @@ def raw_metrics(rep):
     return {n: (u, v) for n, u, v in zip(rows[0], rows[1], rows[2])}
 
 
+def _num(x):
+    try:
+        return float(x or 0)
+    except ValueError:
+        return 0.0
+
+
 def source_tables(rep):
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
                          capture_output=True, text=True).stdout
@@ -59,12 +66,12 @@ def source_tables(rep):
         if hdr is None:
             continue
         if r[0].isdigit():
-            lines.append((cur, int(r[0]), r[1].strip(), float(r[ii] or 0), float(r[si] or 0)))
+            lines.append((cur, int(r[0]), r[1].strip(), _num(r[ii]), _num(r[si])))
         elif r[0] == '' and len(r) > ii and r[2].startswith('0x'):
             m = re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[3])
             try:
                 if m:
-                    ops[m.group(2).split('.')[0]] += float(r[ii])
+                    ops[m.group(2).split('.')[0]] += _num(r[ii])
             except ValueError:
                 pass
     return lines, ops
