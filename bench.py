@@ -377,9 +377,11 @@ def run_engine(args):
                             build=lib.mxb_build_info().decode(), parallelism='photon-range sharding x{0}'.format(world)),
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                               traffic=(traffic * n if traffic else None), peak_source=peak_src,
-                              kernel='mxb_trace_kernel<true>', kernel_ms=kern_ms,
-                              algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
-                              note='fp64-pipe bound (see DESIGN.md): ~3.5k fp64 ops per photon'),
+                              kernel=('mxb_jit_kernel (program-specialised, NVRTC sm_100a)'
+                                      if lib.mxb_jit_info().startswith(b'jit') else 'mxb_trace_kernel<true> (interpreter)'),
+                              kernel_ms=kern_ms, algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
+                              note='one launch traces all photons of the step; limited by dependent fp64 issue latency at '
+                                   '5 warps/SMSP (see DESIGN.md section 4), not by HBM'),
                 clocks=clocks, e2e=e2e, gpu_launches=K, kernel_path=lib.mxb_jit_info().decode(),
                 checks=dict(ccd_hit_fraction=hit_ccd, image_sum=img_sum, prob_range_errors=int(st[0]),
                             multi_hit=int(st[1]), brute_force_photons=int(st[2])))

@@ -109,7 +109,7 @@ def main():
             'sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active',
             'sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active']
     with open(os.path.join(ROOT, 'profiles', tag + '_trace_kernel.md'), 'w') as f:
-        f.write('# {0}: mxb_trace_kernel<true>, ncu --set full --clock-control none ({1:.0e} photons/launch)\n\n'.format(tag, nph))
+        f.write('# {0}: {2}, ncu --set full --clock-control none ({1:.0e} photons/launch)\n\n'.format(tag, nph, m.get('Kernel Name', ('', 'trace kernel'))[1] if 'Kernel Name' in m else 'trace kernel'))
         f.write('Source: `{0}` (scratch), launch list `{1}`.\n\n'.format(os.path.basename(rep), os.path.basename(lpath)))
         f.write('| metric | value | unit |\n|---|---|---|\n')
         for k in keys:
