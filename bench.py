@@ -7,8 +7,8 @@
 One *step* = one pass of the fused trace (HRMA FlatStack -> HETG 336-facet array ->
 ACIS-S 6 chips, all 21 diagnostic columns of the reference materialised, detector
 image accumulated by the same kernel) over one batch of 1e7 synthetic photons per GPU.  Inputs are resident in HBM when the timed region
-starts; every step reads a fresh input copy (the trace is in place), and one copy
-(0.88 GB read) is much larger than the 126 MB L2.  ``e2e`` is the same trace through
+starts; every step reads the same pristine input table out of place (mxb_trace_from), and
+one pass (0.88 GB read, 2.4 GB written) is much larger than the 126 MB L2.  ``e2e`` is the same trace through
 ``mxb_trace_host`` with pinned HOST buffers, H2D and D2H inside the timed region.
 Prints ONE JSON line (rank 0).
 """
@@ -275,29 +275,23 @@ def run_engine(args):
     if not args.no_image:
         inst.elements[2].image = image
 
-    # one input copy per step (the trace is in place); outputs are shared
+    # every step reads the same pristine input table (0.88 GB of core planes, never modified) and
+    # writes all results into one output table: mxb_trace_from = instrument(photons.copy()) fused
     base = synth_c2_device(n, 20261017 + rank, device)
     base.id0 = rank * n
     lw = Lowering(base.colnames, meta=base.meta)
     inst._lower(lw)
     prog = lw.finish()
     blob = prog.device_blob(device)
-    batches = [base] + [base.copy() for _ in range(K + W - 1)]
-    structs = []
-    for b in batches:
-        for name in prog.out_f64 + prog.out_i64:
-            if name not in b and name not in prog.aux:
-                if name in batches[0]:
-                    b._store[name] = batches[0].storage(name)
-        cols, _ = prog.columns_struct(b)
-        structs.append(cols)
+    out0 = base.copy()
+    cols, _ = prog.columns_struct(out0)
+    src = prog.source_planes(base, n)
     status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
-    out0 = batches[0]
 
     def step(k):
-        rc = lib.mxb_trace(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, ctypes.byref(structs[k]),
-                           n, rank * n, 1234 + k, status.data_ptr(), stream)
+        rc = lib.mxb_trace_from(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, src, ctypes.byref(cols),
+                                n, rank * n, 1234 + k, status.data_ptr(), stream)
         if rc:
             raise RuntimeError(lib.mxb_last_error().decode())
 
@@ -332,6 +326,7 @@ def run_engine(args):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ka, kb)]))
     kern_ms = mdist.max_over_ranks(kern_ms, device)
     clocks = sampler.stop() if rank == 0 else None
+    kernel_path = lib.mxb_jit_info().decode()
     st = status.cpu().numpy()
     hit_ccd = float((out0['CCD_ID'] >= 0).double().mean())
     img_sum = float(image.sum())
@@ -373,16 +368,16 @@ def run_engine(args):
                 dtype='f64', data='synthetic',
                 config=dict(workload=WORKLOAD, photons_per_gpu_per_step=n, facets=336, chips=6,
                             diagnostic_columns=DIAG_COLS, rng='device Philox4x32-10',
-                            l2='every step reads a fresh 0.88 GB input copy (> 126 MB L2); no flush needed',
+                            l2='every step streams the 0.88 GB input table and 2.4 GB of outputs (>> 126 MB L2); no flush needed',
                             build=lib.mxb_build_info().decode(), parallelism='photon-range sharding x{0}'.format(world)),
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                               traffic=(traffic * n if traffic else None), peak_source=peak_src,
                               kernel=('mxb_jit_kernel (program-specialised, NVRTC sm_100a)'
-                                      if lib.mxb_jit_info().startswith(b'jit') else 'mxb_trace_kernel<true> (interpreter)'),
+                                      if kernel_path.startswith('jit') else 'mxb_trace_kernel<true> (interpreter)'),
                               kernel_ms=kern_ms, algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
                               note='one launch traces all photons of the step; limited by dependent fp64 issue latency at '
                                    '5 warps/SMSP (see DESIGN.md section 4), not by HBM'),
-                clocks=clocks, e2e=e2e, gpu_launches=K, kernel_path=lib.mxb_jit_info().decode(),
+                clocks=clocks, e2e=e2e, gpu_launches=K, kernel_path=kernel_path,
                 checks=dict(ccd_hit_fraction=hit_ccd, image_sum=img_sum, prob_range_errors=int(st[0]),
                             multi_hit=int(st[1]), brute_force_photons=int(st[2])))
     if world == 1 and not args.no_cpu:
@@ -395,7 +390,7 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--photons', type=int, default=N_PER_GPU, help='photons per GPU per step')

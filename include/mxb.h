@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 4
+#define MXB_ABI_VERSION 5
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -149,6 +149,15 @@ void        mxb_host_release(void);      /* free the staging buffers mxb_trace_h
 int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host,
               const MxbColumns* cols, int64_t n, int64_t photon_id0, uint64_t seed,
               unsigned long long* status_dev, void* stream);
+
+/* mxb_trace reading the photons from OTHER planes than it writes: src_core[0..10] are the 11 core
+ * planes (pos xyz, dir xyz, polarization xyz, energy, probability) of the input, left untouched; all
+ * results, including the core planes, go to cols.  This is `instrument(photons.copy())` - the idiom
+ * the reference asks of callers that need their input afterwards (optics/base.py:168-173) - without
+ * the copy.  src_core == NULL is mxb_trace (in place). */
+int mxb_trace_from(const double* prog_dev, size_t prog_words, const double* prog_host,
+                   const double* const* src_core, const MxbColumns* cols, int64_t n,
+                   int64_t photon_id0, uint64_t seed, unsigned long long* status_dev, void* stream);
 
 /* Kernel selection for mxb_trace / mxb_trace_host.  A program runs either on the op-list
  * interpreter kernel or on a kernel specialised for the program's structure (compiled once with

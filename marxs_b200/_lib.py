@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 4
+MXB_ABI_VERSION = 5
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -63,6 +63,8 @@ def load(strict=None):
     lib.mxb_host_release.restype = None
     lib.mxb_trace.restype = ci
     lib.mxb_trace.argtypes = [vp, sz, vp, ctypes.POINTER(MxbColumns), i64, i64, u64, vp, vp]
+    lib.mxb_trace_from.restype = ci
+    lib.mxb_trace_from.argtypes = [vp, sz, vp, vp, ctypes.POINTER(MxbColumns), i64, i64, u64, vp, vp]
     lib.mxb_trace_host.restype = ci
     lib.mxb_trace_host.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), ctypes.POINTER(MxbColumns), i64, i64, i64, u64, vp]
     lib.mxb_plane_intersect.restype = ci
@@ -102,5 +104,5 @@ def check(lib, rc, what):
 
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
-                    'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d',
+                    'mxb_trace_from', 'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d',
                     'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile']

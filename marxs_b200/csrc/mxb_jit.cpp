@@ -503,7 +503,7 @@ struct Gen {
         if (!emit) return true;
         std::string body;
         body.swap(src);         // body holds the op code; src receives the preamble
-        if ((6 + fmap.size() + imap.size() + dmap.size() + smap.size()) * 8 > 32000) return fail("program has too many scalar parameters");
+        if ((17 + fmap.size() + imap.size() + dmap.size() + smap.size()) * 8 > 32000) return fail("program has too many scalar parameters");
         out("// generated by libmxb (mxb_jit.cpp): specialised driver of one element program");
         out("#include \"mxb_ops.cuh\"");
         out("using namespace mxb;");
@@ -521,6 +521,7 @@ struct Gen {
         out("    unsigned long long seed;");
         out("    unsigned long long* status;");
         out("    const double* prog;");
+        out("    const double* in[11];  // core planes the photons are read from (== f[0..10] in place)");
         out("    double* f[%d];", (int)std::max<size_t>(fmap.size(), 1));
         out("    long long* i[%d];", (int)std::max<size_t>(imap.size(), 1));
         out("    const double* d[%d];", (int)std::max<size_t>(dmap.size(), 1));
@@ -579,19 +580,19 @@ struct Gen {
         out("    pipe.bar = nullptr;");
         out("#endif");
         out("    long long base = (long long)blockIdx.x * JIT_THREADS + (tid & ~31);   // whole warps");
-        out("    pipe_start(pipe, P.f, base, P.n, tma_ok, lane);");
+        out("    pipe_start(pipe, P.in, base, P.n, tma_ok, lane);");
         out("    for (; base < P.n; base += stride) {");
         out("        const long long i = base + lane;");
         out("        const bool active = i < P.n;");
         out("        const unsigned long long gid = (unsigned long long)(P.id0 + i);");
         out("        (void)gid;");
         out("        Photon ph;");
-        out("        pipe_load(pipe, P.f, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
+        out("        pipe_load(pipe, P.in, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
         out("        photon_loaded(ph);");
         out("#if JIT_PREFETCH");
         out("        if (i + stride < P.n) {   // next group's inputs -> L2 while this one is traced");
         out("#pragma unroll");
-        out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.f[k] + i + stride));");
+        out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.in[k] + i + stride));");
         out("        }");
         out("#endif");
         out("        ph.ip = V3{kNaN, kNaN, kNaN};");
@@ -604,6 +605,7 @@ struct Gen {
         out("            P.f[3][i] = ph.dir.x; P.f[4][i] = ph.dir.y; P.f[5][i] = ph.dir.z;");
         out("            P.f[6][i] = ph.pol.x; P.f[7][i] = ph.pol.y; P.f[8][i] = ph.pol.z;");
         out("            P.f[10][i] = ph.prob;");
+        out("            if (P.flags & 2) P.f[9][i] = ph.energy;   // out of place: energy travels too");
         out("        }");
         out("    }");
         out("    if ((tid & 31) == 0) {");
@@ -898,8 +900,8 @@ std::string source_for(const double* prog_host, size_t words, const MxbColumns* 
 }
 
 int launch(const double* prog_dev, const double* prog_host, size_t words, int n_ops, int stage_words,
-           const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed, unsigned long long* status,
-           cudaStream_t stream, bool fast_build, std::string* err, bool* unavailable) {
+           const double* const* src, const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed,
+           unsigned long long* status, cudaStream_t stream, bool fast_build, std::string* err, bool* unavailable) {
     (void)n_ops; (void)stage_words;
     *unavailable = false;
     if (!nvrtc().h) { *unavailable = true; *err = "NVRTC unavailable: " + nvrtc().why; return MXB_EJIT; }
@@ -925,16 +927,18 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     }
     // parameter block: n id0 seed status prog f[] i[] d[] s[]   (all 8-byte words)
     std::vector<uint64_t> pw;
-    pw.reserve(6 + k->fmap.size() + k->imap.size() + k->dmap.size() + k->smap.size() + 4);
+    pw.reserve(17 + k->fmap.size() + k->imap.size() + k->dmap.size() + k->smap.size() + 4);
     pw.push_back((uint64_t)n);
     pw.push_back((uint64_t)id0);
-    uint64_t flags = 1;   // bit 0: the 11 core planes are 16-byte aligned (TMA input pipeline)
+    uint64_t flags = 1;   // bit 0: the 11 source planes are 16-byte aligned (TMA input pipeline)
     for (int c = 0; c <= MXB_COL_PROB; ++c)
-        if ((uintptr_t)cols->f64[c] & 15) flags = 0;
+        if ((uintptr_t)(src ? src[c] : cols->f64[c]) & 15) flags = 0;
+    if (src && src[MXB_COL_ENERGY] != cols->f64[MXB_COL_ENERGY]) flags |= 2;   // bit 1: store energy
     pw.push_back(flags);
     pw.push_back(seed);
     pw.push_back((uint64_t)(uintptr_t)status);
     pw.push_back((uint64_t)(uintptr_t)prog_dev);
+    for (int c = 0; c <= MXB_COL_PROB; ++c) pw.push_back((uint64_t)(uintptr_t)(src ? src[c] : cols->f64[c]));
     for (int c : k->fmap) pw.push_back((uint64_t)(uintptr_t)cols->f64[c]);
     if (k->fmap.empty()) pw.push_back(0);
     for (int c : k->imap) pw.push_back((uint64_t)(uintptr_t)cols->i64[c]);

@@ -24,8 +24,8 @@ long long auto_threshold();    // photons per launch from which `auto` specialis
 // Launch the specialised kernel of this program.  Returns MXB_OK, or an MXB_E* code with *err set.
 // `unavailable` is set when NVRTC cannot be loaded at all (auto mode then uses the interpreter).
 int launch(const double* prog_dev, const double* prog_host, size_t words, int n_ops, int stage_words,
-           const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed, unsigned long long* status,
-           cudaStream_t stream, bool fast_build, std::string* err, bool* unavailable);
+           const double* const* src, const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed,
+           unsigned long long* status, cudaStream_t stream, bool fast_build, std::string* err, bool* unavailable);
 
 // CUDA source of the specialised kernel (for inspection / profiles); empty + *err on failure
 std::string source_for(const double* prog_host, size_t words, const MxbColumns* cols, std::string* err);

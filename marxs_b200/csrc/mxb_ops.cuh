@@ -114,19 +114,19 @@ struct InputPipe {
     unsigned phase;
     bool pending;     // a group is in flight / has landed in buf
 };
-MXB_DEV void pipe_issue(InputPipe& p, double* const* planes, long long base) {   // lane 0 only
+MXB_DEV void pipe_issue(InputPipe& p, const double* const* planes, long long base) {   // lane 0 only
     mbar_expect_tx(p.bar, MXB_IN_PLANES * 256u);
 #pragma unroll
     for (int k = 0; k < MXB_IN_PLANES; ++k) bulk_g2s(p.buf + 32 * k, planes[k] + base, 256u, p.bar);
 }
-MXB_DEV void pipe_start(InputPipe& p, double* const* planes, long long base, long long n, bool tma_ok, int lane) {
+MXB_DEV void pipe_start(InputPipe& p, const double* const* planes, long long base, long long n, bool tma_ok, int lane) {
     p.phase = 0u;
     p.pending = tma_ok && (base + 32 <= n);
     if (p.pending && lane == 0) pipe_issue(p, planes, base);
 }
 // photon `base + lane` into registers, then start fetching the group at next_base.  Lanes past the
 // end of the batch re-read the last photon (their results are never stored).
-MXB_DEV void pipe_load(InputPipe& p, double* const* planes, long long base, long long next_base, long long n,
+MXB_DEV void pipe_load(InputPipe& p, const double* const* planes, long long base, long long next_base, long long n,
                        bool tma_ok, int lane, bool active, V3& pos, V3& dir, V3& pol, double& energy, double& prob) {
     if (p.pending) {
         mbar_wait(p.bar, p.phase);

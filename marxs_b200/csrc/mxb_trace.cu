@@ -49,6 +49,8 @@ struct TraceParams {
     long long id0;
     unsigned long long seed;
     unsigned long long* status;
+    const double* src[11];   // core planes the photons are READ from (== cols.f64[0..10] in place)
+    int store_energy;        // out of place: energy has to be copied to the destination
     MxbColumns cols;
 };
 
@@ -190,12 +192,11 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         ctx.active = i < P.n;
         Photon ph;
         if (ctx.active) {
-            const MxbColumns& C = P.cols;
-            ph.pos = V3{C.f64[0][i], C.f64[1][i], C.f64[2][i]};
-            ph.dir = V3{C.f64[3][i], C.f64[4][i], C.f64[5][i]};
-            ph.pol = V3{C.f64[6][i], C.f64[7][i], C.f64[8][i]};
-            ph.energy = C.f64[9][i];
-            ph.prob = C.f64[10][i];
+            ph.pos = V3{P.src[0][i], P.src[1][i], P.src[2][i]};
+            ph.dir = V3{P.src[3][i], P.src[4][i], P.src[5][i]};
+            ph.pol = V3{P.src[6][i], P.src[7][i], P.src[8][i]};
+            ph.energy = P.src[9][i];
+            ph.prob = P.src[10][i];
         } else {
             ph.pos = ph.dir = ph.pol = V3{kNaN, kNaN, kNaN};
             ph.energy = ph.prob = kNaN;
@@ -458,6 +459,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             C.f64[3][i] = ph.dir.x; C.f64[4][i] = ph.dir.y; C.f64[5][i] = ph.dir.z;
             C.f64[6][i] = ph.pol.x; C.f64[7][i] = ph.pol.y; C.f64[8][i] = ph.pol.z;
             C.f64[10][i] = ph.prob;
+            if (P.store_energy) C.f64[9][i] = ph.energy;
         }
     }
 
@@ -584,8 +586,8 @@ int validate_program(const double* h, size_t words, int* n_ops, int* stage_words
 
 thread_local std::string g_kernel_info = "none";
 
-int launch_interp(const double* prog_dev, int n_ops, int stage_words, const MxbColumns* cols, int64_t n,
-                  int64_t id0, uint64_t seed, unsigned long long* status_dev, cudaStream_t stream) {
+int launch_interp(const double* prog_dev, int n_ops, int stage_words, const double* const* src, const MxbColumns* cols,
+                  int64_t n, int64_t id0, uint64_t seed, unsigned long long* status_dev, cudaStream_t stream) {
     TraceParams P;
     P.prog = prog_dev;
     P.n_ops = n_ops;
@@ -595,6 +597,11 @@ int launch_interp(const double* prog_dev, int n_ops, int stage_words, const MxbC
     P.seed = seed;
     P.status = status_dev;
     P.cols = *cols;
+    P.store_energy = 0;
+    for (int k = 0; k <= MXB_COL_PROB; ++k) {
+        P.src[k] = src ? src[k] : cols->f64[k];
+        if (k == MXB_COL_ENERGY && P.src[k] != cols->f64[k]) P.store_energy = 1;
+    }
     const size_t stage_bytes = (size_t)stage_words * 8;
     const int grid = grid_for(n, kThreads, 1);
     if (stage_bytes <= (size_t)kMaxSmemStageBytes) {
@@ -621,13 +628,13 @@ constexpr bool kFastBuild = false;
 
 // kernel selection (see mxb_set_jit in mxb.h): specialised kernel or the interpreter
 int launch_trace(const double* prog_dev, const double* prog_host, size_t prog_words, int n_ops, int stage_words,
-                 const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed, unsigned long long* status_dev,
-                 cudaStream_t stream) {
+                 const double* const* src, const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed,
+                 unsigned long long* status_dev, cudaStream_t stream) {
     const mxbjit::Mode mode = mxbjit::mode();
     if (mode == mxbjit::kForce || (mode == mxbjit::kAuto && n >= mxbjit::auto_threshold())) {
         std::string err;
         bool unavailable = false;
-        const int rc = mxbjit::launch(prog_dev, prog_host, prog_words, n_ops, stage_words, cols, n, id0, seed,
+        const int rc = mxbjit::launch(prog_dev, prog_host, prog_words, n_ops, stage_words, src, cols, n, id0, seed,
                                       status_dev, stream, kFastBuild, &err, &unavailable);
         if (rc == MXB_OK) {
             g_kernel_info = mxbjit::last_info();
@@ -636,7 +643,7 @@ int launch_trace(const double* prog_dev, const double* prog_host, size_t prog_wo
         if (mode == mxbjit::kForce || !unavailable) return fail(rc, err);
         // auto mode without NVRTC on this machine: the interpreter kernel runs the program
     }
-    return launch_interp(prog_dev, n_ops, stage_words, cols, n, id0, seed, status_dev, stream);
+    return launch_interp(prog_dev, n_ops, stage_words, src, cols, n, id0, seed, status_dev, stream);
 }
 
 // cached staging state of mxb_trace_host (one per host thread)
@@ -731,18 +738,26 @@ int mxb_device_count(void) {
     return n;
 }
 
-int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host, const MxbColumns* cols,
-              int64_t n, int64_t photon_id0, uint64_t seed, unsigned long long* status_dev, void* stream) {
+int mxb_trace_from(const double* prog_dev, size_t prog_words, const double* prog_host, const double* const* src_core,
+                   const MxbColumns* cols, int64_t n, int64_t photon_id0, uint64_t seed,
+                   unsigned long long* status_dev, void* stream) {
     int n_ops = 0, stage_words = 0;
     const int rc = validate_program(prog_host, prog_words, &n_ops, &stage_words);
     if (rc) return rc;
     if (!prog_dev || !cols || !status_dev) return fail(MXB_EINVAL, "mxb_trace: null pointer");
     if (n < 0) return fail(MXB_EINVAL, "mxb_trace: negative photon count");
     if (n == 0) return MXB_OK;
-    for (int k = 0; k <= MXB_COL_PROB; ++k)
+    for (int k = 0; k <= MXB_COL_PROB; ++k) {
         if (!cols->f64[k]) return fail(MXB_EINVAL, "mxb_trace: core photon column missing");
-    return launch_trace(prog_dev, prog_host, prog_words, n_ops, stage_words, cols, n, photon_id0, seed,
+        if (src_core && !src_core[k]) return fail(MXB_EINVAL, "mxb_trace_from: source plane missing");
+    }
+    return launch_trace(prog_dev, prog_host, prog_words, n_ops, stage_words, src_core, cols, n, photon_id0, seed,
                         status_dev, (cudaStream_t)stream);
+}
+
+int mxb_trace(const double* prog_dev, size_t prog_words, const double* prog_host, const MxbColumns* cols,
+              int64_t n, int64_t photon_id0, uint64_t seed, unsigned long long* status_dev, void* stream) {
+    return mxb_trace_from(prog_dev, prog_words, prog_host, nullptr, cols, n, photon_id0, seed, status_dev, stream);
 }
 
 int mxb_plane_intersect(const double* geom14_host, int circular, const double* const dir[3],
@@ -884,8 +899,8 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             }
             HTRY(cudaEventRecord(S.ev_in[b], s_in));
             HTRY(cudaStreamWaitEvent(s_k, S.ev_in[b], 0));
-            rc = launch_trace(dprog, prog_host, prog_words, n_ops, stage_words, &dc, m, photon_id0 + off, seed,
-                              dstatus, s_k);
+            rc = launch_trace(dprog, prog_host, prog_words, n_ops, stage_words, nullptr, &dc, m, photon_id0 + off,
+                              seed, dstatus, s_k);
             if (rc) { result = rc; goto cleanup; }
             HTRY(cudaEventRecord(S.ev_k[b], s_k));
             HTRY(cudaStreamWaitEvent(s_out, S.ev_k[b], 0));

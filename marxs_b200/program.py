@@ -558,9 +558,27 @@ class Program:
                 cols.draws[k] = t.data_ptr()
         return cols, keep
 
-    def run(self, photons, draws=None, seed=0, id0=0, check=True, strict=None):
+    def source_planes(self, source, n):
+        """ctypes array of the 11 core plane pointers of ``source`` (mxb_trace_from)."""
+        ptrs = (ctypes.c_void_p * 11)()
+        for vi, name in enumerate(('pos', 'dir', 'polarization')):
+            st = source.storage(name)
+            if st.dtype != torch.float64 or not st.is_contiguous() or st.shape != (4, n):
+                raise ValueError('source column {0} must be a contiguous (4, N) float64 block'.format(name))
+            for k in range(3):
+                ptrs[3 * vi + k] = st.data_ptr() + k * n * 8
+        for idx, name in ((9, 'energy'), (10, 'probability')):
+            st = source.storage(name)
+            if st.dtype != torch.float64 or not st.is_contiguous() or st.shape != (n,):
+                raise ValueError('source column {0} must be contiguous (N,) float64'.format(name))
+            ptrs[idx] = st.data_ptr()
+        return ptrs
+
+    def run(self, photons, draws=None, seed=0, id0=0, check=True, strict=None, source=None):
         """Launch on ``photons`` (in place).  With ``check`` the status block is read
-        back (one sync) and reference errors are raised (optics/base.py:45-46)."""
+        back (one sync) and reference errors are raised (optics/base.py:45-46).
+        ``source``: another table on the same device whose core columns are READ instead of
+        those of ``photons`` (which then only receives results: mxb_trace_from)."""
         if photons.device.type != 'cuda':
             raise _lib.MxbError('marxs_b200 runs on CUDA devices only (no CPU fallback); '
                                 'photons are on {0}'.format(photons.device))
@@ -576,8 +594,13 @@ class Program:
             blob = self.device_blob(photons.device)
             status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device=photons.device)
             stream = torch.cuda.current_stream(photons.device).cuda_stream
-            rc = lib.mxb_trace(blob.data_ptr(), self.blob.size, self.blob.ctypes.data, ctypes.byref(cols),
-                               n, int(id0), int(seed) & 0xFFFFFFFFFFFFFFFF, status.data_ptr(), stream)
+            src = None
+            if source is not None:
+                if source.device != photons.device or len(source) != n:
+                    raise ValueError('source and destination tables must have the same length and device')
+                src = self.source_planes(source, n)
+            rc = lib.mxb_trace_from(blob.data_ptr(), self.blob.size, self.blob.ctypes.data, src, ctypes.byref(cols),
+                                    n, int(id0), int(seed) & 0xFFFFFFFFFFFFFFFF, status.data_ptr(), stream)
             _lib.check(lib, rc, 'mxb_trace')
             for t in keep:
                 t.record_stream(torch.cuda.current_stream(photons.device))

@@ -17,7 +17,7 @@ from .program import Lowering, NotFusable
 from . import rng
 
 __all__ = ['SimulationSetupError', 'BaseContainer', 'Sequence', 'Parallel', 'ParallelCalculated',
-           'KeepCol', 'Propagator', 'propagate', 'run_fused']
+           'KeepCol', 'Propagator', 'propagate', 'run_fused', 'trace_from']
 
 
 class SimulationSetupError(Exception):
@@ -60,6 +60,52 @@ def run_fused(elements, photons, check=True):
         prog.run(photons, draws=draws, seed=rng.next_launch_seed(), id0=getattr(photons, 'id0', 0), check=check)
         i = j
     return photons
+
+
+def trace_from(instrument, source, out=None, check=True):
+    """``instrument(source.copy())`` without the copy: the fused kernel reads the photons from
+    ``source`` (left untouched) and writes every result into ``out`` (a new table by default; pass
+    the table of a previous call to reuse its memory).  The reference mutates its argument and
+    asks callers that still need the input to copy it first (optics/base.py:168-173).
+    Instruments that do not lower to one program fall back to copy + call."""
+    import torch
+    from .photons import PhotonBatch
+    elements = [instrument]
+    lw = Lowering(source.colnames, meta=source.meta)
+    try:
+        if not _lowerable(instrument):
+            raise NotFusable('not lowerable')
+        instrument._lower(lw)
+    except NotFusable:
+        return instrument(source.copy() if out is None else PhotonBatch(source, device=source.device))
+    prog = lw.finish()
+    n = len(source)
+    if out is None:
+        out = PhotonBatch(device=source.device, meta=type(source.meta)(source.meta))
+    out.id0 = getattr(source, 'id0', 0)
+    for name in ('pos', 'dir', 'polarization'):
+        if name not in out or out.storage(name).shape != (4, n):
+            out.new_column(name, torch.float64, vector=True, n=n)
+        if name in source:
+            out.storage(name)[3].copy_(source.storage(name)[3])     # w planes are never touched by kernels
+        else:
+            out.storage(name)[3].fill_(1. if name == 'pos' else 0.)
+    for name in ('energy', 'probability'):
+        if name not in out or out.storage(name).shape != (n,):
+            out.new_column(name, torch.float64, n=n)
+    for name in source.colnames:      # other columns of the input travel by reference-free copy
+        if name not in out:
+            out[name] = source[name]
+    src = source
+    if lw.needs_pos and 'pos' not in source:
+        src = PhotonBatch(device=source.device)
+        for name in source.colnames:
+            src._store[name] = source.storage(name)
+        src.new_column('pos', torch.float64, fill=0., vector=True, n=n)[3] = 1.
+        out.storage('pos')[3].fill_(1.)
+    draws = rng.take_injected(len(prog.slot_kinds))
+    prog.run(out, draws=draws, seed=rng.next_launch_seed(), id0=out.id0, check=check, source=src)
+    return out
 
 
 class BaseContainer(SimulationSequenceElement):

@@ -686,6 +686,57 @@ def test_host_buffer_path_matches_device_path(mode):
     assert np.array_equal(src['pos'], table['pos'])              # inputs untouched
 
 
+def test_trace_from_is_copy_then_trace(mode):
+    """mxb_trace_from: reading the photons from another table gives exactly instrument(source.copy())
+    and leaves the source untouched (both kernels, injected draws and device Philox)."""
+    mb = _mb()
+    from marxs_b200 import simulator
+    from marxs_b200.missions import chandra
+    rng = np.random.default_rng(SEED + 21)
+    n = 30000
+    radii = mo.HRMA_RADII
+    shell = rng.integers(0, 4, n)
+    r = np.sqrt(rng.uniform(radii[shell, 0] ** 2, radii[shell, 1] ** 2))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    pos = np.ones((n, 4))
+    pos[:, 0], pos[:, 1], pos[:, 2] = 10161.65, r * np.cos(phi), r * np.sin(phi)
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    pol = np.zeros((n, 4))
+    pol[:, 2] = 1.
+    table = mo.PhotonTable(pos=pos, dir=d, energy=rng.uniform(0.5, 8., n), polarization=pol, probability=rng.uniform(0.5, 1, n))
+    table.meta['ROLL_PNT'] = (0., 'roll')
+    inst = simulator.Sequence(elements=[chandra.HRMA(), chandra.HETG(),
+                                        chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])])
+    for draws in ([rng.standard_normal(n), rng.standard_normal(n), rng.random(n)], None):
+        source = mb.PhotonBatch(table, device='cuda')
+        before = source.to_numpy()
+        if draws is not None:
+            with mb.inject_draws(draws):
+                want = inst(source.copy()).to_numpy()
+            with mb.inject_draws(draws):
+                got = simulator.trace_from(inst, source)
+        else:
+            mb.set_seed(77)
+            want = inst(source.copy()).to_numpy()
+            mb.set_seed(77)
+            got = simulator.trace_from(inst, source)
+        got2 = got.to_numpy()
+        assert set(got2) == set(want)
+        for c in want:
+            assert np.array_equal(got2[c], want[c], equal_nan=True), c
+        after = source.to_numpy()
+        for c in before:
+            assert np.array_equal(before[c], after[c]), c
+        # reusing the output table of a previous call
+        if draws is None:
+            mb.set_seed(77)
+            again = simulator.trace_from(inst, source, out=got)
+            assert again is got
+            for c in want:
+                assert np.array_equal(again.to_numpy()[c], want[c], equal_nan=True), c
+
+
 def test_fused_detector_image():
     """The image accumulated inside the trace kernel == mxb_hist2d on the output columns == numpy."""
     mb = _mb()
