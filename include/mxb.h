@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 5
+#define MXB_ABI_VERSION 6
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -210,6 +210,17 @@ int mxb_parallel_transport(const double* const dir_old[3], const double* const d
 int mxb_hist2d(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
                int n_sel, double x0, double y0, int64_t n, int nx, int ny, double* img,
                unsigned long long* counts, void* stream);
+
+/* Event compaction for the multi-GPU epilogue (NCCL all-gather-v of detector events): rows i with
+ * sel[i] >= sel_min (sel == NULL: all) and weight[i] > 0 (weight == NULL: no test; NaN drops) are
+ * packed densely, in order, for n_planes (<= 64) planes of 8-byte values (fp64 or int64 columns):
+ * dst_planes[p][k] = src_planes[p][i_k].  src/dst_planes are HOST arrays of device pointers; every
+ * dst plane must hold n values.  *n_out_dev (device) receives the number of rows kept.  workspace:
+ * device memory of mxb_compact_workspace(n) bytes.  Asynchronous on `stream`. */
+size_t mxb_compact_workspace(int64_t n);
+int mxb_compact_events(const void* const* src_planes, void* const* dst_planes, int n_planes,
+                       const long long* sel, long long sel_min, const double* weight, int64_t n,
+                       long long* n_out_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 5
+MXB_ABI_VERSION = 6
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -79,6 +79,10 @@ def load(strict=None):
     lib.mxb_jit_info.restype = ctypes.c_char_p
     lib.mxb_jit_source.restype = ctypes.c_longlong
     lib.mxb_jit_source.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), vp, sz]
+    lib.mxb_compact_workspace.restype = sz
+    lib.mxb_compact_workspace.argtypes = [i64]
+    lib.mxb_compact_events.restype = ci
+    lib.mxb_compact_events.argtypes = [vp, vp, ci, vp, ctypes.c_longlong, vp, i64, vp, vp, sz, vp]
     lib.mxb_jit_compile.restype = ctypes.c_longlong
     lib.mxb_jit_compile.argtypes = [vp, sz, ctypes.POINTER(MxbColumns)]
     if lib.mxb_version() != MXB_ABI_VERSION:
@@ -105,4 +109,4 @@ def check(lib, rc, what):
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
                     'mxb_trace_from', 'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d',
-                    'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile']
+                    'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events']

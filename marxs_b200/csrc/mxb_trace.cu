@@ -552,6 +552,92 @@ hist2d_kernel(const double* x, const double* y, const double* w, const long long
     hot_flush(hot, threadIdx.x, blockDim.x);
 }
 
+// ---------------------------------------------------------------------------
+// event compaction (multi-GPU epilogue): rows with sel >= sel_min (and weight > 0) of up to 64
+// 8-byte planes are packed densely, order preserved.  Three passes: per-block counts, one-block scan,
+// scatter (flags are recomputed: cheaper than storing them).  HBM-bound: 8 B read per row for the
+// selector (+8 weight) twice, 8 B read + 8 B written per selected row and plane.
+// ---------------------------------------------------------------------------
+constexpr int kCompactThreads = 1024;
+constexpr int kCompactMaxPlanes = 64;
+struct CompactPlanes {
+    const unsigned long long* src[kCompactMaxPlanes];
+    unsigned long long* dst[kCompactMaxPlanes];
+};
+__device__ __forceinline__ bool compact_keep(const long long* sel, long long sel_min, const double* w, long long i,
+                                             long long n) {
+    if (i >= n) return false;
+    bool k = sel ? (sel[i] >= sel_min) : true;
+    if (w) k = k && (w[i] > 0.0);   // NaN weights are dropped
+    return k;
+}
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(const long long* sel, long long sel_min, const double* w, long long n, long long* block_counts) {
+    const long long i = (long long)blockIdx.x * kCompactThreads + threadIdx.x;
+    const int c = __syncthreads_count(compact_keep(sel, sel_min, w, i, n) ? 1 : 0);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(long long* block_counts, long long n_blocks, long long* n_out) {
+    // exclusive scan in place, one CTA: chunks of 1024 with a running carry
+    __shared__ long long warp_sum[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < n_blocks; base += 1024) {
+        const long long k = base + threadIdx.x;
+        const long long v = k < n_blocks ? block_counts[k] : 0;
+        long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            long long ws = warp_sum[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, ws, d);
+                if (threadIdx.x >= d) ws += y;
+            }
+            warp_sum[threadIdx.x] = ws;   // inclusive over warps
+        }
+        __syncthreads();
+        const long long before = ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0) + carry;
+        if (k < n_blocks) block_counts[k] = before + x - v;   // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+__global__ void __launch_bounds__(kCompactThreads)
+compact_scatter_kernel(const __grid_constant__ CompactPlanes P, int n_planes, const long long* sel, long long sel_min,
+                       const double* w, long long n, const long long* block_offsets) {
+    __shared__ int warp_cnt[kCompactThreads / 32];
+    const long long i = (long long)blockIdx.x * kCompactThreads + threadIdx.x;
+    const bool keep = compact_keep(sel, sel_min, w, i, n);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+        int c = warp_cnt[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, c, d);
+            if (lane >= d) c += y;
+        }
+        warp_cnt[lane] = c;   // inclusive
+    }
+    __syncthreads();
+    if (!keep) return;
+    const long long o = block_offsets[blockIdx.x] + (warp ? warp_cnt[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u));
+    for (int p = 0; p < n_planes; ++p) P.dst[p][o] = P.src[p][i];
+}
+
 int sm_count() {
     static int sms = 0;
     if (sms == 0) {
@@ -729,6 +815,39 @@ long long mxb_jit_compile(const double* prog_host, size_t prog_words, const MxbC
     return sz;
 }
 
+size_t mxb_compact_workspace(int64_t n) {
+    const int64_t blocks = (n + kCompactThreads - 1) / kCompactThreads;
+    return (size_t)(blocks + 1) * sizeof(long long);
+}
+
+int mxb_compact_events(const void* const* src_planes, void* const* dst_planes, int n_planes, const long long* sel,
+                       long long sel_min, const double* weight, int64_t n, long long* n_out_dev, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!src_planes || !dst_planes || !n_out_dev || !workspace) return fail(MXB_EINVAL, "mxb_compact_events: null pointer");
+    if (n_planes < 1 || n_planes > kCompactMaxPlanes) return fail(MXB_EINVAL, "mxb_compact_events: 1..64 planes");
+    if (n < 0) return fail(MXB_EINVAL, "negative n");
+    if (workspace_bytes < mxb_compact_workspace(n)) return fail(MXB_EINVAL, "mxb_compact_events: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(n_out_dev, 0, sizeof(long long), s));
+        return MXB_OK;
+    }
+    CompactPlanes P;
+    memset(&P, 0, sizeof(P));
+    for (int p = 0; p < n_planes; ++p) {
+        if (!src_planes[p] || !dst_planes[p]) return fail(MXB_EINVAL, "mxb_compact_events: null plane");
+        P.src[p] = static_cast<const unsigned long long*>(src_planes[p]);
+        P.dst[p] = static_cast<unsigned long long*>(dst_planes[p]);
+    }
+    const long long blocks = (n + kCompactThreads - 1) / kCompactThreads;
+    long long* counts = static_cast<long long*>(workspace);
+    compact_count_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(sel, sel_min, weight, n, counts);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(counts, blocks, n_out_dev);
+    compact_scatter_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(P, n_planes, sel, sel_min, weight, n, counts);
+    CUDA_TRY(cudaGetLastError());
+    return MXB_OK;
+}
+
 int mxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -811,7 +930,7 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
     if (n < 0) return fail(MXB_EINVAL, "negative n");
     for (int k = 0; k <= MXB_COL_PROB; ++k)
         if (!host_in->f64[k]) return fail(MXB_EINVAL, "mxb_trace_host: core photon column missing");
-    if (chunk <= 0) chunk = 1 << 21;
+    if (chunk <= 0) chunk = 1 << 20;   // 1 Mi photons: short pipeline fill, copies still >= 8 MB each
     if (chunk > n && n > 0) chunk = n;
     memset(status_host, 0, sizeof(unsigned long long) * MXB_STATUS_WORDS);
     if (n == 0) return MXB_OK;

@@ -15,7 +15,7 @@ HEADER = open(os.path.join(ROOT, 'include', 'mxb.h')).read()
 
 
 def header_functions():
-    names = re.findall(r'^\s*(?:int|void|const char\*|long long)\s+(mxb_\w+)\s*\(', HEADER, flags=re.M)
+    names = re.findall(r'^\s*(?:int|void|const char\*|long long|size_t)\s+(mxb_\w+)\s*\(', HEADER, flags=re.M)
     return sorted(set(names))
 
 

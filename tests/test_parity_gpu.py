@@ -737,6 +737,29 @@ def test_trace_from_is_copy_then_trace(mode):
                 assert np.array_equal(again.to_numpy()[c], want[c], equal_nan=True), c
 
 
+def test_event_compaction():
+    """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
+    mb = _mb()
+    from marxs_b200 import events
+    rng = np.random.default_rng(SEED + 31)
+    for n in (1, 1023, 1024, 1025, 50000, 1048577 + 3):
+        ccd = rng.integers(-1, 6, n)
+        prob = rng.uniform(-0.2, 1., n)
+        prob[rng.random(n) < 0.05] = np.nan
+        pos = rng.normal(size=(n, 4))
+        tab = {'pos': pos, 'energy': rng.random(n), 'probability': prob, 'CCD_ID': ccd}
+        b = mb.PhotonBatch(tab, device='cuda')
+        keep = (ccd >= 0) & (prob > 0)
+        got = events.compact(b).to_numpy()
+        assert len(got['energy']) == keep.sum()
+        for c in tab:
+            assert np.array_equal(got[c], np.asarray(tab[c])[keep]), (n, c)
+        got = events.compact(b, columns=['energy'], sel='CCD_ID', sel_min=3, weight=None).to_numpy()
+        assert np.array_equal(got['energy'], tab['energy'][ccd >= 3])
+        got = events.compact(b, columns=['CCD_ID'], sel=None, weight='probability').to_numpy()
+        assert np.array_equal(got['CCD_ID'], ccd[prob > 0])
+
+
 def test_fused_detector_image():
     """The image accumulated inside the trace kernel == mxb_hist2d on the output columns == numpy."""
     mb = _mb()
