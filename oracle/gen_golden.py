@@ -545,16 +545,100 @@ def case_parallel_overlap(marxs, rng):
          **inp, **table_to_dict(out))
 
 
+def case_cat_stack(marxs, rng):
+    """SNL CAT grating stack (membrane + quality factor + L1 + L2 absorption + L2 diffraction) and a
+    Parallel of such stacks: catgrating.py:147-374."""
+    from marxs.missions.mitsnl import catgrating as cg
+    from marxs.optics import OrderSelector
+    from marxs.simulator import Parallel
+    n = 1200
+    arrays = {}
+    arrays['trans_1um'] = np.asarray(cg.l1transtab['transmission'].data, float)
+    sel = OrderSelector(np.arange(-2, 9), p=np.array([.01, .02, .2, .05, .05, .05, .1, .15, .15, .1, .02]))
+    pos4d = rand_pos4d(rng, zoom=(1., 14., 15.), shift=2.)
+    p = make_photons(rng, n, spread=0.03, lateral=20., x0=70., e_lo=0.25, e_hi=2.0)
+    st = cg.CATL1L2Stack(pos4d=pos4d, order_selector=sel, groove_angle=0.05)
+    st.elements[0]._slots = [0]
+    st.elements[2]._slots = [1, 2]
+    st.elements[4]._slots = [3, 4]
+    arrays['trans_energy'] = np.asarray(st.elements[2].transfunc.x, float)     # keV, as the reference uses it
+    draws = [rng.random(n), rng.random(n), rng.random(n), rng.standard_normal(n), rng.random(n)]
+    inp = inputs_dict(p)
+    with Injector(marxs, draws):
+        out = st(p)
+    arrays.update({'stack_' + k: v for k, v in inp.items()})
+    arrays.update({'stack_' + k: v for k, v in table_to_dict(out).items()})
+    arrays['stack_pos4d'] = pos4d
+    arrays['stack_sel_orders'], arrays['stack_sel_p'] = sel.orderlist, sel.p
+    for k, d in enumerate(draws):
+        arrays['stack_draw{0}'.format(k)] = d
+    # a small array of stacks + the support-bar rule
+    pos = [[0., y, z] for y in (-16., 0., 16.) for z in (-17., 0., 17.)]
+    par = Parallel(elem_class=cg.CATL1L2Stack, elem_pos={'position': pos}, id_col='facet',
+                   elem_args={'zoom': [1, 7.5, 8.], 'order_selector': sel,
+                              'orientation': rand_pos4d(rng)[:3, :3] * 0 + np.array(
+                                  [[np.cos(0.03), -np.sin(0.03), 0], [np.sin(0.03), np.cos(0.03), 0], [0, 0, 1.]])})
+    for e in par.elements:
+        e.elements[0]._slots = [0]
+        e.elements[2]._slots = [1, 2]
+        e.elements[4]._slots = [3, 4]
+    p = make_photons(rng, n, spread=0.02, lateral=26., x0=60., e_lo=0.3, e_hi=1.5)
+    draws = [rng.random(n), rng.random(n), rng.random(n), rng.standard_normal(n), rng.random(n)]
+    inp = inputs_dict(p)
+    with Injector(marxs, draws):
+        out = par(p)
+    out = cg.catsupportbars(out)
+    arrays.update({'par_' + k: v for k, v in inp.items()})
+    arrays.update({'par_' + k: v for k, v in table_to_dict(out).items()})
+    arrays['par_pos4d'] = np.array([e.pos4d for e in par.elements])
+    for k, d in enumerate(draws):
+        arrays['par_draw{0}'.format(k)] = d
+    save('cat_stack', **arrays)
+
+
+def case_cylinder(marxs, rng):
+    """Cylinder.intersect (geometry.py:470-564) and CircularDetector (detector.py:78-118)."""
+    from marxs.math.geometry import Cylinder
+    from marxs.optics import CircularDetector
+    from transforms3d.euler import euler2mat
+    from transforms3d.affines import compose
+    n = 1000
+    arrays = {}
+    for tag, zoom, phi_lim, inside in (('full', [40., 40., 6.], None, False),
+                                       ('half', [30., 30., 10.], [-0.15, 2.2], False),
+                                       ('wrap', [25., 35., 8.], [2.5, -2.5], False)):
+        R = euler2mat(*rng.uniform(-0.3, 0.3, 3))
+        pos4d = compose(rng.uniform(-3, 3, 3), R, zoom)
+        kw = {'pos4d': pos4d}
+        if phi_lim is not None:
+            kw['phi_lim'] = phi_lim
+        p = make_photons(rng, n, spread=0.25, lateral=12., x0=(5. if inside else 90.))
+        p['dir'][:20, :3] = np.array([0., 0., 1.])           # along the axis: a == 0
+        g = Cylinder(dict(kw))
+        hit, ipos, loc = g.intersect(p['dir'].data, p['pos'].data)
+        arrays[tag + '_pos4d'] = pos4d
+        arrays[tag + '_phi_lim'] = np.array(phi_lim if phi_lim is not None else [-np.pi, np.pi])
+        arrays[tag + '_hit'], arrays[tag + '_interpos'], arrays[tag + '_loc'] = hit, ipos, loc
+        arrays.update({tag + '_' + k: v for k, v in inputs_dict(p).items()})
+        det = CircularDetector(pixsize=0.05, **kw)
+        out = det(p)
+        arrays.update({tag + '_' + k: v for k, v in table_to_dict(out).items()})
+    save('cylinder', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
     import marxs.missions.mitsnl.catgrating  # noqa: F401
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])      # python oracle/gen_golden.py [case_name ...]: regenerate only those
     for i, case in enumerate([case_intersect, case_parallel_transport, case_gratings,
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
-                              case_parallel_overlap]):
+                              case_parallel_overlap, case_cat_stack, case_cylinder]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
+        if only and case.__name__ not in only:
+            continue
         case(marxs, rng)
 
 

@@ -642,6 +642,9 @@ class RandomGaussianScatter(Element):
         self.scatter = float(kwargs.pop('scatter'))
         super().__init__(**kwargs)
 
+    def scatter_angle(self, photons, hit, draws):
+        return self.scatter * self.draw(draws, 0, hit, 'normal')
+
     def specific_process_photons(self, photons, hit, interpos, loc, draws):
         if self.scatter == 0:
             return {}
@@ -652,7 +655,7 @@ class RandomGaussianScatter(Element):
         guess[ind, 0] = 1
         guess[~ind, 1] = 1
         perpvec = cross3(pdir, guess)
-        angle = self.scatter * self.draw(draws, 0, hit, 'normal')
+        angle = self.scatter_angle(photons, hit, draws)
         outdir = axangle_rotate_T(perpvec, angle, pdir)
         angle2 = self.draw(draws, 1, hit, 'uniform') * 2 * np.pi
         outdir = e2h(axangle_rotate_T(pdir, angle2, outdir), 0)
@@ -896,6 +899,217 @@ class ACISChip(FlatDetector):
         skyy = ACIS_ODET[1] + x * np.sin(roll) + y * np.cos(roll)
         return {'chipx': chipx, 'chipy': chipy, 'tdetx': tdetx, 'tdety': tdety,
                 'detx': detx, 'dety': dety, 'x': skyx, 'y': skyy}
+
+
+# ---------------------------------------------------------------------------
+# SNL CAT grating stack  (missions/mitsnl/catgrating.py:147-374)
+# ---------------------------------------------------------------------------
+L1_ORDERS = np.array([-4, -3, -2, -1, 0, 1, 2, 3, 4])                       # catgrating.py:44-45
+L1_P = np.array([0.006, 0.0135, 0.022, 0.028, 0.861, 0.028, 0.022, 0.0135, 0.006])
+L1_DIMS = {'bardepth': 0.004, 'period': 0.005, 'barwidth': 0.0009}          # mm, :53
+L2_DIMS = {'bardepth': 0.5, 'period': 0.9622504, 'barwidth': 0.0962250}     # mm, :56
+QUALITYFACTOR = {'d': 200., 'sigma': 1.75}                                  # um, :59
+CAT_D = 0.0002                                                              # :38
+
+
+class QualityFactor(Element):
+    """catgrating.py:147-161: Debye-Waller scaling by the order of the membrane grating."""
+
+    def __init__(self, qualityfactor=QUALITYFACTOR, **kwargs):
+        self.factor = np.exp(-(2 * np.pi * qualityfactor['sigma'] / qualityfactor['d']) ** 2)
+        super().__init__(**kwargs)
+
+    def specific_process_photons(self, photons, hit, interpos, loc, draws):
+        return {'probability': self.factor ** (photons['order'][hit] ** 2)}
+
+
+class L1(CATGrating):
+    """catgrating.py:170-219.  l1_dims in mm; transmission table = (energy keV, transmission of 1 um Si)."""
+    blaze_name = 'blaze_L1'
+    order_name = 'order_L1'
+    n_slots = 2
+    slot_kinds = ('uniform', 'uniform')
+
+    def __init__(self, l1_dims=L1_DIMS, trans_energy=None, trans_1um=None, **kwargs):
+        if not (l1_dims['barwidth'] < l1_dims['period']):
+            raise ValueError('Period of grating must be larger than bar width.')
+        self.openfraction = 1 - l1_dims['barwidth'] / l1_dims['period']
+        with np.errstate(divide='ignore'):
+            logtranstab = np.log(np.asarray(trans_1um, dtype=float))
+        # bardepth / (1 um): the table is per micrometre of Si
+        trans = np.exp(logtranstab * (l1_dims['bardepth'] * 1e3))
+        self.transfunc = Tabulated1D(trans_energy, trans, bounds_error=True)
+        kwargs['d'] = l1_dims['period']
+        super().__init__(**kwargs)
+
+    def specific_process_photons(self, photons, hit, interpos, loc, draws):
+        cat = super().specific_process_photons(photons, hit, interpos, loc, draws)
+        l1 = self.draw(draws, 1, hit, 'uniform') > self.openfraction
+        cat['dir'][l1] = photons['dir'][hit][l1]
+        cat['polarization'][l1] = photons['polarization'][hit][l1]
+        cat[self.order_name] = np.asarray(cat[self.order_name], dtype=float)
+        cat[self.order_name][l1] = 0
+        prob = np.array(cat['probability'], dtype=float)
+        if l1.any():
+            prob[l1] = self.transfunc(photons['energy'][hit][l1])
+        cat['probability'] = prob
+        return cat
+
+
+class L2Abs(Element):
+    """catgrating.py:222-259: shadowing by the hexagonal L2 support."""
+
+    def __init__(self, l2_dims=L2_DIMS, **kwargs):
+        if not (l2_dims['barwidth'] < l2_dims['period']):
+            raise ValueError('Period of grating must be larger than bar width.')
+        self.bardepth = l2_dims['bardepth']
+        self.period = l2_dims['period']
+        self.barwidth = l2_dims['barwidth']
+        super().__init__(**kwargs)
+        self.innerfree = self.period - self.barwidth
+
+    def specific_process_photons(self, photons, hit, interpos, loc, draws):
+        p3 = normalize3(photons['dir'][hit])
+        en = self.g.e_x
+        with np.errstate(invalid='ignore'):
+            angle = np.arccos(np.abs(dot3(p3, en)))       # no clip in the reference: NaN above 1
+        openfraction = (self.innerfree / self.period) ** 2
+        shadowarea = (self.bardepth * self.innerfree * np.sin(angle))
+        totalarea = self.period ** 2 / 2 * np.sqrt(3)
+        shadowfraction = shadowarea / totalarea
+        return {'probability': openfraction - shadowfraction}
+
+
+class L2Diffraction(RandomGaussianScatter):
+    """catgrating.py:262-285: Gaussian scatter with sigma = 1.22 * 0.4 * arcsin(lambda / innerfree)."""
+    scattername = 'L2Diffraction'
+
+    def __init__(self, l2_dims=L2_DIMS, **kwargs):
+        self.innerfree = l2_dims['period'] - l2_dims['barwidth']
+        kwargs['scatter'] = 1.
+        super().__init__(**kwargs)
+
+    def scatter_angle(self, photons, hit, draws):
+        wave = (HC_KEV_NM * 1e-6) / photons['energy'][hit]      # astropy u.spectral(): keV -> mm
+        with np.errstate(invalid='ignore'):
+            sigma = 1.22 * 0.4 * np.arcsin(wave / self.innerfree)
+        return self.draw(draws, 0, hit, 'normal') * sigma
+
+
+class CATL1L2Stack(FlatStack):
+    """catgrating.py:326-374"""
+
+    def __init__(self, l1_dims=L1_DIMS, l2_dims=L2_DIMS, l1_order_selector=None, qualityfactor=QUALITYFACTOR,
+                 trans_energy=None, trans_1um=None, **kwargs):
+        if l1_order_selector is None:
+            l1_order_selector = OrderSelector(L1_ORDERS, L1_P)
+        groove_angle = kwargs.pop('groove_angle', 0.)
+        kwargs['elements'] = [NonParallelCATGrating, QualityFactor, L1, L2Abs, L2Diffraction]
+        kwargs['keywords'] = [{'order_selector': kwargs.pop('order_selector'), 'd': kwargs.pop('d', CAT_D),
+                               'groove_angle': groove_angle},
+                              {'qualityfactor': qualityfactor},
+                              {'l1_dims': l1_dims, 'order_selector': l1_order_selector,
+                               'groove_angle': np.pi / 2. + groove_angle,
+                               'trans_energy': trans_energy, 'trans_1um': trans_1um},
+                              {'l2_dims': l2_dims},
+                              {'l2_dims': l2_dims}]
+        super().__init__(**kwargs)
+
+
+def catsupportbars(photons):
+    """catgrating.py:314-323"""
+    if 'facet' in photons:
+        photons['probability'][photons['facet'] < 0] = 0.
+    else:
+        photons['probability'][:] = 0.
+    return photons
+
+
+# ---------------------------------------------------------------------------
+# Cylinder geometry and CircularDetector  (math/geometry.py:383-564, optics/detector.py:78-118)
+# ---------------------------------------------------------------------------
+def angle_between(angle, border1, border2):
+    """math/utils.py:180-215"""
+    twopi = 2 * np.pi
+    b1 = (twopi + (border1 % twopi)) % twopi
+    b2 = (twopi + (border2 % twopi)) % twopi
+    ang = (twopi + (angle % twopi)) % twopi
+    if b1 < b2:
+        return (b1 <= ang) & (ang <= b2)
+    return (b1 <= ang) | (ang <= b2)
+
+
+def cylinder_intersect(pos4d, phi_lim, dir, pos):
+    """Cylinder.intersect, geometry.py:470-564: unit circle in the local xy plane, |z| <= 1.
+    Returns (hit, interpos (N,4) global, loc (N,2) = (phi, z * zoom_z))."""
+    pos4d = np.asarray(pos4d, dtype=float)
+    inv = np.linalg.inv(pos4d)
+    n = pos.shape[0]
+    # 4-term dot products written out (np.dot(invpos4d, v.T).T in the reference)
+    dl = np.empty((n, 4))
+    pl = np.empty((n, 4))
+    for r in range(4):
+        dl[:, r] = inv[r, 0] * dir[:, 0] + inv[r, 1] * dir[:, 1] + inv[r, 2] * dir[:, 2] + inv[r, 3] * dir[:, 3]
+        pl[:, r] = inv[r, 0] * pos[:, 0] + inv[r, 1] * pos[:, 1] + inv[r, 2] * pos[:, 2] + inv[r, 3] * pos[:, 3]
+    xyz = pl[:, :3] / pl[:, 3:4]
+    c = (xyz[:, 0] ** 2 + xyz[:, 1] ** 2) - 1.
+    b = 2 * (xyz[:, 0] * dl[:, 0] + xyz[:, 1] * dl[:, 1])
+    a = dl[:, 0] ** 2 + dl[:, 1] ** 2
+    underroot = b ** 2 - 4 * a * c
+    with np.errstate(invalid='ignore', divide='ignore'):
+        hit = underroot >= 0
+        sq = np.sqrt(underroot)
+        denom = 2 * a
+        a1 = (-b + sq) / denom
+        a2 = (-b - sq) / denom
+        x1, y1 = xyz[:, 0] + a1 * dl[:, 0], xyz[:, 1] + a1 * dl[:, 1]
+        x2, y2 = xyz[:, 0] + a2 * dl[:, 0], xyz[:, 1] + a2 * dl[:, 1]
+        phi1, phi2 = np.arctan2(y1, x1), np.arctan2(y2, x2)
+        z1, z2 = xyz[:, 2] + a1 * dl[:, 2], xyz[:, 2] + a2 * dl[:, 2]
+        hit1 = hit & (a1 >= 0) & (np.abs(z1) <= 1.) & angle_between(phi1, phi_lim[0], phi_lim[1])
+        hit2 = hit & (a2 >= 0) & (np.abs(z2) <= 1.) & angle_between(phi2, phi_lim[0], phi_lim[1])
+        hit1 = hit1 & ~(hit2 & (a2 < a1))
+        hit2 = hit2 & ~(hit1 & (a2 >= a1))
+    hit = hit1 | hit2
+    loc = np.full((n, 2), np.nan)
+    loc[hit1, 0], loc[hit1, 1] = phi1[hit1], z1[hit1]
+    loc[hit2, 0], loc[hit2, 1] = phi2[hit2], z2[hit2]
+    il = np.full((n, 4), np.nan)
+    for k in range(3):
+        il[hit1, k] = (xyz[:, k] + a1 * dl[:, k])[hit1]
+        il[hit2, k] = (xyz[:, k] + a2 * dl[:, k])[hit2]
+    il[hit, 3] = 1.
+    t, rot, zoom, sh = decompose44(pos4d)
+    loc[:, 1] = loc[:, 1] * zoom[2]
+    interpos = np.empty((n, 4))
+    for r in range(4):
+        interpos[:, r] = pos4d[r, 0] * il[:, 0] + pos4d[r, 1] * il[:, 1] + pos4d[r, 2] * il[:, 2] + pos4d[r, 3] * il[:, 3]
+    return hit, interpos, loc
+
+
+class CircularDetector(Element):
+    """detector.py:78-118 on a Cylinder geometry."""
+    loc_coos_name = ['det_phi', 'det_y']
+    detpix_name = ['detpix_x', 'detpix_y']
+    centerpix = [0, 0]
+
+    def __init__(self, pixsize=1, phi_lim=(-np.pi, np.pi), **kwargs):
+        self.pixsize = pixsize
+        self.phi_lim = [float(phi_lim[0]), float(phi_lim[1])]
+        super().__init__(**kwargs)
+
+    @property
+    def R(self):
+        return decompose44(self.pos4d)[2][0]
+
+    def __call__(self, photons, draws=None):
+        hit, interpos, loc = cylinder_intersect(self.pos4d, self.phi_lim, photons['dir'], photons['pos'])
+        return self.process_photons(photons, hit, interpos, loc, draws)
+
+    def specific_process_photons(self, photons, hit, interpos, loc, draws):
+        detx = loc[hit, 0] * self.R / self.pixsize + self.centerpix[0]
+        dety = loc[hit, 1] / self.pixsize + self.centerpix[1]
+        return {self.detpix_name[0]: detx, self.detpix_name[1]: dety}
 
 
 # ---------------------------------------------------------------------------

@@ -70,6 +70,10 @@ def _convert(value, src, dst, equivalencies=None):
     value = np.asanyarray(value, dtype=float).view(np.ndarray)
     if src.dims == dst.dims:
         return value * (src.scale / dst.scale)
+    # numpy's inverse trigonometric ufuncs drop the unit here (astropy returns radians): a bare
+    # number converted to an angle is taken to be in radians
+    if src.dims == (0, 0, 0, 0) and dst.dims == (0, 0, 1, 0):
+        return value * (src.scale / dst.scale)
     eq = set(equivalencies or ()) | set(_ENABLED[-1])
     # angles are dimensionless
     strip = lambda d: (d[0], d[1], 0, d[3])
@@ -103,6 +107,41 @@ class Quantity(np.ndarray):
 
     def __array_finalize__(self, obj):
         self.unit = getattr(obj, 'unit', dimensionless_unscaled)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        """exp / log need a dimensionless argument and astropy first converts a SCALED dimensionless
+        unit (mm / um = 1000) to a bare number (catgrating.py:192 relies on it); every other ufunc
+        keeps the plain ndarray-subclass behaviour (result carries the unit of the first Quantity)."""
+        unscale = ufunc in _UNSCALED_UFUNCS
+        args, first_unit = [], None
+        for x in inputs:
+            if isinstance(x, Quantity):
+                v = x.view(np.ndarray)
+                if first_unit is None:
+                    first_unit = x.unit
+                if unscale:
+                    if any(x.unit.dims):
+                        raise UnitConversionError('{0} needs a dimensionless argument'.format(ufunc.__name__))
+                    v = v * x.unit.scale
+                args.append(v)
+            else:
+                args.append(x)
+        if out is not None:
+            kwargs['out'] = tuple(o.view(np.ndarray) if isinstance(o, Quantity) else o for o in out)
+        res = getattr(ufunc, method)(*args, **kwargs)
+        if out is not None:
+            return out[0] if len(out) == 1 else out
+        unit = dimensionless_unscaled if unscale else first_unit
+
+        def wrap(r):
+            if isinstance(r, np.ndarray) and r.dtype.kind == 'f':
+                q = r.view(Quantity)
+                q.unit = unit
+                return q
+            if isinstance(r, (float, np.floating)):
+                return Quantity(r, unit)
+            return r
+        return tuple(wrap(r) for r in res) if isinstance(res, tuple) else wrap(res)
 
     @property
     def value(self):
@@ -148,8 +187,16 @@ class Quantity(np.ndarray):
         return Quantity(out, Unit(1. / self.unit.scale, [-d for d in self.unit.dims]))
 
     def __pow__(self, p):
+        if np.ndim(p) > 0:
+            # array exponents need a dimensionless base (astropy raises otherwise)
+            if any(self.unit.dims):
+                raise UnitConversionError('array exponent needs a dimensionless base')
+            return Quantity((self.view(np.ndarray) * self.unit.scale) ** np.asanyarray(p).view(np.ndarray),
+                            dimensionless_unscaled)
         return Quantity(self.view(np.ndarray) ** p, self.unit ** p)
 
+
+_UNSCALED_UFUNCS = (np.exp, np.exp2, np.expm1, np.log, np.log2, np.log10, np.log1p)
 
 dimensionless_unscaled = Unit(1., (0, 0, 0, 0), 'dimensionless')
 one = dimensionless_unscaled
@@ -158,6 +205,7 @@ mm = Unit(1e-3, (1, 0, 0, 0), 'mm')
 cm = Unit(1e-2, (1, 0, 0, 0), 'cm')
 um = Unit(1e-6, (1, 0, 0, 0), 'um')
 micron = um
+micrometer = um
 nm = Unit(1e-9, (1, 0, 0, 0), 'nm')
 Angstrom = Unit(1e-10, (1, 0, 0, 0), 'Angstrom')
 AA = Angstrom

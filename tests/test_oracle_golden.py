@@ -363,3 +363,54 @@ def test_golden_chandra_c2():
     ok = out['CCD_ID'] >= 0
     for c in ('chipx', 'chipy', 'tdetx', 'tdety'):
         np.testing.assert_array_equal(np.round(out[c][ok]), np.round(g['out_' + c][ok]), err_msg=c)
+
+
+# ---------------------------------------------------------------------------
+# SNL CAT stack, Cylinder, CircularDetector (golden from the reference)
+# ---------------------------------------------------------------------------
+CAT_SEL = dict(orderlist=np.arange(-2, 9), p=np.array([.01, .02, .2, .05, .05, .05, .1, .15, .15, .1, .02]))
+
+
+def test_golden_cat_stack():
+    """missions/mitsnl/catgrating.py:147-374 incl. the L1 revert quirk and the support-bar rule."""
+    g = load('cat_stack')
+    sel = mo.OrderSelector(CAT_SEL['orderlist'], CAT_SEL['p'])
+    st = mo.CATL1L2Stack(pos4d=g['stack_pos4d'], order_selector=sel, groove_angle=0.05,
+                         trans_energy=g['trans_energy'], trans_1um=g['trans_1um'])
+    kinds = mo.assign_slots(st)
+    assert kinds == ['uniform', 'uniform', 'uniform', 'normal', 'uniform']
+    out = st(table_from(g, 'stack_'), mo.Draws([g['stack_draw{0}'.format(k)] for k in range(5)]))
+    assert (out['order_L1'] == 0).sum() > 200 and np.isfinite(out['L2Diffraction']).mean() > 0.3
+    # polarization: the L2 scatter angles are ~1e-6 rad, so s = d1 x d2 has |s| ~ 1e-6 and its rounding
+    # error (1e-16) becomes a 1e-10 component along the ray after normalisation - the reference's own
+    # parallel transport is that ill-conditioned (einsum order vs left-to-right sums differ by it)
+    assert_cols(out, g, 'stack_', exact=('order', 'order_L1'), rtol=1e-12, skip=('polarization',))
+    np.testing.assert_allclose(out['polarization'], g['stack_out_polarization'], rtol=0, atol=5e-10)
+    # Parallel of stacks + catsupportbars
+    pos = [[0., y, z] for y in (-16., 0., 16.) for z in (-17., 0., 17.)]
+    rot = np.array([[np.cos(0.03), -np.sin(0.03), 0], [np.sin(0.03), np.cos(0.03), 0], [0, 0, 1.]])
+    par = mo.Parallel(mo.CATL1L2Stack, {'position': pos},
+                      {'zoom': [1, 7.5, 8.], 'order_selector': sel, 'orientation': rot,
+                       'trans_energy': g['trans_energy'], 'trans_1um': g['trans_1um']}, id_col='facet')
+    np.testing.assert_allclose(np.array([e.pos4d for e in par.elements]), g['par_pos4d'], rtol=1e-15, atol=1e-15)
+    mo.assign_slots(par)
+    out = par(table_from(g, 'par_'), mo.Draws([g['par_draw{0}'.format(k)] for k in range(5)]))
+    out = mo.catsupportbars(out)
+    assert len(set(out['facet'])) == 10
+    assert_cols(out, g, 'par_', exact=('facet', 'order', 'order_L1'), rtol=1e-12, skip=('polarization',))
+    np.testing.assert_allclose(out['polarization'], g['par_out_polarization'], rtol=0, atol=5e-10)
+
+
+@pytest.mark.parametrize('tag', ['full', 'half', 'wrap'])
+def test_golden_cylinder(tag):
+    """math/geometry.py:470-564 Cylinder.intersect and optics/detector.py:78-118 CircularDetector."""
+    g = load('cylinder')
+    t = table_from(g, tag + '_')
+    hit, ipos, loc = mo.cylinder_intersect(g[tag + '_pos4d'], g[tag + '_phi_lim'], t['dir'], t['pos'])
+    np.testing.assert_array_equal(hit, g[tag + '_hit'])
+    assert 0.05 < hit.mean() < 0.99
+    np.testing.assert_allclose(ipos, g[tag + '_interpos'], rtol=1e-12, atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(loc, g[tag + '_loc'], rtol=1e-12, atol=1e-12, equal_nan=True)
+    det = mo.CircularDetector(pixsize=0.05, pos4d=g[tag + '_pos4d'], phi_lim=g[tag + '_phi_lim'])
+    out = det(t)
+    assert_cols(out, g, tag + '_', rtol=1e-12, atol=1e-11)
