@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 6
+#define MXB_ABI_VERSION 7
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -102,11 +102,19 @@ typedef struct MxbColumns {
 #define MXB_OP_BAFFLE       5  /* baffles.py:25-28: pos = interpos on hit, probability = 0 on miss                                  */
 #define MXB_OP_LENS         6  /* mirror.py:53-82 PerfectLens: params P[3] f                                                        */
 #define MXB_OP_RSCATTER     7  /* scatter.py:49-77 RadialMirrorScatter: params center[3] sig_in sig_perp; s0,s1 normals; c0,c1 cols   */
-#define MXB_OP_GSCATTER     8  /* scatter.py:109-145 RandomGaussianScatter: params sigma; s0 normal s1 uniform; c0 col               */
+#define MXB_OP_GSCATTER     8  /* scatter.py:109-145 RandomGaussianScatter: params sigma; s0 normal s1 uniform; c0 col.
+                                  flags bit0: L2Diffraction (mitsnl/catgrating.py:262-285): params innerfree,
+                                  sigma = 1.22 * 0.4 * asin(lambda / innerfree) per photon                                         */
 #define MXB_OP_FILTER       9  /* filter.py:90-94 EnergyFilter: params n, x[n], y[n] (n==0: constant y[0]); flags bit0 bounds_error  */
-#define MXB_OP_GRATING     10  /* grating.py:233-277: params l[3] dd[3] d blaze0 dblaze ; flags bit0 CAT bit1 reflection;
-                                  pg: selector block; s0 uniform; c0 order c1 blaze                                                 */
-#define MXB_OP_DETPIX      11  /* detector.py:73-75: params pixsize cp0 cp1; c0,c1 detpix cols                                       */
+#define MXB_OP_GRATING     10  /* grating.py:233-277: params l[3] dd[3] d blaze0 dblaze ; flags bit0 CAT bit1 reflection
+                                  bit2 blaze modifier; pg: selector block; s0 uniform; c0 order c1 blaze.
+                                  flags bit3: L1 support (mitsnl/catgrating.py:170-219): s1 = second uniform, c2 = word offset
+                                  (a plain integer, not a column) of the block  openfraction, table_off ; table (global):
+                                  n, energy[n], transmission[n].  Photons with u1 > openfraction pass through the Si bar:
+                                  dir / polarization unchanged, order 0, probability *= interp1d(energy)                        */
+#define MXB_OP_DETPIX      11  /* detector.py:73-75: params pixsize cp0 cp1; c0,c1 detpix cols.  flags bit0: id_num from the facet
+                                  row; bit1: CircularDetector (detector.py:113-116): params pixsize cp0 cp1 R,
+                                  detpix_x = phi * R / pixsize + cp0                                                             */
 #define MXB_OP_ACIS        12  /* det_acis.py:31-58 + data.py:169-190: per-facet pixsize cp0 cp1 sh ct st ox oy; pg: f pixrad odet0 odet1 cosroll sinroll; c0..c7 */
 #define MXB_OP_BREWSTER    13  /* multiLayerMirror.py:44-91: params Pinv[9] P[9] ex[3]                                               */
 #define MXB_OP_MLEFF       14  /* multiLayerMirror.py:132-170: params Ly n_refl n_pol then tables                                    */
@@ -116,6 +124,11 @@ typedef struct MxbColumns {
 #define MXB_OP_GFILTER     17  /* filter.py:48-53 GlobalEnergyFilter (all photons); params as FILTER                                 */
 #define MXB_OP_LOADHIT     18  /* process_photons(photons, intersect, interpos, intercoos) with an EXTERNAL intersect:
                                   c0 hit (0/1 as f64) c1..c3 interpos c4,c5 intercoos columns; pg: geom[14]                        */
+#define MXB_OP_QFACTOR     19  /* mitsnl/catgrating.py:147-161 QualityFactor: params factor ; probability *= factor ** order**2
+                                  with the order drawn by the preceding GRATING op of the same stack                             */
+#define MXB_OP_L2ABS       20  /* mitsnl/catgrating.py:222-259 L2Abs: params openfraction, bardepth*innerfree, totalarea         */
+#define MXB_OP_CYLINDER    21  /* math/geometry.py:470-564 Cylinder.intersect: pg: inv(pos4d)[16] pos4d[16] (row major)
+                                  phi_lo phi_hi (normalised to [0, 2 pi)) zoom_z ; local coordinates (phi, z * zoom_z)           */
 
 /* selector kinds (first word of the selector block) */
 #define MXB_SEL_ORDERSELECTOR 1  /* grating.py:12-57:  n, psum, cdf[n], orders[n]                                                   */

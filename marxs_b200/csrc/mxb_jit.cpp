@@ -312,7 +312,7 @@ struct Gen {
             out("            if (ph.hit) {");
             out("                const double zn = %s;", draw(o.s0, 1).c_str());
             out("                const double u = %s;", draw(o.s1, 0).c_str());
-            out("                op_gscatter(ph, %s, zn, u, a);", PR(o, 1).c_str());
+            out("                op_gscatter(ph, %s, %d, zn, u, a);", PR(o, 1).c_str(), fl);
             out("            }");
             put(o.c[0], "a");
             out("            }");
@@ -343,8 +343,15 @@ struct Gen {
             out("            double order = 0, blaze = 0;");
             out("            if (ph.hit) {");
             out("                const double u = %s;", draw(o.s0, 0).c_str());
+            out("                bool blocked = false;");
+            out("                double trans = 0.0;");
+            if (fl & 8) {   // L1 support: block = openfraction, offset of the Si transmission table (global)
+                const std::string lb = S(o.c[2], 2);
+                out("                blocked = %s > %s[0];", draw(o.s1, 0).c_str(), lb.c_str());
+                out("                if (blocked) trans = filter_value(st_sm, PRef<false>{P.prog, (int)%s[1]}, ph.energy, 1);", lb.c_str());
+            }
             out("                op_grating(st_sm, ph, %s, %s, %d,", PR(o, 9).c_str(), geom.c_str(), fl);
-            out("                           [&](double energy, double bl, double& psel) { return %s; }, order, blaze);", select.c_str());
+            out("                           [&](double energy, double bl, double& psel) { return %s; }, order, blaze, blocked, trans);", select.c_str());
             out("            }");
             put(o.c[0], "order");
             put(o.c[1], "blaze");
@@ -354,7 +361,7 @@ struct Gen {
         case MXB_OP_DETPIX: {
             out("            {");
             out("            double px = 0, py = 0;");
-            out("            if (ph.hit) op_detpix(ph, %s, px, py);", PR(o, 3).c_str());
+            out("            if (ph.hit) op_detpix(ph, %s, %d, px, py);", PR(o, (fl & 2) ? 4 : 3).c_str(), fl);
             put(o.c[0], "px");
             put(o.c[1], "py");
             if (o.s0 >= 0 && o.s0 < MXB_MAX_F64_COLS && cols->f64[o.s0]) {
@@ -383,6 +390,20 @@ struct Gen {
         }
         case MXB_OP_BREWSTER:
             out("            if (ph.hit) op_brewster(st_sm, ph, %s);", PR(o, 21).c_str());
+            break;
+        case MXB_OP_CYLINDER: {
+            if (in_array) return fail("CYLINDER inside an array");
+            geom = S(o.pg, 35);
+            new_hit();
+            out("            ph.hit = cylinder_intersect(%s, ph.pos, ph.dir, ph.ip, ph.l0, ph.l1) && active;", geom.c_str());
+            hit_count(pc);
+            break;
+        }
+        case MXB_OP_QFACTOR:
+            out("            if (ph.hit) op_qfactor(st_sm, ph, %s);", PR(o, 1).c_str());
+            break;
+        case MXB_OP_L2ABS:
+            out("            if (ph.hit) op_l2abs(st_sm, ph, %s, %s);", PR(o, 3).c_str(), geom.c_str());
             break;
         case MXB_OP_MLEFF: {
             // tables are searched with per-photon indices: shared memory
@@ -565,7 +586,7 @@ struct Gen {
         out("    (void)B;");
         for (int pc = 0; pc < n_ops; ++pc) {
             const int t = ops[pc].type;
-            if (t == MXB_OP_PLANE || t == MXB_OP_LOADHIT || t == MXB_OP_APERTURE || t == MXB_OP_ARRAY_BEGIN) out("    unsigned h%d = 0u;", pc);
+            if (t == MXB_OP_PLANE || t == MXB_OP_LOADHIT || t == MXB_OP_APERTURE || t == MXB_OP_ARRAY_BEGIN || t == MXB_OP_CYLINDER) out("    unsigned h%d = 0u;", pc);
         }
         out("    const double kNaN = nan64();");
         out("    const long long stride = (long long)gridDim.x * JIT_THREADS;");
@@ -611,7 +632,7 @@ struct Gen {
         out("    if ((tid & 31) == 0) {");
         for (int pc = 0; pc < n_ops; ++pc) {
             const int t = ops[pc].type;
-            if (t == MXB_OP_PLANE || t == MXB_OP_LOADHIT || t == MXB_OP_APERTURE || t == MXB_OP_ARRAY_BEGIN)
+            if (t == MXB_OP_PLANE || t == MXB_OP_LOADHIT || t == MXB_OP_APERTURE || t == MXB_OP_ARRAY_BEGIN || t == MXB_OP_CYLINDER)
                 out("        if (h%d) atomicAdd(&P.status[MXB_ST_OPHITS + %d], (unsigned long long)h%d);", pc, pc, pc);
         }
         out("    }");

@@ -83,6 +83,8 @@ struct SRef {
     MXB_DEV double2 ld2(int k) const { return make_double2(s[2 * k], s[2 * k + 1]); }
 };
 
+MXB_DEV double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 // ---------------------------------------------------------------------------
 // per-thread photon state
 // ---------------------------------------------------------------------------
@@ -91,11 +93,13 @@ struct Photon {
     double energy, prob;
     V3 ip;          // intersection point of the current element
     double l0, l1;  // local coordinates on the current element
+    double last_order;   // order drawn by the latest GRATING op (QualityFactor reads photons['order'])
     bool hit;
     bool unit;      // |dir| == 1 to rounding (fast build: see kTrackUnit in mxb_device.cuh)
 };
 MXB_DEV void photon_loaded(Photon& ph) {   // after pos/dir/pol/energy/prob are in registers
     ph.hit = false;
+    ph.last_order = nan64();
     ph.unit = kTrackUnit && (dot(ph.dir, ph.dir) == 1.0);
 }
 
@@ -150,7 +154,6 @@ MXB_DEV void pipe_load(InputPipe& p, const double* const* planes, long long base
     if (p.pending && lane == 0) pipe_issue(p, planes, next_base);
 }
 
-MXB_DEV double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 MXB_DEV void st_global(double* p, double v) {
     asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -280,11 +283,17 @@ MXB_DEV void rscatter_draws(double sig_in, double sig_perp, const double* inj0, 
 
 // scatter.py:109-145  params: sigma ; zn standard normal, u uniform
 template <typename PP>
-MXB_DEV void op_gscatter(Photon& ph, PP p, double zn, double u, double& ang) {
+MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, double& ang) {
     const V3 pdir = normalize_unless(ph.unit, ph.dir);
     const V3 guess = (fabs(pdir.x) < 0.99999) ? V3{1, 0, 0} : V3{0, 1, 0};
     const V3 perp = cross(pdir, guess);
-    ang = p[0] * zn;
+    if (flags & 1) {   // L2Diffraction (mitsnl/catgrating.py:280-285): Airy-disk sigma of the L2 mesh, p[0] = innerfree
+        const double wave = div(kHcKevNm * 1e-6, ph.energy);   // astropy u.spectral(): keV -> mm
+        const double sigma = (1.22 * 0.4) * asin(div(wave, p[0]));
+        ang = zn * sigma;
+    } else {
+        ang = p[0] * zn;
+    }
     V3 out = axangle_rotate_T(perp, ang, pdir);
     const double ang2 = u * 2 * 3.141592653589793;
     out = axangle_rotate_T(pdir, ang2, out);
@@ -386,7 +395,7 @@ MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy
 // select(energy, blaze, psel) -> diffraction order (the caller binds the draw and the table)
 template <typename PP, typename GP, typename SELECT>
 MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, int flags, SELECT select,
-                        double& order, double& blaze) {
+                        double& order, double& blaze, bool l1_blocked = false, double l1_trans = 0.0) {
     const V3 pn = normalize_unless(ph.unit, ph.dir);
     const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
     const double wave = div(kEnergy2Wave, ph.energy);
@@ -406,11 +415,35 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
     const double q = direction * p_n;
     const V3 nd{p_d * dd.x + p_l * l.x + q * n.x, p_d * dd.y + p_l * l.y + q * n.y,
                 p_d * dd.z + p_l * l.z + q * n.z};
+    if (l1_blocked) {
+        // L1 support bar (mitsnl/catgrating.py:203-218): the photon goes through solid Si instead of the
+        // open grating: direction and polarization stay, order 0, probability = Si transmission
+        order = 0.0;
+        ph.last_order = order;
+        mul_prob(st_sm, ph, l1_trans);
+        return;
+    }
+    ph.last_order = order;
     // nd is a unit vector by construction (p_d^2 + p_l^2 + p_n^2 = 1 in the orthonormal frame d, l, n)
     ph.pol = parallel_transport(kTrackUnit ? pn : ph.dir, nd, ph.pol, kTrackUnit, true);
     ph.dir = nd;
     ph.unit = true;
     mul_prob(st_sm, ph, psel);
+}
+
+// mitsnl/catgrating.py:147-161  params: factor
+template <typename PP>
+MXB_DEV void op_qfactor(unsigned long long* st_sm, Photon& ph, PP p) {
+    mul_prob(st_sm, ph, pow(p[0], ph.last_order * ph.last_order));
+}
+
+// mitsnl/catgrating.py:222-259  params: openfraction, bardepth * innerfree, totalarea ; n = e_x of the geometry
+template <typename PP, typename GP>
+MXB_DEV void op_l2abs(unsigned long long* st_sm, Photon& ph, PP p, GP geom) {
+    const V3 p3 = normalize_unless(ph.unit, ph.dir);
+    const V3 en = ld3(geom + 3);
+    const double angle = acos(fabs(dot(p3, en)));   // no clip in the reference: NaN above 1
+    mul_prob(st_sm, ph, p[0] - div(p[1] * sin(angle), p[2]));
 }
 
 // multiLayerMirror.py:44-91  params: Pinv[9] P[9] ex[3]
@@ -469,9 +502,57 @@ MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
 
 // detector.py:73-75  pr: pixsize cp0 cp1
 template <typename PP>
-MXB_DEV void op_detpix(const Photon& ph, PP pr, double& px, double& py) {
-    px = div(ph.l0, pr[0]) + pr[1];
+MXB_DEV void op_detpix(const Photon& ph, PP pr, int flags, double& px, double& py) {
+    if (flags & 2) px = div(ph.l0 * pr[3], pr[0]) + pr[1];   // CircularDetector: phi * R / pixsize (detector.py:114)
+    else px = div(ph.l0, pr[0]) + pr[1];
     py = div(ph.l1, pr[0]) + pr[2];
+}
+
+// ---------------------------------------------------------------------------
+// math/geometry.py:470-564 Cylinder.intersect: unit circle in the local xy plane, |z| <= 1.
+// g: inv(pos4d)[16] pos4d[16] (row major) phi_lo phi_hi zoom_z.  Of the two roots the nearer valid
+// one (a >= 0, |z| <= 1, phi inside the limits) wins; local coordinates are (phi, z * zoom_z).
+// ---------------------------------------------------------------------------
+MXB_DEV double py_mod(double a, double m) {   // np.remainder: result carries the sign of m
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+    return r;
+}
+MXB_DEV bool angle_between(double angle, double b1, double b2) {   // math/utils.py:180-215, borders pre-normalised
+    const double ang = py_mod(kTwoPi + py_mod(angle, kTwoPi), kTwoPi);
+    return (b1 < b2) ? ((b1 <= ang) && (ang <= b2)) : ((b1 <= ang) || (ang <= b2));
+}
+template <typename P>
+MXB_DEV bool cylinder_intersect(P g, const V3& pos, const V3& dir, V3& ip, double& l0, double& l1) {
+    double dl[3], pl[4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dl[r] = g[4 * r] * dir.x + g[4 * r + 1] * dir.y + g[4 * r + 2] * dir.z;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pl[r] = g[4 * r] * pos.x + g[4 * r + 1] * pos.y + g[4 * r + 2] * pos.z + g[4 * r + 3];
+    const double x = pl[0] / pl[3], y = pl[1] / pl[3], z = pl[2] / pl[3];
+    const double c = (x * x + y * y) - 1.;
+    const double b = 2 * (x * dl[0] + y * dl[1]);
+    const double a = dl[0] * dl[0] + dl[1] * dl[1];
+    const double underroot = b * b - 4 * a * c;
+    const bool real = underroot >= 0;
+    const double sq = sqrt(underroot);
+    const double denom = 2 * a;
+    const double a1 = (-b + sq) / denom, a2 = (-b - sq) / denom;
+    const double x1 = x + a1 * dl[0], y1 = y + a1 * dl[1], z1 = z + a1 * dl[2];
+    const double x2 = x + a2 * dl[0], y2 = y + a2 * dl[1], z2 = z + a2 * dl[2];
+    const double phi1 = atan2(y1, x1), phi2 = atan2(y2, x2);
+    bool hit1 = real && (a1 >= 0) && (fabs(z1) <= 1.) && angle_between(phi1, g[32], g[33]);
+    bool hit2 = real && (a2 >= 0) && (fabs(z2) <= 1.) && angle_between(phi2, g[32], g[33]);
+    hit1 = hit1 && !(hit2 && (a2 < a1));   // both valid: the closer one
+    hit2 = hit2 && !(hit1 && (a2 >= a1));
+    const double lx = hit1 ? x1 : x2, ly = hit1 ? y1 : y2, lz = hit1 ? z1 : z2;
+    l0 = hit1 ? phi1 : phi2;
+    l1 = lz * g[34];
+    P q = g + 16;
+    ip.x = q[0] * lx + q[1] * ly + q[2] * lz + q[3];
+    ip.y = q[4] * lx + q[5] * ly + q[6] * lz + q[7];
+    ip.z = q[8] * lx + q[9] * ly + q[10] * lz + q[11];
+    return hit1 || hit2;
 }
 
 // det_acis.py:31-58 + data.py:169-190 ; per-facet pr: pixsize cp0 cp1 sh ct st ox oy ;

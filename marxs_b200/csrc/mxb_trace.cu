@@ -292,7 +292,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 if (ph.hit) {
                     const double zn = draw(ctx, c.s0, 1);
                     const double u = draw(ctx, c.s1, 0);
-                    op_gscatter(ph, pr, zn, u, a);
+                    op_gscatter(ph, pr, op.flags, zn, u, a);
                 }
                 put(ctx, wm, 0, c.cp[0], ph.hit, a);
                 break;
@@ -312,11 +312,18 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 if (ph.hit) {
                     const double u = draw(ctx, c.s0, 0);
                     const Ref sel = B + op.pg;
+                    bool blocked = false;
+                    double trans = 0.0;
+                    if (op.flags & 8) {   // L1 support: block = openfraction, offset of the Si transmission table
+                        const Ref lb = B + c.c[2];
+                        blocked = draw(ctx, c.s1, 0) > lb[0];
+                        if (blocked) trans = filter_value(st_sm, PRef<false>{P.prog, (int)lb[1]}, ph.energy, 1);
+                    }
                     op_grating(st_sm, ph, pr, B + geom, op.flags,
                                [&](double energy, double bl, double& psel) {
                                    return select_order(sel, P.prog, u, energy, bl, psel);
                                },
-                               order, blaze);
+                               order, blaze, blocked, trans);
                 }
                 put(ctx, wm, 0, c.cp[0], ph.hit, order);
                 put(ctx, wm, 1, c.cp[1], ph.hit, blaze);
@@ -327,7 +334,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const OpCold& c = opc[pc];
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 double px, py;
-                op_detpix(ph, pr, px, py);
+                op_detpix(ph, pr, op.flags, px, py);
                 put(ctx, wm, 0, c.cp[0], ph.hit, px);
                 put(ctx, wm, 1, c.cp[1], ph.hit, py);
                 if (c.s0 >= 0 && ph.hit) {
@@ -352,6 +359,21 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     const long long idn = (long long)(B + row)[c.w15];
                     accumulate_image(hot, P.cols.f64[c.s0], gp + 6, idn, chipx - 1.0, chipy - 1.0, ph.prob);
                 }
+                break;
+            }
+            case MXB_OP_CYLINDER: {
+                geom = op.pg;
+                ph.hit = cylinder_intersect(B + geom, ph.pos, ph.dir, ph.ip, ph.l0, ph.l1) && ctx.active;
+                const unsigned m = __ballot_sync(0xffffffffu, ph.hit);
+                if (lane0) my_hits[pc] += __popc(m);
+                break;
+            }
+            case MXB_OP_QFACTOR: {
+                if (ph.hit) op_qfactor(st_sm, ph, pr);
+                break;
+            }
+            case MXB_OP_L2ABS: {
+                if (ph.hit) op_l2abs(st_sm, ph, pr, B + geom);
                 break;
             }
             case MXB_OP_BREWSTER: {

@@ -13,7 +13,7 @@ from . import _lib
 from .base import _parse_position_keywords
 from .program import geom14
 
-__all__ = ['NoGeometry', 'Geometry', 'FinitePlane', 'PlaneWithHole', 'RectangleHole', 'CircularHole']
+__all__ = ['NoGeometry', 'Geometry', 'FinitePlane', 'PlaneWithHole', 'RectangleHole', 'CircularHole', 'Cylinder']
 
 
 class NoGeometry:
@@ -134,3 +134,61 @@ class CircularHole(PlaneWithHole):
             raise ValueError('phi[1] - phi[0] must be less than 2 pi.')
         self.phi = phi
         super().__init__(kwargs)
+
+
+class Cylinder(Geometry):
+    """Ring / tube: circle (ellipse) in the local xy plane, flat along z (reference
+    marxs/math/geometry.py:383-564).  ``zoom[0], zoom[1]`` are the radii, ``zoom[2]`` the half
+    width; ``phi_lim`` restricts the covered angle range."""
+
+    loc_coos_name = ['phi', 'z']
+    shape = 'surface'
+
+    def __init__(self, kwargs={}):
+        self.coos_limits = [np.asanyarray(kwargs.pop('phi_lim', [-np.pi, np.pi]), dtype=float), np.array([-1., 1.])]
+        super().__init__(kwargs)
+
+    def __getitem__(self, value):
+        if value == 'R':
+            from .affines import decompose44
+            return decompose44(self.pos4d)[2][0]
+        return super().__getitem__(value)
+
+    @property
+    def phi_lim(self):
+        return self.coos_limits[0]
+
+    def intersect(self, dir, pos):
+        """-> (intersect bool (N,), interpos (N, 4), interpos_local (N, 2) = (phi, z)), NaN on miss.
+        Runs the CYLINDER op of the trace kernel on a scratch table."""
+        from .photons import PhotonBatch
+        from .program import Lowering
+        if not isinstance(dir, torch.Tensor):
+            if not torch.cuda.is_available():
+                raise _lib.MxbError('Geometry.intersect needs a CUDA device (no CPU fallback)')
+            dir = torch.as_tensor(np.asarray(dir), device='cuda')
+            pos = torch.as_tensor(np.asarray(pos), device='cuda')
+        if dir.device.type != 'cuda':
+            raise _lib.MxbError('Geometry.intersect needs CUDA tensors (no CPU fallback)')
+        if bool(torch.any(dir.as_subclass(torch.Tensor)[:, 3] != 0)):
+            raise ValueError('First input must be direction vectors.')
+        n = dir.shape[0]
+        b = PhotonBatch(device=dir.device)
+        b['pos'] = pos.as_subclass(torch.Tensor).clone()
+        b['dir'] = dir.as_subclass(torch.Tensor).clone()
+        b['polarization'] = torch.zeros((n, 4), dtype=torch.float64, device=dir.device)
+        b['energy'] = torch.ones(n, dtype=torch.float64, device=dir.device)
+        b['probability'] = torch.ones(n, dtype=torch.float64, device=dir.device)
+        lw = Lowering(b.colnames)
+        lw.cylinder(self.pos4d, self.phi_lim)
+        lw.commit(['_phi', '_z'], None, 0)
+        prog = lw.finish()
+        prog.run(b, check=True)
+        if '_phi' not in b:     # nothing hit: the columns were pruned like the reference does
+            nan = torch.full((n,), float('nan'), dtype=torch.float64, device=dir.device)
+            return torch.zeros(n, dtype=torch.bool, device=dir.device), torch.stack([nan] * 4, 1), torch.stack([nan] * 2, 1)
+        loc = torch.stack([b['_phi'].as_subclass(torch.Tensor), b['_z'].as_subclass(torch.Tensor)], 1)
+        hit = torch.isfinite(loc[:, 0])
+        ipos = b['pos'].as_subclass(torch.Tensor).clone()
+        ipos[~hit] = float('nan')
+        return hit, ipos, loc

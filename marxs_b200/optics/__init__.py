@@ -1,6 +1,6 @@
 """Optical elements (same names as ``marxs.optics``)."""
 from .aperture import RectangleAperture, CircleAperture, MultiAperture
-from .detector import FlatDetector
+from .detector import FlatDetector, CircularDetector
 from .grating import FlatGrating, CATGrating, OrderSelector, EfficiencyFile
 from .mirror import PerfectLens
 from .baffles import Baffle, CircularBaffle

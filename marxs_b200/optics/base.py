@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from ..base import SimulationSequenceElement
-from ..geometry import Geometry, FinitePlane
+from ..geometry import Geometry, FinitePlane, Cylinder
 from ..program import NotFusable
 from ..simulator import BaseContainer, run_fused
 
@@ -67,10 +67,18 @@ class OpticalElement(SimulationSequenceElement):
         for c in mro[:owner]:
             if any(h in c.__dict__ for h in _PY_HOOKS):
                 return False
-        return isinstance(self.geometry, FinitePlane)
+        return isinstance(self.geometry, self._lowerable_geometries)
+
+    _lowerable_geometries = (FinitePlane,)
+
+    def _lower_intersect(self, lw):
+        if isinstance(self.geometry, Cylinder):
+            lw.cylinder(self.pos4d, self.geometry.phi_lim)
+        else:
+            lw.plane(self.pos4d, circular=getattr(self.geometry, 'circular', False))
 
     def _lower(self, lw):
-        lw.plane(self.pos4d, circular=getattr(self.geometry, 'circular', False))
+        self._lower_intersect(lw)
         self._lower_specific(lw)
         lw.commit(self.loc_coos_name, self.id_col, self.id_num)
 

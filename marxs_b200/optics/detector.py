@@ -4,9 +4,10 @@ import warnings
 import numpy as np
 
 from ..affines import decompose44
-from .base import FlatOpticalElement
+from ..geometry import Cylinder
+from .base import FlatOpticalElement, OpticalElement
 
-__all__ = ['FlatDetector']
+__all__ = ['FlatDetector', 'CircularDetector']
 
 
 class SimulationSetupWarning(Warning):
@@ -49,3 +50,23 @@ class FlatDetector(FlatOpticalElement):
               pf=lw.eparams([self.pixsize, self.centerpix[0], self.centerpix[1]]),
               cols=[lw.fcol(self.detpix_name[0]), lw.fcol(self.detpix_name[1])], s0=s0,
               w14=self.id_num if lw.array is None else 0)
+
+
+class CircularDetector(OpticalElement):
+    """Detector shaped like a ring or tube following the Rowland circle (reference :78-118): adds
+    det_phi [rad], det_y [mm] and detpix_x = phi * R / pixsize, detpix_y = y / pixsize."""
+
+    loc_coos_name = ['det_phi', 'det_y']
+    detpix_name = ['detpix_x', 'detpix_y']
+    display = {'color': (1.0, 1.0, 0.), 'opacity': 0.7}
+    centerpix = [0, 0]
+    default_geometry = Cylinder
+    _lowerable_geometries = (Cylinder,)
+
+    def __init__(self, pixsize=1, **kwargs):
+        self.pixsize = pixsize
+        super().__init__(**kwargs)
+
+    def _lower_specific(self, lw):
+        lw.op('DETPIX', flags=2, pf=lw.eparams([self.pixsize, self.centerpix[0], self.centerpix[1], self.geometry['R']]),
+              cols=[lw.fcol(self.detpix_name[0]), lw.fcol(self.detpix_name[1])], w14=self.id_num)

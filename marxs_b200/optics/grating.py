@@ -125,9 +125,19 @@ class FlatGrating(FlatOpticalElement):
         dd = -e_perp[0]
         mod = self._blaze_modifier()
         flags = (1 if self._cat else 0) | (0 if self.transmission else 2) | (4 if mod is not None else 0)
-        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [self._d], list(mod) if mod is not None else []]))
-        lw.op('GRATING', flags=flags, pg=lower_selector(self.order_selector, lw), pf=pf,
-              cols=[lw.fcol(self.order_name), lw.fcol(self.blaze_name)], s0=lw.slot('uniform'))
+        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [self._d], list(mod) if mod is not None else [0., 0.]]))
+        extra = self._lower_l1(lw)         # (flag, second draw slot, block offset) for the L1 support variant
+        cols = [lw.fcol(self.order_name), lw.fcol(self.blaze_name)]
+        s0 = lw.slot('uniform')
+        if extra is not None:
+            cols.append(extra[1])
+            flags |= 8
+        lw.op('GRATING', flags=flags, pg=lower_selector(self.order_selector, lw), pf=pf, cols=cols, s0=s0,
+              s1=lw.slot('uniform') if extra is not None else -1)
+        lw.last_order_col = self.order_name
+
+    def _lower_l1(self, lw):
+        return None
 
 
 class CATGrating(FlatGrating):

@@ -46,7 +46,8 @@ class RandomGaussianScatter(FlatOpticalElement):
     def _lower_specific(self, lw):
         if callable(self.scatter):
             from ..program import UnsupportedCallable
-            raise UnsupportedCallable('callable scatter(photons, ...) is not supported on the device')
+            raise UnsupportedCallable('callable scatter(photons, ...) is not supported on the device '
+                                      '(L2Diffraction has its own fused form)')
         sigma = _rad(self.scatter)
         if sigma == 0:
             return                      # reference returns {} : nothing changes (:121-123)

@@ -31,11 +31,11 @@ CORE_F64 = ['pos_x', 'pos_y', 'pos_z', 'dir_x', 'dir_y', 'dir_z', 'pol_x', 'pol_
 
 OP = dict(END=0, PLANE=1, COMMIT=2, ARRAY_BEGIN=3, ARRAY_END=4, BAFFLE=5, LENS=6, RSCATTER=7,
           GSCATTER=8, FILTER=9, GRATING=10, DETPIX=11, ACIS=12, BREWSTER=13, MLEFF=14, APERTURE=15,
-          PROPAGATE=16, GFILTER=17, LOADHIT=18)
+          PROPAGATE=16, GFILTER=17, LOADHIT=18, QFACTOR=19, L2ABS=20, CYLINDER=21)
 SEL_ORDERSELECTOR, SEL_EFFFILE, SEL_INTERPTABLE = 1, 2, 3
 ARRAY_HEADER_WORDS = 24
 MAX_STAGE_BYTES = 200 * 1024
-HIT_OPS = (OP['PLANE'], OP['APERTURE'], OP['ARRAY_BEGIN'], OP['LOADHIT'])
+HIT_OPS = (OP['PLANE'], OP['APERTURE'], OP['ARRAY_BEGIN'], OP['LOADHIT'], OP['CYLINDER'])
 
 
 class NotFusable(Exception):
@@ -159,6 +159,7 @@ class Lowering:
         self.needs_pos = False            # an aperture creates the pos column
         self.aux = OrderedDict()          # name -> device tensor reached through an f64 pointer slot
         self._no_fold = None
+        self.last_order_col = None        # column written by the latest GRATING op of the current element stack
         self.image = None                 # (tensor, sel_lo) of the detector array being lowered
 
     # ---- transactions (an element that turns out not to be fusable is rolled back) ----
@@ -327,6 +328,21 @@ class Lowering:
                 raise NotFusable('arrays of circular elements are not supported')
             return
         self.op('PLANE', flags=1 if circular else 0, pg=self.params(geom14(pos4d)))
+        self.last_order_col = None
+
+    def cylinder(self, pos4d, phi_lim):
+        """Start an element on a Cylinder geometry (math/geometry.py:470-564)."""
+        if self.array is not None:
+            raise NotFusable('arrays of cylinders are not supported')
+        p = np.asarray(pos4d, dtype=float)
+        twopi = 2 * np.pi
+        b1 = (twopi + (float(phi_lim[0]) % twopi)) % twopi      # angle_between, math/utils.py:208-210
+        b2 = (twopi + (float(phi_lim[1]) % twopi)) % twopi
+        # zoom_z as transforms3d.affines.decompose44 gives it: norm of the third column of the 3x3 part
+        from .affines import decompose44
+        zoom = decompose44(p)[2]
+        self.op('CYLINDER', pg=self.params(np.concatenate([np.linalg.inv(p).ravel(), p.ravel(), [b1, b2, zoom[2]]])))
+        self.last_order_col = None
 
     FOLDABLE = ('PLANE', 'LENS', 'RSCATTER', 'GSCATTER', 'FILTER', 'GRATING', 'DETPIX', 'BREWSTER', 'MLEFF')
     COMMIT_BIT, COMMIT_ROW_ID = 256, 512
@@ -339,7 +355,8 @@ class Lowering:
         c2 = self.icol(id_col) if id_col is not None else -1
         a = self.array
         if a is not None:
-            a['id_num'] = id_num
+            if id_col is not None:
+                a['id_num'] = id_num                 # layers of a FlatStack carry no id column of their own
             if a['facet'] > 0:                       # replay the template facet's decision
                 folded = a['folds'][a['fold_cursor']]
                 a['fold_cursor'] += 1
