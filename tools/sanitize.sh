@@ -24,6 +24,25 @@ out = inst(mb.PhotonBatch(src, device='cuda')).to_numpy()
 assert (out['CCD'] >= 0).sum() > 100
 ht = mhost.HostPhotonTable.from_columns({k: out[k] if k in out else v for k, v in src.items()} | {'pos': np.tile([60., 0, 0, 1.], (n, 1))})
 mhost.trace_host(optics.FlatDetector(pixsize=0.1, zoom=[1, 5, 5]), ht, chunk=1024)
+# specialised kernel of the same small programs, event compaction, CAT stack + cylinder detector
+from marxs_b200 import _lib, events
+from marxs_b200.missions import mitsnl
+_lib.load().mxb_set_jit(2)
+out2 = inst(mb.PhotonBatch(src, device='cuda'))
+assert _lib.load().mxb_jit_info().startswith(b'jit ')
+ev = events.compact(out2, sel='CCD', weight='probability')
+assert len(ev) == int(((out2['CCD'] >= 0) & (out2['probability'] > 0)).sum())
+sel = optics.OrderSelector(np.arange(-2, 3))
+cat = simulator.Sequence(elements=[simulator.Parallel(elem_class=mitsnl.CATL1L2Stack, id_col='facet',
+                                                       elem_pos={'position': [[0., -3, 0], [0., 3, 0]]},
+                                                       elem_args={'zoom': [1, 2.5, 5], 'order_selector': sel}),
+                                    optics.CircularDetector(pixsize=0.1, position=[-50., 0, 0], zoom=[50., 50., 10.])])
+ph = {k: v for k, v in src.items()} | {'pos': np.tile([60., 0, 0, 1.], (n, 1)) + rng.uniform(-4, 4, (n, 4)) * [0, 1, 1, 0]}
+for jit in (2, 0):
+    _lib.load().mxb_set_jit(jit)
+    o = cat(mb.PhotonBatch(ph, device='cuda')).to_numpy()
+    assert np.isfinite(o['det_phi']).sum() > 100
+_lib.load().mxb_set_jit(-1)
 print('sanitizer workload ok')
 PY
 done
