@@ -626,6 +626,85 @@ def case_cylinder(marxs, rng):
     save('cylinder', **arrays)
 
 
+class SeqFeeder:
+    """Replace np.random.uniform / rand for code that draws outside any optical element (sources):
+    the k-th call returns low + (high - low) * table[k]."""
+
+    def __init__(self, table):
+        self.table, self.k = table, 0
+
+    def _next(self, n):
+        v = np.asarray(self.table[self.k])
+        self.k += 1
+        assert len(v) == n, (len(v), n)
+        return v
+
+    def uniform(self, low=0., high=1., size=None):
+        return low + (high - low) * self._next(size)
+
+    def rand(self, n):
+        return self._next(n)
+
+    def __enter__(self):
+        self._orig = (np.random.uniform, np.random.rand)
+        np.random.uniform, np.random.rand = self.uniform, self.rand
+        return self
+
+    def __exit__(self, *exc):
+        np.random.uniform, np.random.rand = self._orig
+
+
+def case_sources(marxs, rng):
+    """Photon birth without sky frames: RandomArbitraryPdf, polarization_vectors, LabPointSourceCone,
+    FarLabPointSource (source/labSource.py, math/random.py, math/polarization.py:12-62)."""
+    import astropy.units as u
+    from astropy.table import QTable
+    from marxs.math.random import RandomArbitraryPdf
+    from marxs.math.polarization import polarization_vectors
+    from marxs.source import LabPointSourceCone, FarLabPointSource
+    arrays = {}
+    n = 1000
+    # arbitrary pdf (spectrum): upper bin edges + flux densities
+    x = np.array([0.3, 0.5, 0.9, 1.4, 2.2, 3.5, 6.0, 10.])
+    pdf = np.array([0., 3., 1., 5., 0.2, 4., 0.05, 1.])
+    u0, u1 = rng.random(n), rng.random(n)
+    with SeqFeeder([u0, u1]):
+        arrays['pdf_out'] = RandomArbitraryPdf(x, pdf)(n)
+    arrays['pdf_x'], arrays['pdf_pdf'], arrays['pdf_u0'], arrays['pdf_u1'] = x, pdf, u0, u1
+    # polarization vectors incl. rays along +-y
+    d = np.zeros((n, 4))
+    d[:, :3] = rng.normal(size=(n, 3))
+    d[:10, :3] = [0., 1., 0.]
+    d[10:20, :3] = [0., -2.5, 0.]
+    ang = rng.uniform(0, 2 * np.pi, n)
+    arrays['polvec_dir'], arrays['polvec_angle'] = d, ang
+    arrays['polvec_out'] = polarization_vectors(d, ang)
+    # cone source with a tabulated spectrum and random polarization
+    spec = QTable({'energy': x * u.keV, 'fluxdensity': pdf / u.s / u.cm**2 / u.keV})
+    cone = LabPointSourceCone(position=[200., 3., -2.], direction=[-1., 0.2, 0.1], half_opening=0.02,
+                              flux=100. / u.s, energy=spec)
+    draws = [rng.random(n) for _ in range(5)]      # energy bin, energy in bin, polangle, theta, v
+    with SeqFeeder(draws):
+        p = cone.generate_photons(10. * u.s)
+    assert len(p) == n
+    for c in ('time', 'energy', 'polangle', 'probability', 'pos', 'dir', 'polarization'):
+        arrays['cone_' + c] = np.asarray(p[c].data if hasattr(p[c], 'data') else p[c], dtype=float)
+    for k, dr in enumerate(draws):
+        arrays['cone_draw{0}'.format(k)] = dr
+    # far source behind a rectangular aperture, fixed energy and polarization angle
+    far = FarLabPointSource([500., 20., -30.], position=[50., 1., 2.], zoom=[1., 4., 7.],
+                            flux=100. / u.s, energy=1.5 * u.keV, polarization=0.7 * u.rad)
+    draws = [rng.random(n) for _ in range(2)]
+    with SeqFeeder(draws):
+        p = far.generate_photons(10. * u.s)
+    for c in ('time', 'energy', 'polangle', 'probability', 'pos', 'dir', 'polarization'):
+        arrays['far_' + c] = np.asarray(p[c].data if hasattr(p[c], 'data') else p[c], dtype=float)
+    arrays['far_pos4d'] = far.pos4d
+    for k, dr in enumerate(draws):
+        arrays['far_draw{0}'.format(k)] = dr
+    save('sources', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -635,7 +714,7 @@ def main():
     for i, case in enumerate([case_intersect, case_parallel_transport, case_gratings,
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
-                              case_parallel_overlap, case_cat_stack, case_cylinder]):
+                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

@@ -1375,6 +1375,270 @@ def make_draws(kinds, n, seed, aperture_weights=None):
 
 
 # ---------------------------------------------------------------------------
+# photon birth: sources and pointing  (source/basesources.py, source/labSource.py,
+# source/pointing.py, math/random.py, math/polarization.py:12-62)   -- SURVEY 8(f) rank 1
+# ---------------------------------------------------------------------------
+class RandomArbitraryPdf:
+    """math/random.py:4-95 (sort=True, randomize_in_bin=True): piecewise-constant pdf with UPPER bin
+    edges x.  Two uniforms per sample: u0 picks the bin through the cdf of the size-sorted bins,
+    u1 the position inside the bin."""
+
+    def __init__(self, x, pdf):
+        self.x = np.asarray(x, dtype=float)
+        self.bin_width = np.hstack(([0], np.diff(self.x)))
+        pdf = np.asarray(pdf, dtype=float) * self.bin_width
+        self.sortindex = np.argsort(pdf)
+        self.pdf = pdf[self.sortindex]
+        self.cdf = np.cumsum(self.pdf)
+
+    def __call__(self, u0, u1):
+        choice = 0. + (self.cdf[-1] - 0.) * u0            # np.random.uniform(high=cdf[-1])
+        index = self.sortindex[np.searchsorted(self.cdf, choice)]
+        return self.x[index - 1] + self.bin_width[index] * u1
+
+
+def polarization_vectors(dir_array, angles):
+    """math/polarization.py:12-62: angle 0 = the vector perpendicular to the ray closest to +y
+    (closest to +x for rays along y)."""
+    r = dir_array[:, 0:3] / norm3(dir_array)[:, None]
+    conv_x = np.isclose(r[:, 0], 0.) & np.isclose(r[:, 2], 0.)
+    v_1 = np.empty_like(r)
+    # y - r (r.y) resp. x - r (r.x)
+    ry, rx = r[:, 1], r[:, 0]
+    v_y = np.stack([0. - r[:, 0] * ry, 1. - r[:, 1] * ry, 0. - r[:, 2] * ry], axis=1)
+    v_x = np.stack([1. - r[:, 0] * rx, 0. - r[:, 1] * rx, 0. - r[:, 2] * rx], axis=1)
+    v_1 = np.where(conv_x[:, None], v_x, v_y)
+    v_1 = v_1 / norm3(v_1)[:, None]
+    v_2 = cross3(r, v_1)
+    pol = np.zeros((len(angles), 4))
+    pol[:, 0:3] = v_1 * np.cos(angles)[:, None] + v_2 * np.sin(angles)[:, None]
+    return pol
+
+
+class Source:
+    """source/basesources.py:85-277 for constant flux (photons per second through the aperture),
+    energy = number [keV] or (x, y) table (RandomArbitraryPdf, first y ignored), polarization = None
+    (uniform angle), number [rad] or (x, y) table.  Draw slots in reference call order."""
+
+    def __init__(self, energy=1., flux=1., polarization=None, geomarea=1.):
+        self.energy, self.flux, self.polarization, self.geomarea = energy, flux, polarization, geomarea
+        self.slots = None
+
+    def slot_kinds(self):
+        k = []
+        if isinstance(self.energy, tuple):
+            k += ['uniform', 'uniform']
+        if self.polarization is None:
+            k += ['uniform']
+        elif isinstance(self.polarization, tuple):
+            k += ['uniform', 'uniform']
+        return k
+
+    def _take(self, draws, n, cursor):
+        if draws is None:
+            return np.random.random_sample(n)
+        return draws.table[self.slots[cursor]]
+
+    def generate_times(self, exposuretime):
+        return np.arange(0, exposuretime, 1. / (self.flux * self.geomarea))
+
+    def generate_photons(self, exposuretime, draws=None):
+        times = self.generate_times(exposuretime)
+        n = len(times)
+        c = 0
+        if isinstance(self.energy, tuple):
+            x = np.asarray(self.energy[0], dtype=float)
+            y = np.hstack(([0], np.asarray(self.energy[1], dtype=float)[1:]))
+            en = RandomArbitraryPdf(x, y)(self._take(draws, n, c), self._take(draws, n, c + 1))
+            c += 2
+        else:
+            en = np.ones(n) * self.energy
+        if self.polarization is None:
+            pol = 0. + (2 * np.pi - 0.) * self._take(draws, n, c)
+            c += 1
+        elif isinstance(self.polarization, tuple):
+            pol = RandomArbitraryPdf(self.polarization[0], self.polarization[1])(
+                self._take(draws, n, c), self._take(draws, n, c + 1))
+            c += 2
+        else:
+            pol = np.ones(n) * self.polarization
+        t = PhotonTable(time=times, energy=en, polangle=pol, probability=np.ones(n))
+        return t, c
+
+
+class PointSource(Source):
+    """basesources.py:337-352: + ra, dec [deg]."""
+
+    def __init__(self, coords, **kwargs):
+        self.ra, self.dec = float(coords[0]), float(coords[1])
+        super().__init__(**kwargs)
+
+    def generate_photons(self, exposuretime, draws=None):
+        t, c = super().generate_photons(exposuretime, draws)
+        t['ra'] = np.ones(len(t)) * self.ra
+        t['dec'] = np.ones(len(t)) * self.dec
+        return t
+
+
+class LabPointSourceCone(Source):
+    """labSource.py:62-137: rays uniformly distributed inside a cone around ``direction``."""
+
+    def __init__(self, position=(0, 0, 0), half_opening=np.pi, direction=(1., 0., 0.), **kwargs):
+        self.dir = e2h(np.asanyarray(direction, dtype=float)[None, :] / np.linalg.norm(direction), 0)[0]
+        self.position = np.array([position[0], position[1], position[2], 1.], dtype=float)
+        self.half_opening = half_opening
+        kwargs.setdefault('flux', 1.)
+        super().__init__(geomarea=1., **kwargs)
+
+    def slot_kinds(self):
+        return super().slot_kinds() + ['uniform', 'uniform']
+
+    def rotation(self):
+        axis = np.cross(self.dir[:3], [0, 0, 1])
+        angle = np.arccos(self.dir[2])
+        return axangle2mat_single(axis, -angle)
+
+    def generate_photons(self, exposuretime, draws=None):
+        t, c = super().generate_photons(exposuretime, draws)
+        n = len(t)
+        theta = 0. + (2 * np.pi - 0.) * self._take(draws, n, c)
+        fractional_area = 2 * np.pi * (1 - np.cos(self.half_opening)) / (4 * np.pi)
+        v = 0. + (fractional_area - 0.) * self._take(draws, n, c + 1)
+        phi = np.arccos(1 - 2 * v)
+        d = np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+        R = self.rotation()
+        dr = np.zeros((n, 4))
+        for r in range(3):
+            dr[:, r] = R[r, 0] * d[:, 0] + R[r, 1] * d[:, 1] + R[r, 2] * d[:, 2]
+        t['pos'] = np.tile(self.position, (n, 1))
+        t['dir'] = dr
+        t['polarization'] = polarization_vectors(dr, t['polangle'])
+        return t
+
+
+class FarLabPointSource(Source):
+    """labSource.py:13-59: start positions uniform on a rectangular aperture, rays from ``sourcePos``."""
+
+    def __init__(self, sourcePos, **kwargs):
+        self.sourcePos = np.asarray(sourcePos, dtype=float)
+        pos_kw = {k: kwargs.pop(k) for k in ('pos4d', 'position', 'orientation', 'zoom') if k in kwargs}
+        self.pos4d = parse_position_keywords(pos_kw)
+        kwargs.setdefault('flux', 1.)
+        super().__init__(geomarea=1., **kwargs)
+
+    def slot_kinds(self):
+        return super().slot_kinds() + ['uniform', 'uniform']
+
+    def generate_photons(self, exposuretime, draws=None):
+        t, c = super().generate_photons(exposuretime, draws)
+        n = len(t)
+        y = -1 + (1 - -1) * self._take(draws, n, c)
+        z = -1 + (1 - -1) * self._take(draws, n, c + 1)
+        P = self.pos4d
+        pos = np.empty((n, 4))
+        for r in range(4):
+            pos[:, r] = P[r, 0] * 0. + P[r, 1] * y + P[r, 2] * z + P[r, 3] * 1.
+        d = np.zeros((n, 4))
+        d[:, :3] = pos[:, :3] - self.sourcePos[None, :]
+        t['pos'] = pos
+        t['dir'] = d
+        t['polarization'] = polarization_vectors(d, t['polangle'])
+        return t
+
+
+def skyoffset_matrix(ra0, dec0, roll):
+    """Rotation ICRS cartesian -> SkyOffsetFrame(origin=(ra0, dec0), rotation=roll) cartesian, angles in
+    rad.  astropy/coordinates/builtin_frames/skyoffset.py: R_x(-roll) R_y(-dec0) R_z(ra0) with astropy's
+    passive ``rotation_matrix``.  NOT runnable here (no astropy): pinned through the known answers of
+    source/tests/test_pointing.py."""
+    def rot(angle, axis):
+        c, s_ = np.cos(angle), np.sin(angle)
+        i, j = {'x': (1, 2), 'y': (2, 0), 'z': (0, 1)}[axis]
+        R = np.eye(3)
+        R[i, i], R[j, j] = c, c
+        R[i, j], R[j, i] = s_, -s_
+        return R
+    return rot(-roll, 'x') @ rot(-dec0, 'y') @ rot(ra0, 'z')
+
+
+class FixedPointing:
+    """source/pointing.py:45-177: photon direction and polarization vector from ra, dec, polangle."""
+
+    def __init__(self, coords, roll=0., reference_transform=None):
+        self.ra0, self.dec0, self.roll = np.deg2rad(coords[0]), np.deg2rad(coords[1]), roll
+        self.reference_transform = np.eye(4) if reference_transform is None else np.asarray(reference_transform, float)
+        self.coords = coords
+        self.slots = None
+
+    slot_kinds_list = []
+
+    def matrix(self):
+        return skyoffset_matrix(self.ra0, self.dec0, self.roll)
+
+    def sky_to_offset(self, ra_deg, dec_deg):
+        ra, dec = np.deg2rad(ra_deg), np.deg2rad(dec_deg)
+        v = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)], axis=1)
+        M = self.matrix()
+        out = np.empty_like(v)
+        for r in range(3):
+            out[:, r] = M[r, 0] * v[:, 0] + M[r, 1] * v[:, 1] + M[r, 2] * v[:, 2]
+        return out
+
+    def _apply_ref(self, v3):
+        T = self.reference_transform
+        out = np.zeros((v3.shape[0], 4))
+        for r in range(4):
+            out[:, r] = T[r, 0] * v3[:, 0] + T[r, 1] * v3[:, 1] + T[r, 2] * v3[:, 2]
+        return out
+
+    def photons_dir(self, ra, dec):
+        xyz = self.sky_to_offset(ra, dec)
+        return self._apply_ref(normalize3(-xyz))
+
+    def photons_pol(self, photonsdir, polangle):
+        north = self.sky_to_offset(np.array([0.]), np.array([90.]))
+        northdir = self._apply_ref(north)[0]
+        proj = photonsdir[:, 0] * northdir[0] + photonsdir[:, 1] * northdir[1] + photonsdir[:, 2] * northdir[2]
+        n_in = northdir[None, :3] - photonsdir[:, :3] * proj[:, None]
+        n_in = n_in / norm3(n_in)[:, None]
+        e_in = cross3(photonsdir, n_in)
+        pol = np.zeros((len(polangle), 4))
+        pol[:, :3] = np.cos(polangle)[:, None] * n_in + np.sin(polangle)[:, None] * e_in
+        return pol
+
+    def __call__(self, photons, draws=None):
+        photons['dir'] = self.photons_dir(photons['ra'], photons['dec'])
+        photons['polarization'] = self.photons_pol(photons['dir'], photons['polangle'])
+        photons.meta['RA_PNT'] = (self.coords[0], '[deg] Pointing RA')
+        photons.meta['DEC_PNT'] = (self.coords[1], '[deg] Pointing Dec')
+        photons.meta['ROLL_PNT'] = (np.rad2deg(self.roll), '[deg] Pointing Roll')
+        return photons
+
+
+class JitterPointing(FixedPointing):
+    """source/pointing.py:180-211: uncorrelated Gaussian jitter about a random axis in the yz plane."""
+
+    def __init__(self, jitter, **kwargs):
+        self.jitter = abs(jitter)
+        super().__init__(**kwargs)
+
+    def __call__(self, photons, draws=None):
+        photons = super().__call__(photons, draws)
+        n = len(photons)
+        u = np.random.random_sample(n) if draws is None else draws.table[self.slots[0]]
+        randang = u * 2. * np.pi
+        ax = np.stack([np.zeros(n), np.sin(randang), np.cos(randang)], axis=1)
+        if self.jitter > 0:
+            z = np.random.normal(size=n) if draws is None else draws.table[self.slots[1]]
+            jitterang = 0. + self.jitter * z
+            d = axangle_rotate_T(ax, jitterang, photons['dir'])
+            p = axangle_rotate_T(ax, jitterang, photons['polarization'])
+            photons['dir'] = e2h(d, 0)
+            photons['polarization'] = e2h(p, 0)
+        return photons
+
+
+# ---------------------------------------------------------------------------
 # Chandra configuration  (missions/chandra/{hess,hrma_py,det_acis}.py)
 # ---------------------------------------------------------------------------
 HRMA_RADII = np.array([[598., 610.], [481, 491], [424, 433], [315, 322]])  # hrma_py.py:13

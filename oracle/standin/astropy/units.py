@@ -148,6 +148,10 @@ class Quantity(np.ndarray):
         v = self.view(np.ndarray)
         return v if v.ndim else float(v)
 
+    @property
+    def isscalar(self):
+        return self.ndim == 0
+
     def to(self, unit, equivalencies=None):
         return Quantity(_convert(self.view(np.ndarray), self.unit, unit,
                                  equivalencies), unit)

@@ -414,3 +414,81 @@ def test_golden_cylinder(tag):
     det = mo.CircularDetector(pixsize=0.05, pos4d=g[tag + '_pos4d'], phi_lim=g[tag + '_phi_lim'])
     out = det(t)
     assert_cols(out, g, tag + '_', rtol=1e-12, atol=1e-11)
+
+
+# ---------------------------------------------------------------------------
+# photon birth.  Lab sources: golden from the reference.  Sky pointing: the
+# reference needs astropy's SkyOffsetFrame (not installable here), so the restated rotation is
+# pinned by the known answers of marxs/source/tests/test_pointing.py instead ("parity pinned to the
+# reference's own tests", not to a reference run).
+# ---------------------------------------------------------------------------
+def test_golden_sources():
+    g = load('sources')
+    out = mo.RandomArbitraryPdf(g['pdf_x'], g['pdf_pdf'])(g['pdf_u0'], g['pdf_u1'])
+    np.testing.assert_allclose(out, g['pdf_out'], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(mo.polarization_vectors(g['polvec_dir'], g['polvec_angle']), g['polvec_out'],
+                               rtol=1e-13, atol=1e-15)
+    cone = mo.LabPointSourceCone(position=[200., 3., -2.], direction=[-1., 0.2, 0.1], half_opening=0.02,
+                                 flux=100., energy=(g['pdf_x'], g['pdf_pdf']))
+    assert cone.slot_kinds() == ['uniform'] * 5
+    cone.slots = list(range(5))
+    p = cone.generate_photons(10., mo.Draws([g['cone_draw{0}'.format(k)] for k in range(5)]))
+    for c in ('time', 'energy', 'polangle', 'probability', 'pos', 'dir', 'polarization'):
+        np.testing.assert_allclose(p[c], g['cone_' + c], rtol=1e-13, atol=1e-15, err_msg=c)
+    far = mo.FarLabPointSource([500., 20., -30.], position=[50., 1., 2.], zoom=[1., 4., 7.], flux=100.,
+                               energy=1.5, polarization=0.7)
+    np.testing.assert_allclose(far.pos4d, g['far_pos4d'], rtol=0, atol=0)
+    far.slots = [0, 1]
+    p = far.generate_photons(10., mo.Draws([g['far_draw0'], g['far_draw1']]))
+    for c in ('time', 'energy', 'polangle', 'probability', 'pos', 'dir', 'polarization'):
+        np.testing.assert_allclose(p[c], g['far_' + c], rtol=1e-13, atol=1e-15, err_msg=c)
+
+
+def test_pointing_known_answers():
+    """source/tests/test_pointing.py:12-60."""
+    xyz2zxy = np.array([[0., 0, 1, 0], [1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1]]).T
+    photons = mo.PointSource((12., 34.)).generate_photons(5.)
+    p_x = mo.FixedPointing((12., 34.))(photons.copy())
+    assert np.allclose(p_x['dir'][:, 0], -1.) and np.allclose(p_x['dir'][:, 1:], 0)
+    p_z = mo.FixedPointing((12., 34.), reference_transform=xyz2zxy)(photons.copy())
+    assert np.allclose(p_z['dir'][:, 2], -1.) and np.allclose(p_z['dir'][:, :2], 0)
+    photons = mo.PointSource((187.4, 0.)).generate_photons(5.)
+    photons['polangle'] = np.deg2rad(np.array([0., 90., 180., 270., 45.]))
+    p_x = mo.FixedPointing((187.4, 0.))(photons.copy())
+    for k, want in enumerate([[0, 0, 1, 0], [0, 1, 0, 0], [0, 0, -1, 0], [0, -1, 0, 0], [0, 2 ** -0.5, 2 ** -0.5, 0]]):
+        assert np.allclose(p_x['polarization'][k], want), k
+    p_z = mo.FixedPointing((187.4, 0.), reference_transform=xyz2zxy)(photons.copy())
+    assert np.allclose(p_z['polarization'][0], [0, 1, 0, 0]) and np.allclose(p_z['polarization'][1], [1, 0, 0, 0])
+    assert np.allclose(p_z['polarization'][4], [2 ** -0.5, 2 ** -0.5, 0, 0])
+    # photons pointing east at the same RA have parallel polarization vectors, for any pointing
+    photons = mo.PointSource((22.5, 0.)).generate_photons(5.)
+    photons['dec'] = np.array([67., 23., 0., -45.454, -67.88])
+    photons['polangle'] = np.full(5, np.pi / 2)
+    p = mo.FixedPointing((94.3, 23.))(photons.copy())
+    for i in range(1, 5):
+        assert np.isclose(np.dot(p['polarization'][0], p['polarization'][i]), 1)
+
+
+def test_pointing_offsets_and_jitter():
+    """East of the pointing is +y on the sky (photons then travel towards -y), North is +z at roll 0;
+    jitter keeps polarization perpendicular to the ray and has the requested width
+    (source/tests/test_pointing.py:62-115)."""
+    ph = mo.PointSource((30.01, 10.)).generate_photons(3.)
+    ph['dec'] = np.array([10., 10.01, 9.99])
+    ph['ra'] = np.array([30.01, 30., 30.])
+    p = mo.FixedPointing((30., 10.))(ph)
+    assert p['dir'][0, 1] < 0 and abs(p['dir'][0, 2]) < 1e-6
+    assert p['dir'][1, 2] < 0 and abs(p['dir'][1, 1]) < 1e-12 and p['dir'][2, 2] > 0
+    assert np.isclose(-p['dir'][0, 1], np.deg2rad(0.01) * np.cos(np.deg2rad(10.)), rtol=1e-6)
+    rng = np.random.default_rng(3)
+    n = 20000
+    t = mo.PhotonTable(ra=rng.uniform(0, 360, n), dec=np.rad2deg(np.arcsin(rng.uniform(-1, 1, n))), time=np.arange(n, dtype=float),
+                       polangle=rng.uniform(0, 2 * np.pi, n), probability=np.ones(n))
+    fixed = mo.FixedPointing((25., -10.))(t.copy())
+    jp = mo.JitterPointing(jitter=np.deg2rad(1. / 3600.), coords=(25., -10.))
+    jp.slots = [0, 1]
+    jit = jp(t.copy(), mo.Draws([rng.random(n), rng.standard_normal(n)]))
+    ang = np.arccos(np.clip(np.einsum('ij,ij->i', fixed['dir'], jit['dir']), -1, 1))
+    assert 0.5 < np.std(ang) / np.deg2rad(1. / 3600.) < 0.7          # |N(0, s)| has std 0.60 s
+    assert np.allclose(np.einsum('ij,ij->i', jit['dir'], jit['polarization']), 0, atol=1e-12)
+    assert np.allclose(np.linalg.norm(jit['polarization'], axis=1), 1)
