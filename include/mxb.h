@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 7
+#define MXB_ABI_VERSION 8
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -79,7 +79,8 @@ typedef struct MxbColumns {
  * fields are stored as exact small doubles).  Layout:
  *   [0] magic 0x4D5842 ('MXB')   [1] ABI version   [2] n_ops   [3] total words
  *   [4] words staged into shared memory (ops + geometry + facet rows + grids + small tables)
- *   [5..15] reserved
+ *   [5] flags: bit0 = photons are BORN by the program (first op GENERATE): the core planes are not read
+ *   [6..15] reserved
  *   [16 + 16*i ...] op i: 16 words
  *        w0 type   w1 flags   w2 pg (word offset of global params, -1)   w3 pf (offset inside facet row, -1)
  *        w4..w11 c0..c7 : column indices (f64 slot, or i64 slot for id columns; -1 = do not materialise,
@@ -129,6 +130,20 @@ typedef struct MxbColumns {
 #define MXB_OP_L2ABS       20  /* mitsnl/catgrating.py:222-259 L2Abs: params openfraction, bardepth*innerfree, totalarea         */
 #define MXB_OP_CYLINDER    21  /* math/geometry.py:470-564 Cylinder.intersect: pg: inv(pos4d)[16] pos4d[16] (row major)
                                   phi_lo phi_hi (normalised to [0, 2 pi)) zoom_z ; local coordinates (phi, z * zoom_z)           */
+
+#define MXB_OP_GENERATE    22  /* photon birth, source/basesources.py:158-277 (constant flux): pg: dt, e_mode, e_const, e_table,
+                                  p_mode, p_const, p_table, sky, ra, dec.  time = id * dt; energy: mode 0 constant, 1
+                                  RandomArbitraryPdf table (math/random.py:80-95; draws s0, s1); polangle: mode 0 constant,
+                                  1 uniform [0, 2 pi) (draw w14), 2 table (draws w14, w15); probability = 1.
+                                  Tables live after the staged region: n, cdf[n], sortindex[n], x[n], bin_width[n].
+                                  c0 time, c1 polangle, c2 ra, c3 dec output columns (sky != 0: AstroSource)                  */
+#define MXB_OP_POINTING    23  /* source/pointing.py:101-211 FixedPointing / JitterPointing: c0 ra, c1 dec, c2 polangle INPUT
+                                  columns; pg: M[9] (ICRS -> offset frame), T[9] (reference_transform), north[3], jitter sigma;
+                                  flags bit0: jitter (draws s0 uniform axis angle, s1 normal); all photons                   */
+#define MXB_OP_LABCONE     24  /* source/labSource.py:62-137 LabPointSourceCone: pg: position[3], R[9], fractional area;
+                                  draws s0 (theta), s1 (v); c0 polangle INPUT column; sets pos, dir, polarization            */
+#define MXB_OP_FARLAB      25  /* source/labSource.py:13-59 FarLabPointSource: pg: pos4d rows 0..2 [12], sourcePos[3];
+                                  draws s0, s1; c0 polangle INPUT column; sets pos, dir, polarization                        */
 
 /* selector kinds (first word of the selector block) */
 #define MXB_SEL_ORDERSELECTOR 1  /* grating.py:12-57:  n, psum, cdf[n], orders[n]                                                   */

@@ -94,6 +94,7 @@ struct Gen {
     std::map<std::pair<int, int>, int> sidx;
     bool need_blob = false;       // some op reads the blob through PRef (staging needed)
     bool need_hot = false;        // a detector image is accumulated: per-CTA hot-pixel cache
+    bool born = false;            // header flag: the program creates the photons (no loads)
     int threads = 640;            // CTA size the kernel is compiled for
     bool pipe_wanted = true, pipe = false;
     std::vector<Op> ops;
@@ -237,6 +238,8 @@ struct Gen {
         for (int k = 0; k < MXB_MAX_I64_COLS; ++k) key.push_back(cols->i64[k] ? 1 : 0);
         for (int k = 0; k < MXB_MAX_SLOTS; ++k) key.push_back(cols->draws[k] ? 1 : 0);
         keyi(stage_words);
+        born = ((int)W[5] & 1) != 0;
+        keyi(born ? 1 : 0);
         return true;
     }
 
@@ -391,6 +394,58 @@ struct Gen {
         case MXB_OP_BREWSTER:
             out("            if (ph.hit) op_brewster(st_sm, ph, %s);", PR(o, 21).c_str());
             break;
+        case MXB_OP_GENERATE: {
+            if (in_array) return fail("GENERATE inside an array");
+            const std::string p = S(o.pg, 10);
+            out("            {");
+            out("            double time = 0, polangle = 0;");
+            out("            if (active) op_generate(ph, %s, P.prog, gid, [&](int s) {", p.c_str());
+            // the draw source of each slot is known: emit a switch over the (at most four) slots used
+            out("                switch (s) {");
+            for (int sl : {o.s0, o.s1, o.w14, o.w15})
+                if (sl >= 0 && sl < MXB_MAX_SLOTS) out("                case %d: return %s;", sl, draw(sl, 0).c_str());
+            out("                default: return 0.0;");
+            out("                } }, %d, %d, %d, %d, time, polangle);", o.s0, o.s1, o.w14, o.w15);
+            for (int k = 0; k < 4; ++k) {
+                const char* val[] = {"time", "polangle", nullptr, nullptr};
+                if (!has_f(o.c[k])) continue;
+                const int idx = o.c[k] >= MXB_COL_INIT ? o.c[k] - MXB_COL_INIT : o.c[k];
+                if (k < 2) out("            jput(%s, i, active, true, %s);", F(idx).c_str(), val[k]);
+                else out("            jput(%s, i, active, true, %s[%d]);", F(idx).c_str(), p.c_str(), 6 + k);
+            }
+            out("            }");
+            break;
+        }
+        case MXB_OP_POINTING: {
+            if (in_array) return fail("POINTING inside an array");
+            for (int j = 0; j < 3; ++j)
+                if (o.c[j] < 0 || o.c[j] >= MXB_MAX_F64_COLS || !cols->f64[o.c[j]]) return fail("POINTING: missing ra / dec / polangle column");
+            const std::string p = S(o.pg, 22);
+            out("            if (active) {");
+            out("                double ua = 0, zj = 0;");
+            if (fl & 1) {
+                out("                ua = %s;", draw(o.s0, 0).c_str());
+                out("                if (%s[21] > 0.0) zj = %s;", p.c_str(), draw(o.s1, 1).c_str());
+            }
+            out("                op_pointing(ph, %s, %d, %s[i], %s[i], %s[i], ua, zj);", p.c_str(), fl, F(o.c[0]).c_str(),
+                F(o.c[1]).c_str(), F(o.c[2]).c_str());
+            out("            }");
+            break;
+        }
+        case MXB_OP_LABCONE:
+        case MXB_OP_FARLAB: {
+            if (in_array) return fail("source op inside an array");
+            if (o.c[0] < 0 || o.c[0] >= MXB_MAX_F64_COLS || !cols->f64[o.c[0]]) return fail("source op: missing polangle column");
+            const bool cone = o.type == MXB_OP_LABCONE;
+            pos_committed = false;
+            out("            if (active) {");
+            out("                const double u0 = %s;", draw(o.s0, 0).c_str());
+            out("                const double u1 = %s;", draw(o.s1, 0).c_str());
+            out("                %s(ph, %s, u0, u1, %s[i]);", cone ? "op_labcone" : "op_farlab", S(o.pg, cone ? 13 : 15).c_str(),
+                F(o.c[0]).c_str());
+            out("            }");
+            break;
+        }
         case MXB_OP_CYLINDER: {
             if (in_array) return fail("CYLINDER inside an array");
             geom = S(o.pg, 35);
@@ -608,9 +663,14 @@ struct Gen {
         out("        const unsigned long long gid = (unsigned long long)(P.id0 + i);");
         out("        (void)gid;");
         out("        Photon ph;");
-        out("        pipe_load(pipe, P.in, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
+        if (born) {
+            out("        ph.pos = ph.dir = ph.pol = V3{kNaN, kNaN, kNaN};   // born by the program: nothing is read");
+            out("        ph.energy = ph.prob = kNaN;");
+        } else {
+            out("        pipe_load(pipe, P.in, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
+        }
         out("        photon_loaded(ph);");
-        out("#if JIT_PREFETCH");
+        out("#if JIT_PREFETCH && !%d", born ? 1 : 0);
         out("        if (i + stride < P.n) {   // next group's inputs -> L2 while this one is traced");
         out("#pragma unroll");
         out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.in[k] + i + stride));");
@@ -955,6 +1015,7 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     for (int c = 0; c <= MXB_COL_PROB; ++c)
         if ((uintptr_t)(src ? src[c] : cols->f64[c]) & 15) flags = 0;
     if (src && src[MXB_COL_ENERGY] != cols->f64[MXB_COL_ENERGY]) flags |= 2;   // bit 1: store energy
+    if ((int)prog_host[5] & 1) flags = (flags | 2) & ~1ULL;                     // born photons: energy is a result, no input pipe
     pw.push_back(flags);
     pw.push_back(seed);
     pw.push_back((uint64_t)(uintptr_t)status);

@@ -599,6 +599,131 @@ MXB_DEV void op_aperture(unsigned long long* st_sm, Photon& ph, PP pr, int flags
 }
 
 // ---------------------------------------------------------------------------
+// photon birth: sources and pointing as ops, so a simulation can start from
+// nothing but a photon count
+// ---------------------------------------------------------------------------
+// math/random.py:80-95 RandomArbitraryPdf (sort=True, randomize_in_bin=True); t (global): n, cdf[n],
+// sortindex[n], x[n], bin_width[n]
+MXB_DEV double arbitrary_pdf(const double* t, double u0, double u1) {
+    const int n = (int)__ldg(t);
+    const double* cdf = t + 1;
+    const double choice = 0. + (__ldg(cdf + n - 1) - 0.) * u0;
+    int lo = 0, hi = n;                      // np.searchsorted(cdf, choice): first i with cdf[i] >= choice
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(cdf + mid) < choice) lo = mid + 1; else hi = mid;
+    }
+    if (lo > n - 1) lo = n - 1;
+    const int index = (int)__ldg(t + 1 + n + lo);
+    const int below = index > 0 ? index - 1 : n - 1;     // python x[index - 1] wraps around
+    return __ldg(t + 1 + 2 * n + below) + __ldg(t + 1 + 3 * n + index) * u1;
+}
+
+// math/polarization.py:12-62 polarization_vectors
+MXB_DEV V3 polarization_vector(const V3& dir, double angle) {
+    const double nr = sqrt(dot(dir, dir));
+    const V3 r{dir.x / nr, dir.y / nr, dir.z / nr};
+    const bool conv_x = (fabs(r.x) <= 1e-8) && (fabs(r.z) <= 1e-8);     // np.isclose(., 0.)
+    const double rp = conv_x ? r.x : r.y;
+    V3 v1{(conv_x ? 1. : 0.) - r.x * rp, (conv_x ? 0. : 1.) - r.y * rp, 0. - r.z * rp};
+    const double n1 = sqrt(dot(v1, v1));
+    v1 = V3{v1.x / n1, v1.y / n1, v1.z / n1};
+    const V3 v2 = cross(r, v1);
+    double s, c;
+    sincos(angle, &s, &c);
+    return V3{v1.x * c + v2.x * s, v1.y * c + v2.y * s, v1.z * c + v2.z * s};
+}
+
+// source/basesources.py:158-277: p = dt e_mode e_const e_table p_mode p_const p_table sky ra dec
+template <typename PP, typename DRAW>
+MXB_DEV void op_generate(Photon& ph, PP p, const double* gprog, unsigned long long gid, DRAW draw, int s0, int s1,
+                         int s2, int s3, double& time, double& polangle) {
+    time = (double)gid * p[0];                       // np.arange(0, T, dt)[i]
+    if ((int)p[1] == 1) {
+        const double u0 = draw(s0), u1 = draw(s1);
+        ph.energy = arbitrary_pdf(gprog + (long long)p[3], u0, u1);
+    } else {
+        ph.energy = 1. * p[2];
+    }
+    const int pm = (int)p[4];
+    if (pm == 1) polangle = 0. + (kTwoPi - 0.) * draw(s2);      // np.random.uniform(0, 2 pi)
+    else if (pm == 2) {
+        const double u0 = draw(s2), u1 = draw(s3);
+        polangle = arbitrary_pdf(gprog + (long long)p[6], u0, u1);
+    } else polangle = 1. * p[5];
+    ph.prob = 1.;
+}
+
+// source/pointing.py:101-177 (+ :180-211 jitter): p = M[9] T[9] north[3] sigma
+template <typename PP>
+MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_deg, double polangle, double u_axis,
+                         double z_jitter) {
+    const double ra = ra_deg * (3.141592653589793 / 180.), dec = dec_deg * (3.141592653589793 / 180.);   // np.deg2rad
+    double sr, cr, sd, cd;
+    sincos(ra, &sr, &cr);
+    sincos(dec, &sd, &cd);
+    const V3 v{cd * cr, cd * sr, sd};
+    const V3 o{p[0] * v.x + p[1] * v.y + p[2] * v.z, p[3] * v.x + p[4] * v.y + p[5] * v.z,
+               p[6] * v.x + p[7] * v.y + p[8] * v.z};
+    const V3 m{-o.x, -o.y, -o.z};
+    const double nm = sqrt(dot(m, m));
+    const V3 d0{m.x / nm, m.y / nm, m.z / nm};
+    PP T = p + 9;
+    V3 d{T[0] * d0.x + T[1] * d0.y + T[2] * d0.z, T[3] * d0.x + T[4] * d0.y + T[5] * d0.z,
+         T[6] * d0.x + T[7] * d0.y + T[8] * d0.z};
+    const V3 north = ld3(p + 18);
+    const double proj = d.x * north.x + d.y * north.y + d.z * north.z;
+    V3 nin{north.x - d.x * proj, north.y - d.y * proj, north.z - d.z * proj};
+    const double nn = sqrt(dot(nin, nin));
+    nin = V3{nin.x / nn, nin.y / nn, nin.z / nn};
+    const V3 ein = cross(d, nin);
+    double sp, cp;
+    sincos(polangle, &sp, &cp);
+    V3 pol{cp * nin.x + sp * ein.x, cp * nin.y + sp * ein.y, cp * nin.z + sp * ein.z};
+    if ((flags & 1) && p[21] > 0.0) {
+        const double randang = u_axis * 2. * 3.141592653589793;
+        double sa, ca;
+        sincos(randang, &sa, &ca);
+        const V3 ax{0., sa, ca};
+        const double ang = 0. + p[21] * z_jitter;
+        d = axangle_rotate_T(ax, ang, d);
+        pol = axangle_rotate_T(ax, ang, pol);
+    }
+    ph.dir = d;
+    ph.pol = pol;
+    ph.unit = false;
+}
+
+// source/labSource.py:62-137: p = position[3] R[9] fractional_area
+template <typename PP>
+MXB_DEV void op_labcone(Photon& ph, PP p, double u_theta, double u_v, double polangle) {
+    const double theta = 0. + (kTwoPi - 0.) * u_theta;
+    const double v = 0. + (p[12] - 0.) * u_v;
+    const double phi = acos(1 - 2 * v);
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    const V3 d{ct * sp, st * sp, cp};
+    PP R = p + 3;
+    ph.dir = V3{R[0] * d.x + R[1] * d.y + R[2] * d.z, R[3] * d.x + R[4] * d.y + R[5] * d.z,
+                R[6] * d.x + R[7] * d.y + R[8] * d.z};
+    ph.pos = ld3(p);
+    ph.pol = polarization_vector(ph.dir, polangle);
+    ph.unit = false;
+}
+
+// source/labSource.py:13-59: p = pos4d rows 0..2 [12] sourcePos[3]
+template <typename PP>
+MXB_DEV void op_farlab(Photon& ph, PP p, double u_y, double u_z, double polangle) {
+    const double y = -1 + (1 - -1) * u_y, z = -1 + (1 - -1) * u_z;
+    ph.pos = V3{p[0] * 0. + p[1] * y + p[2] * z + p[3] * 1., p[4] * 0. + p[5] * y + p[6] * z + p[7] * 1.,
+                p[8] * 0. + p[9] * y + p[10] * z + p[11] * 1.};
+    ph.dir = V3{ph.pos.x - p[12], ph.pos.y - p[13], ph.pos.z - p[14]};
+    ph.pol = polarization_vector(ph.dir, polangle);
+    ph.unit = false;
+}
+
+// ---------------------------------------------------------------------------
 // Parallel containers: facet search with sequential ("last hit wins") semantics
 // (simulator.py:42-49 over a Parallel).  H: array header O[3] nbar[3] u[3] v[3]
 // u0 v0 inv_cell T2.

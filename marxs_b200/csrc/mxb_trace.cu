@@ -50,7 +50,8 @@ struct TraceParams {
     unsigned long long seed;
     unsigned long long* status;
     const double* src[11];   // core planes the photons are READ from (== cols.f64[0..10] in place)
-    int store_energy;        // out of place: energy has to be copied to the destination
+    int store_energy;        // out of place / born photons: energy has to be written to the destination
+    int born;                // header flag: the program creates the photons, nothing is read
     MxbColumns cols;
 };
 
@@ -191,7 +192,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
         ctx.i = i;
         ctx.active = i < P.n;
         Photon ph;
-        if (ctx.active) {
+        if (ctx.active && !P.born) {
             ph.pos = V3{P.src[0][i], P.src[1][i], P.src[2][i]};
             ph.dir = V3{P.src[3][i], P.src[4][i], P.src[5][i]};
             ph.pol = V3{P.src[6][i], P.src[7][i], P.src[8][i]};
@@ -358,6 +359,48 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     // fused detector image (chip pixel convention is 1-based: det_acis.py:33-34)
                     const long long idn = (long long)(B + row)[c.w15];
                     accumulate_image(hot, P.cols.f64[c.s0], gp + 6, idn, chipx - 1.0, chipy - 1.0, ph.prob);
+                }
+                break;
+            }
+            case MXB_OP_GENERATE: {
+                const OpCold& c = opc[pc];
+                double time = 0, polangle = 0;
+                if (ctx.active)
+                    op_generate(ph, pr, P.prog, (unsigned long long)(P.id0 + i), [&](int s) { return draw(ctx, s, 0); },
+                                c.s0, c.s1, c.w14, c.w15, time, polangle);
+                const int wm = store_mask(ctx, c.mode, true);
+                put(ctx, wm, 0, c.cp[0], true, time);
+                put(ctx, wm, 1, c.cp[1], true, polangle);
+                put(ctx, wm, 2, c.cp[2], true, pr[8]);
+                put(ctx, wm, 3, c.cp[3], true, pr[9]);
+                break;
+            }
+            case MXB_OP_POINTING: {
+                const OpCold& c = opc[pc];
+                if (ctx.active) {
+                    const MxbColumns& C = P.cols;
+                    double ua = 0, zj = 0;
+                    if (op.flags & 1) {
+                        ua = draw(ctx, c.s0, 0);
+                        if (pr[21] > 0.0) zj = draw(ctx, c.s1, 1);
+                    }
+                    op_pointing(ph, pr, op.flags, C.f64[c.c[0]][i], C.f64[c.c[1]][i], C.f64[c.c[2]][i], ua, zj);
+                }
+                break;
+            }
+            case MXB_OP_LABCONE: {
+                const OpCold& c = opc[pc];
+                if (ctx.active) {
+                    const double u0 = draw(ctx, c.s0, 0), u1 = draw(ctx, c.s1, 0);
+                    op_labcone(ph, pr, u0, u1, P.cols.f64[c.c[0]][i]);
+                }
+                break;
+            }
+            case MXB_OP_FARLAB: {
+                const OpCold& c = opc[pc];
+                if (ctx.active) {
+                    const double u0 = draw(ctx, c.s0, 0), u1 = draw(ctx, c.s1, 0);
+                    op_farlab(ph, pr, u0, u1, P.cols.f64[c.c[0]][i]);
                 }
                 break;
             }
@@ -694,8 +737,9 @@ int validate_program(const double* h, size_t words, int* n_ops, int* stage_words
 
 thread_local std::string g_kernel_info = "none";
 
-int launch_interp(const double* prog_dev, int n_ops, int stage_words, const double* const* src, const MxbColumns* cols,
-                  int64_t n, int64_t id0, uint64_t seed, unsigned long long* status_dev, cudaStream_t stream) {
+int launch_interp(const double* prog_dev, int n_ops, int stage_words, bool born, const double* const* src,
+                  const MxbColumns* cols, int64_t n, int64_t id0, uint64_t seed, unsigned long long* status_dev,
+                  cudaStream_t stream) {
     TraceParams P;
     P.prog = prog_dev;
     P.n_ops = n_ops;
@@ -710,6 +754,8 @@ int launch_interp(const double* prog_dev, int n_ops, int stage_words, const doub
         P.src[k] = src ? src[k] : cols->f64[k];
         if (k == MXB_COL_ENERGY && P.src[k] != cols->f64[k]) P.store_energy = 1;
     }
+    P.born = born ? 1 : 0;
+    if (born) P.store_energy = 1;
     const size_t stage_bytes = (size_t)stage_words * 8;
     const int grid = grid_for(n, kThreads, 1);
     if (stage_bytes <= (size_t)kMaxSmemStageBytes) {
@@ -751,7 +797,8 @@ int launch_trace(const double* prog_dev, const double* prog_host, size_t prog_wo
         if (mode == mxbjit::kForce || !unavailable) return fail(rc, err);
         // auto mode without NVRTC on this machine: the interpreter kernel runs the program
     }
-    return launch_interp(prog_dev, n_ops, stage_words, src, cols, n, id0, seed, status_dev, stream);
+    return launch_interp(prog_dev, n_ops, stage_words, ((int)prog_host[5] & 1) != 0, src, cols, n, id0, seed, status_dev,
+                         stream);
 }
 
 // cached staging state of mxb_trace_host (one per host thread)

@@ -28,7 +28,8 @@ class ACISChip(FlatDetector):
         theta = t['theta'][self.id_num]
         sh = t['scale'][self.id_num] * t['handedness'][self.id_num]
         ox, oy = t['origin'][self.id_num]
-        roll = np.deg2rad(lw.meta['ROLL_PNT'][0])
+        # the pointing may be part of the same program (source.observe): its meta is pending in meta_updates
+        roll = np.deg2rad(lw.meta_updates['ROLL_PNT'][0] if 'ROLL_PNT' in lw.meta_updates else lw.meta['ROLL_PNT'][0])
         glob = [NOMINAL_FOCALLENGTH, self.pixsize_in_rad, self.ODET[0], self.ODET[1], np.cos(roll), np.sin(roll)]
         s0 = -1
         if lw.image is not None:

@@ -31,7 +31,8 @@ CORE_F64 = ['pos_x', 'pos_y', 'pos_z', 'dir_x', 'dir_y', 'dir_z', 'pol_x', 'pol_
 
 OP = dict(END=0, PLANE=1, COMMIT=2, ARRAY_BEGIN=3, ARRAY_END=4, BAFFLE=5, LENS=6, RSCATTER=7,
           GSCATTER=8, FILTER=9, GRATING=10, DETPIX=11, ACIS=12, BREWSTER=13, MLEFF=14, APERTURE=15,
-          PROPAGATE=16, GFILTER=17, LOADHIT=18, QFACTOR=19, L2ABS=20, CYLINDER=21)
+          PROPAGATE=16, GFILTER=17, LOADHIT=18, QFACTOR=19, L2ABS=20, CYLINDER=21, GENERATE=22, POINTING=23,
+          LABCONE=24, FARLAB=25)
 SEL_ORDERSELECTOR, SEL_EFFFILE, SEL_INTERPTABLE = 1, 2, 3
 ARRAY_HEADER_WORDS = 24
 MAX_STAGE_BYTES = 200 * 1024
@@ -160,6 +161,8 @@ class Lowering:
         self.aux = OrderedDict()          # name -> device tensor reached through an f64 pointer slot
         self._no_fold = None
         self.last_order_col = None        # column written by the latest GRATING op of the current element stack
+        self.born = False                 # a source op creates the photons: header flag, no core planes are read
+        self.rel_fixups = []              # (word, base word, delta): word = value(base word) + delta at finish
         self.image = None                 # (tensor, sel_lo) of the detector array being lowered
 
     # ---- transactions (an element that turns out not to be fusable is rolled back) ----
@@ -215,6 +218,21 @@ class Lowering:
         self.fixups.append((off + index, len(self.big) - 1))
         self._dedupe[key] = off
         return off
+
+    def fixup_relative(self, word, base_word, delta):
+        """At finish: blob[word] = blob[base_word] + delta (second table inside one global block)."""
+        self.rel_fixups.append((int(word), int(base_word), int(delta)))
+
+    def input_col(self, name):
+        """f64 slot of a column an op READS (plain index, like LOADHIT's): it must exist already or be
+        created earlier in this program."""
+        if name not in self.f64_cols:
+            if name not in self.existing:
+                raise NotFusable('input column {0} does not exist'.format(name))
+            if len(self.f64_cols) >= _lib.MXB_MAX_F64_COLS:
+                raise NotFusable('too many output columns in one program')
+            self.f64_cols.append(name)
+        return self.f64_cols.index(name)
 
     # ---- draw slots -----------------------------------------------------------
     def slot(self, kind):
@@ -480,6 +498,9 @@ class Lowering:
             blob = np.concatenate([blob, t, np.zeros(len(t) % 2)])
         for word, idx in self.fixups:
             blob[word] = offs[idx]
+        for word, base, delta in self.rel_fixups:
+            blob[word] = blob[base] + delta
+        blob[5] = 1 if self.born else 0
         blob[0], blob[1], blob[2], blob[3], blob[4] = MXB_MAGIC, _lib.MXB_ABI_VERSION, len(self.ops), len(blob), stage_words
         for i, rec in enumerate(self.ops):
             w = HEADER_WORDS + OP_WORDS * i

@@ -1,0 +1,346 @@
+"""Sources (reference source/basesources.py, source/labSource.py) and pointing (source/pointing.py)
+as ops of the fused trace kernel (GENERATE, LABCONE, FARLAB, POINTING in include/mxb.h).
+
+Supported specifications (the rest raises, there is no CPU fallback): ``flux`` a number or
+Quantity (constant flux -> evenly spaced times, basesources.py:171-174); ``energy`` a number /
+Quantity [keV] or a table with ``energy`` (upper bin edges) and ``fluxdensity`` (basesources.py:191-197);
+``polarization`` None (unpolarised: uniform angle), an angle, or a table with ``angle`` and
+``probabilitydensity``.  Sky coordinates: (ra, dec) in degrees or an astropy SkyCoord."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from ..base import SimulationSequenceElement, _parse_position_keywords
+from ..photons import PhotonBatch
+from ..program import Lowering, NotFusable
+from .. import rng as _rng
+
+__all__ = ['Source', 'PointSource', 'LabPointSourceCone', 'FarLabPointSource', 'FixedPointing', 'JitterPointing',
+           'RandomArbitraryPdfTable', 'observe', 'SourceSpecificationError']
+
+
+class SourceSpecificationError(Exception):
+    pass
+
+
+def _val(x, unit=None):
+    """Plain float from a number or an astropy-like Quantity (converted to ``unit`` first)."""
+    if hasattr(x, 'to') and unit is not None:
+        import astropy.units as u
+        return float(x.to(getattr(u, unit) if isinstance(unit, str) else unit).value)
+    if hasattr(x, 'value'):
+        return float(x.value)
+    return float(x)
+
+
+def _radec(coords):
+    if hasattr(coords, 'ra') and hasattr(coords, 'dec'):
+        c = coords.icrs if hasattr(coords, 'icrs') else coords
+        return float(c.ra.deg), float(c.dec.deg)
+    ra, dec = coords
+    return float(ra), float(dec)
+
+
+class RandomArbitraryPdfTable:
+    """Device table of math/random.py:4-95 RandomArbitraryPdf (sort=True, randomize_in_bin=True):
+    n, cdf[n], sortindex[n], x[n], bin_width[n]."""
+
+    def __init__(self, x, pdf):
+        x, pdf = np.asarray(x, dtype=float), np.asarray(pdf, dtype=float)
+        if len(x) != len(pdf):
+            raise ValueError('x and pdf must have same number of elements.')
+        if not np.all(pdf >= 0):
+            raise ValueError('pdf cannot have negative elements.')
+        self.x = x
+        self.bin_width = np.hstack(([0], np.diff(x)))
+        if not np.all(self.bin_width >= 0):
+            raise ValueError('x must be input in increasing order.')
+        pdf = pdf * self.bin_width
+        self.sortindex = np.argsort(pdf)
+        self.cdf = np.cumsum(pdf[self.sortindex])
+
+    def table(self):
+        return np.concatenate([[len(self.x)], self.cdf, self.sortindex.astype(float), self.x, self.bin_width])
+
+
+def _column(tab, name):
+    col = tab[name]
+    return np.asarray(col.value if hasattr(col, 'value') else col, dtype=float)
+
+
+class Source(SimulationSequenceElement):
+    """Base class of all photon sources (reference basesources.py:85-277)."""
+
+    sky = False
+
+    def __init__(self, energy=1., flux=1., polarization=None, geomarea=1., **kwargs):
+        self.energy, self.flux, self.polarization = energy, flux, polarization
+        self.geomarea = 1 if geomarea is None else geomarea
+        super().__init__(**kwargs)
+
+    def __call__(self, *args, **kwargs):
+        return self.generate_photons(*args, **kwargs)
+
+    # ---- specification -> numbers ---------------------------------------------------------
+    def _rate(self):
+        if callable(self.flux):
+            raise SourceSpecificationError('callable flux (e.g. a Poisson process) is not supported on the device: '
+                                           'only a constant flux')
+        return _val(self.flux) * _val(self.geomarea)
+
+    def n_photons(self, exposuretime):
+        return len(np.arange(0, _val(exposuretime, 's'), 1. / self._rate()))
+
+    def _energy_spec(self):
+        e = self.energy
+        if callable(e):
+            raise SourceSpecificationError('callable energy is not supported on the device')
+        if hasattr(e, 'columns') or isinstance(e, dict):
+            x = _column(e, 'energy')
+            y = np.hstack(([0], _column(e, 'fluxdensity')[1:]))
+            return 1, 0., RandomArbitraryPdfTable(x, y).table()
+        return 0, _val(e, 'keV'), None
+
+    def _pol_spec(self):
+        p = self.polarization
+        if callable(p):
+            raise SourceSpecificationError('callable polarization is not supported on the device')
+        if p is None:
+            return 1, 0., None
+        if hasattr(p, 'columns') or isinstance(p, dict):
+            return 2, 0., RandomArbitraryPdfTable(_column(p, 'angle'), _column(p, 'probabilitydensity')).table()
+        return 0, _val(p, 'rad'), None
+
+    # ---- lowering ------------------------------------------------------------------------------
+    def _lower(self, lw):
+        """GENERATE op: time, energy, polangle, probability (+ ra, dec for sky sources)."""
+        if lw.ops:
+            raise NotFusable('a source must be the first element')
+        lw.born = True
+        e_mode, e_const, e_tab = self._energy_spec()
+        p_mode, p_const, p_tab = self._pol_spec()
+        vals = [1. / self._rate(), e_mode, e_const, -1., p_mode, p_const, -1., 1. if self.sky else 0.,
+                getattr(self, 'ra', 0.), getattr(self, 'dec', 0.)]
+        if e_tab is not None and p_tab is not None:
+            # two global tables: store them back to back and point both fields into the block
+            off = lw.params_with_table(vals, 3, np.concatenate([e_tab, p_tab]))
+            lw.fixup_relative(off + 6, off + 3, len(e_tab))
+        elif e_tab is not None:
+            off = lw.params_with_table(vals, 3, e_tab)
+        elif p_tab is not None:
+            off = lw.params_with_table(vals, 6, p_tab)
+        else:
+            off = lw.params(vals)
+        s = [-1, -1, -1, -1]
+        if e_mode == 1:
+            s[0], s[1] = lw.slot('uniform'), lw.slot('uniform')
+        if p_mode >= 1:
+            s[2] = lw.slot('uniform')
+        if p_mode == 2:
+            s[3] = lw.slot('uniform')
+        cols = [lw.fcol('time'), lw.fcol('polangle')]
+        if self.sky:
+            cols += [lw.fcol('ra'), lw.fcol('dec')]
+        lw.op('GENERATE', pg=off, cols=cols, s0=s[0], s1=s[1], w14=s[2], w15=s[3])
+
+    def _drop_after_birth(self):
+        return ('pos', 'dir', 'polarization')
+
+    def generate_photons(self, exposuretime, device=None, id0=0):
+        """Photon table born on the device (reference :234-277): columns time, energy, polangle,
+        probability (+ ra, dec / pos, dir, polarization depending on the source)."""
+        n = self.n_photons(exposuretime)
+        photons = _empty_batch(n, device, id0)
+        photons.meta['EXTNAME'] = 'EVENTS'
+        photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
+        _run_born([self], photons)
+        for c in self._drop_after_birth():
+            photons.remove_column(c)
+        return photons
+
+
+class AstroSource(Source):
+    sky = True
+
+    def __init__(self, **kwargs):
+        self.ra, self.dec = _radec(kwargs.pop('coords'))
+        super().__init__(**kwargs)
+
+
+class PointSource(AstroSource):
+    """Astrophysical point source (reference basesources.py:337-352)."""
+
+    def generate_photons(self, exposuretime, device=None, id0=0):
+        photons = super().generate_photons(exposuretime, device, id0)
+        photons.meta['COORDSYS'] = ('ICRS', 'Type of coordinate system')
+        return photons
+
+
+class LabPointSourceCone(Source):
+    """In-lab point source shining into a cone (reference labSource.py:62-137)."""
+
+    def __init__(self, position=[0, 0, 0], half_opening=np.pi, direction=[1., 0., 0.], **kwargs):
+        if (len(position) != 3) or (len(direction) != 3):
+            raise ValueError('Direction and position are expected in Euclidean coordinates.')
+        d = np.asanyarray(direction, dtype=float) / np.linalg.norm(direction)
+        self.dir = np.array([d[0], d[1], d[2], 0.])
+        self.position = np.array([position[0], position[1], position[2], 1.], dtype=float)
+        self.half_opening = half_opening
+        kwargs.setdefault('flux', 1.)
+        super().__init__(geomarea=None, **kwargs)
+
+    def _rotation(self):
+        from ..affines import axangle2mat
+        axis = np.cross(self.dir[:3], [0, 0, 1])
+        return axangle2mat(axis, -np.arccos(self.dir[2]))
+
+    def _lower(self, lw):
+        super()._lower(lw)
+        frac = 2 * np.pi * (1 - np.cos(self.half_opening)) / (4 * np.pi)
+        lw.op('LABCONE', pg=lw.params(np.concatenate([self.position[:3], self._rotation().ravel(), [frac]])),
+              cols=[lw.input_col('polangle')], s0=lw.slot('uniform'), s1=lw.slot('uniform'))
+
+    def _drop_after_birth(self):
+        return ()
+
+
+class FarLabPointSource(Source):
+    """Far in-lab point source seen through a rectangular aperture (reference labSource.py:13-59)."""
+
+    def __init__(self, sourcePos, **kwargs):
+        self.sourcePos = np.asarray(sourcePos, dtype=float)
+        self.pos4d = _parse_position_keywords(kwargs)
+        kwargs.setdefault('flux', 1.)
+        super().__init__(geomarea=None, **kwargs)
+
+    def _lower(self, lw):
+        super()._lower(lw)
+        lw.op('FARLAB', pg=lw.params(np.concatenate([self.pos4d[:3].ravel(), self.sourcePos[:3]])),
+              cols=[lw.input_col('polangle')], s0=lw.slot('uniform'), s1=lw.slot('uniform'))
+
+    def _drop_after_birth(self):
+        return ()
+
+
+# -----------------------------------------------------------------------------------------------
+# pointing
+# -----------------------------------------------------------------------------------------------
+def skyoffset_matrix(ra0, dec0, roll):
+    """ICRS cartesian -> SkyOffsetFrame(origin=(ra0, dec0), rotation=roll) cartesian (angles in rad):
+    R_x(-roll) R_y(-dec0) R_z(ra0) with passive rotations, as astropy's skyoffset frame does."""
+    def rot(angle, axis):
+        c, s = np.cos(angle), np.sin(angle)
+        i, j = {'x': (1, 2), 'y': (2, 0), 'z': (0, 1)}[axis]
+        R = np.eye(3)
+        R[i, i], R[j, j] = c, c
+        R[i, j], R[j, i] = s, -s
+        return R
+    return rot(-roll, 'x') @ rot(-dec0, 'y') @ rot(ra0, 'z')
+
+
+class FixedPointing(SimulationSequenceElement):
+    """Photon directions and polarization vectors from ra, dec, polangle for a fixed pointing
+    (reference pointing.py:45-177): x axis to the aimpoint, z axis North at roll 0."""
+
+    jitter = 0.
+
+    def __init__(self, **kwargs):
+        self.ra0, self.dec0 = _radec(kwargs.pop('coords'))
+        self.roll = _val(kwargs.pop('roll', 0.), 'rad')
+        self.reference_transform = np.asarray(kwargs.pop('reference_transform', np.eye(4)), dtype=float)
+        super().__init__(**kwargs)
+
+    def _params(self):
+        M = skyoffset_matrix(np.deg2rad(self.ra0), np.deg2rad(self.dec0), self.roll)
+        T = self.reference_transform[:3, :3]
+        ra, dec = np.deg2rad(0.), np.deg2rad(90.)
+        v = np.array([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)])
+        o = np.array([M[r, 0] * v[0] + M[r, 1] * v[1] + M[r, 2] * v[2] for r in range(3)])
+        north = np.array([T[r, 0] * o[0] + T[r, 1] * o[1] + T[r, 2] * o[2] for r in range(3)])
+        return np.concatenate([M.ravel(), T.ravel(), north, [self.jitter]])
+
+    def _lower(self, lw):
+        jit = isinstance(self, JitterPointing)
+        lw.op('POINTING', flags=1 if jit else 0, pg=lw.params(self._params()),
+              cols=[lw.input_col('ra'), lw.input_col('dec'), lw.input_col('polangle')],
+              s0=lw.slot('uniform') if jit else -1, s1=lw.slot('normal') if jit else -1)
+        lw.creates_core = True
+        lw.meta_updates['RA_PNT'] = (self.ra0, '[deg] Pointing RA')
+        lw.meta_updates['DEC_PNT'] = (self.dec0, '[deg] Pointing Dec')
+        lw.meta_updates['ROLL_PNT'] = (np.rad2deg(self.roll), '[deg] Pointing Roll')
+        lw.meta_updates['RA_NOM'] = (self.ra0, '[deg] Nominal Pointing RA')
+        lw.meta_updates['DEC_NOM'] = (self.dec0, '[deg] Nominal Pointing Dec')
+        lw.meta_updates['ROLL_NOM'] = (np.rad2deg(self.roll), '[deg] Nominal Pointing Roll')
+
+    def __call__(self, photons):
+        n = len(photons)
+        created = []
+        for name in ('pos', 'dir', 'polarization'):
+            if name not in photons:
+                t = photons.new_column(name, torch.float64, vector=True, n=n)
+                t[3] = 1. if name == 'pos' else 0.
+                t[:3] = float('nan') if name == 'pos' else 0.
+                created.append(name)
+        lw = Lowering(photons.colnames, meta=photons.meta)
+        self._lower(lw)
+        prog = lw.finish()
+        draws = _rng.take_injected(len(prog.slot_kinds))
+        prog.run(photons, draws=draws, seed=_rng.next_launch_seed(), id0=getattr(photons, 'id0', 0))
+        if 'pos' in created:
+            photons.remove_column('pos')        # the reference adds pos in the aperture (aperture.py:19-27)
+        return photons
+
+
+class JitterPointing(FixedPointing):
+    """FixedPointing plus uncorrelated Gaussian pointing jitter (reference pointing.py:180-211)."""
+
+    def __init__(self, **kwargs):
+        self.jitter = abs(_val(kwargs.pop('jitter'), 'rad'))
+        super().__init__(**kwargs)
+
+
+# -----------------------------------------------------------------------------------------------
+def _empty_batch(n, device, id0):
+    photons = PhotonBatch(device=device)
+    for name in ('pos', 'dir', 'polarization'):
+        t = photons.new_column(name, torch.float64, vector=True, n=n)
+        t[3] = 1. if name == 'pos' else 0.
+    photons.new_column('energy', torch.float64, n=n)
+    photons.new_column('probability', torch.float64, n=n)
+    photons.id0 = id0
+    return photons
+
+
+def _run_born(elements, photons, check=True):
+    lw = Lowering([], meta=photons.meta)
+    for e in elements:
+        e._lower(lw)
+    prog = lw.finish()
+    draws = _rng.take_injected(len(prog.slot_kinds))
+    prog.run(photons, draws=draws, seed=_rng.next_launch_seed(), id0=getattr(photons, 'id0', 0), check=check)
+    return prog
+
+
+def observe(source, pointing, elements, exposuretime, device=None, id0=0, n=None, check=True):
+    """One observation as ONE kernel launch: source -> pointing -> elements (aperture, mirror, gratings,
+    detectors ...) lowered into a single born-on-device program.  ``pointing`` may be None for lab
+    sources.  ``n`` overrides the photon count (e.g. the size of this rank's shard; ``id0`` is then the
+    global index of its first photon).  Falls back to the reference call sequence when an element
+    cannot be fused."""
+    from ..simulator import _lowerable, Sequence
+    chain = [source] + ([pointing] if pointing is not None else []) + list(elements)
+    n_tot = source.n_photons(exposuretime) if n is None else int(n)
+    photons = _empty_batch(n_tot, device, id0)
+    photons.meta['EXTNAME'] = 'EVENTS'
+    photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
+    if all(_lowerable(e) or isinstance(e, (Source, FixedPointing)) for e in chain):
+        try:
+            _run_born(chain, photons, check=check)
+            return photons
+        except NotFusable:
+            pass
+    photons = source.generate_photons(exposuretime, device=device, id0=id0)
+    if pointing is not None:
+        photons = pointing(photons)
+    return Sequence(elements=list(elements))(photons)

@@ -114,3 +114,20 @@ def test_malformed_program_is_rejected():
     lib = _lib.load(False)
     n = lib.mxb_jit_source(bad.ctypes.data, bad.size, ctypes.byref(cols), None, 0)
     assert n == -5 and b'outside the blob' in lib.mxb_last_error()
+
+
+def test_born_program_compiles():
+    """source -> pointing -> aperture -> detector: header flag 'born', no loads of the core planes."""
+    from marxs_b200 import source
+    src = source.PointSource(coords=(30., 10.), flux=100., energy={'energy': np.array([0.3, 1., 2.]), 'fluxdensity': np.array([0., 1., 2.])})
+    pnt = source.JitterPointing(coords=(30., 10.), jitter=1e-6)
+    prog = lower([src, pnt] + c1()[:1] + c1()[2:], existing=[])
+    assert prog.blob[5] == 1 and prog.slot_kinds == ['uniform', 'uniform', 'uniform', 'uniform', 'normal', 'uniform', 'uniform']
+    cols = fake_columns(prog)
+    text = _lib.jit_source(prog, cols)
+    assert 'op_generate(' in text and 'op_pointing(' in text and 'pipe_load(' not in text
+    lib = _lib.load(False)
+    n = lib.mxb_jit_compile(prog.blob.ctypes.data, prog.blob.size, ctypes.byref(cols))
+    if n < 0 and b'NVRTC unavailable' in lib.mxb_last_error():
+        pytest.skip('no NVRTC on this host')
+    assert n > 10000, lib.mxb_last_error()

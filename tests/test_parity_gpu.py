@@ -835,6 +835,105 @@ def test_cylinder_golden(mode, tag):
     _check_golden(out, g, tag + '_')
 
 
+def test_lab_sources_golden(mode):
+    """LabPointSourceCone (tabulated spectrum, random polarization angle) and FarLabPointSource born on
+    the device against the REFERENCE's output (tests/golden/sources.npz, injected uniforms)."""
+    mb = _mb()
+    from marxs_b200 import source
+    g = load('sources')
+    spec = {'energy': g['pdf_x'], 'fluxdensity': g['pdf_pdf']}
+    cone = source.LabPointSourceCone(position=[200., 3., -2.], direction=[-1., 0.2, 0.1], half_opening=0.02,
+                                     flux=100., energy=spec)
+    with mb.inject_draws([g['cone_draw{0}'.format(k)] for k in range(5)]):
+        p = cone.generate_photons(10., device='cuda')
+    out = p.to_numpy()
+    assert set(out) == {'time', 'energy', 'polangle', 'probability', 'pos', 'dir', 'polarization'}
+    for c in out:
+        np.testing.assert_allclose(out[c], g['cone_' + c], rtol=1e-12, atol=1e-13, err_msg=c)
+    far = source.FarLabPointSource([500., 20., -30.], position=[50., 1., 2.], zoom=[1., 4., 7.], flux=100.,
+                                   energy=1.5, polarization=0.7)
+    with mb.inject_draws([g['far_draw0'], g['far_draw1']]):
+        out = far.generate_photons(10., device='cuda').to_numpy()
+    for c in out:
+        np.testing.assert_allclose(out[c], g['far_' + c], rtol=1e-12, atol=1e-13, err_msg=c)
+
+
+def test_pointing_vs_oracle(mode):
+    """PointSource + FixedPointing / JitterPointing on the device against the oracle (which the
+    reference's own test_pointing.py known answers pin), plus those known answers directly."""
+    mb = _mb()
+    from marxs_b200 import source
+    xyz2zxy = np.array([[0., 0, 1, 0], [1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1]]).T
+    ph = source.PointSource(coords=(12., 34.)).generate_photons(5., device='cuda')
+    assert ph.colnames == ['energy', 'probability', 'time', 'polangle', 'ra', 'dec'] or set(ph.colnames) == {
+        'time', 'energy', 'polangle', 'probability', 'ra', 'dec'}
+    px = source.FixedPointing(coords=(12., 34.))(ph.copy()).to_numpy()
+    assert np.allclose(px['dir'][:, 0], -1.) and np.allclose(px['dir'][:, 1:], 0) and 'pos' not in px
+    pz = source.FixedPointing(coords=(12., 34.), reference_transform=xyz2zxy)(ph.copy()).to_numpy()
+    assert np.allclose(pz['dir'][:, 2], -1.) and np.allclose(pz['dir'][:, :2], 0)
+    ph = source.PointSource(coords=(187.4, 0.)).generate_photons(5., device='cuda')
+    ph['polangle'] = np.deg2rad(np.array([0., 90., 180., 270., 45.]))
+    px = source.FixedPointing(coords=(187.4, 0.))(ph.copy()).to_numpy()
+    for k, want in enumerate([[0, 0, 1, 0], [0, 1, 0, 0], [0, 0, -1, 0], [0, -1, 0, 0], [0, 2 ** -0.5, 2 ** -0.5, 0]]):
+        assert np.allclose(px['polarization'][k], want), k
+    # random sky positions, roll, reference transform, jitter: against the oracle
+    rng = np.random.default_rng(SEED + 51)
+    n = 30000
+    tab = mo.PhotonTable(ra=rng.uniform(0, 360, n), dec=np.rad2deg(np.arcsin(rng.uniform(-1, 1, n))),
+                         time=np.arange(n, dtype=float), polangle=rng.uniform(0, 2 * np.pi, n),
+                         energy=np.ones(n), probability=np.ones(n))
+    T = np.eye(4)
+    T[:3, :3] = rand_pos4d(rng, zoom=(1., 1., 1.))[:3, :3]
+    kw = dict(coords=(25., -10.), roll=0.3, reference_transform=T)
+    want = mo.FixedPointing(**kw)(tab.copy())
+    got = source.FixedPointing(**kw)(mb.PhotonBatch(tab, device='cuda')).to_numpy()
+    for c in ('dir', 'polarization'):
+        np.testing.assert_allclose(got[c], want[c], rtol=1e-12, atol=1e-12, err_msg=c)
+    sig = np.deg2rad(1. / 3600.)
+    oj = mo.JitterPointing(jitter=sig, **kw)
+    oj.slots = [0, 1]
+    draws = [rng.random(n), rng.standard_normal(n)]
+    want = oj(tab.copy(), mo.Draws(draws))
+    with mb.inject_draws(draws):
+        b = source.JitterPointing(jitter=sig, **kw)(mb.PhotonBatch(tab, device='cuda'))
+    got = b.to_numpy()
+    for c in ('dir', 'polarization'):
+        np.testing.assert_allclose(got[c], want[c], rtol=1e-12, atol=1e-12, err_msg=c)
+    assert b.meta['ROLL_PNT'][0] == np.rad2deg(0.3)
+
+
+def test_observe_is_one_launch():
+    """source -> pointing -> aperture -> HRMA -> HETG -> ACIS as ONE born-on-device program equals the
+    reference-style call sequence (same injected draws), and nothing is read from the input planes."""
+    mb = _mb()
+    from marxs_b200 import source, simulator, _lib
+    from marxs_b200.missions import chandra
+    rng = np.random.default_rng(SEED + 52)
+    src = source.PointSource(coords=(30., 10.), flux=2000., energy={'energy': np.array([0.3, 0.5, 1., 2., 4., 8.]),
+                                                                      'fluxdensity': np.array([0., 5., 3., 2., 1., .5])})
+    pnt = source.JitterPointing(coords=(30., 10.), jitter=np.deg2rad(0.2 / 3600.))
+    elements = [chandra.Aperture(), chandra.HRMA(), chandra.HETG(),
+                chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])]
+    n = src.n_photons(10.)
+    assert n == 20000
+    # slots: energy (2), polangle (1), jitter (2), aperture id + xy (3), HRMA scatter (2), HETG order (1)
+    draws = [rng.random(n), rng.random(n), rng.random(n), rng.random(n), rng.standard_normal(n),
+             rng.integers(0, 4, n).astype(float), rng.random(n), rng.random(n),
+             rng.standard_normal(n), rng.standard_normal(n), rng.random(n)]
+    with mb.inject_draws(draws):
+        fused = source.observe(src, pnt, elements, 10., device='cuda')
+    assert _lib.load().mxb_jit_info().startswith(b'jit ')
+    with mb.inject_draws(draws):
+        p = src.generate_photons(10., device='cuda')
+        p = pnt(p)
+        seq = simulator.Sequence(elements=elements)(p)
+    a, b = fused.to_numpy(), seq.to_numpy()
+    assert set(a) == set(b)
+    assert (a['CCD_ID'] >= 0).mean() > 0.5
+    for c in a:
+        assert np.array_equal(a[c], b[c], equal_nan=True), c
+
+
 def test_event_compaction():
     """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
     mb = _mb()
