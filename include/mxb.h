@@ -148,14 +148,17 @@ typedef struct MxbColumns {
 /* selector kinds (first word of the selector block) */
 #define MXB_SEL_ORDERSELECTOR 1  /* grating.py:12-57:  n, psum, cdf[n], orders[n]                                                   */
 #define MXB_SEL_EFFFILE       2  /* grating.py:60-96:  nE, nO, energy[nE], totalprob[nE], orders[nO], cumprob[nE*nO]                 */
-#define MXB_SEL_INTERPTABLE   3  /* mitsnl/catgrating.py:63-144 (k=1): nw, nt, no, table_off (global), wave[nw], theta[nt], orders[no] */
+#define MXB_SEL_INTERPTABLE   3  /* mitsnl/catgrating.py:63-144 (k=1): nw, nt, no, table_off (global), wave[nw], theta[nt], orders[no];
+                                    table: prob[nw][nt][no], then cumsum(prob, order axis)[nw][nt][no]                            */
 
 /* ARRAY_BEGIN: integer fields live in the op words
  *   c0 F (facets)  c1 row stride (words)  c2 rows offset  c3 mode (0 brute force, 1 culling grid)
  *   c4 nu  c5 nv  c6 cell_start offset (packed int32[nu*nv+1])  c7 candidate offset (packed int32)
  *   s0 n_init  s1 offset of packed int32 init column refs (f64 index, or -(i64 index)-2)
- * pg -> 24 doubles: O[3] reference point, nbar[3], u[3], v[3], u0, v0, inv_cell,
+ * pg -> 24 doubles: O[3] reference point, nbar[3], u[3], v[3], u0, v0, inv_cell, T2, Hs:
  *                   T2 = (margin / (3 H))^2 : cone bound on tan^2(theta) for which the grid is conservative
+ *                   Hs : half thickness of the slab |h| <= Hs around the reference plane that contains every
+ *                   facet point (steep rays scan the cells under their footprint inside the slab)
  * facet row: geom[14], per-layer params, id_num; rows are `stride` words apart.
  */
 #define MXB_ARRAY_HEADER_WORDS 24

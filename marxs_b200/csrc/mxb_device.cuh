@@ -12,8 +12,32 @@
 #endif
 
 #define MXB_DEV __device__ __forceinline__
+// -DMXB_SHARE_CODE turns parallel transport / Rodrigues rotation into real functions (one copy, called)
+// for very large programs; measured slower on C3 (r01: 5.9 -> 6.9 ms), so it is off by default.
+#ifdef MXB_SHARE_CODE
+#define MXB_DEV_BIG __device__ __noinline__
+#else
+#define MXB_DEV_BIG __device__ __forceinline__
+#endif
 
 namespace mxb {
+
+// libm routines are 50-300 instructions each once inlined (argument reduction, slow paths) and a fused
+// program uses them at many sites.  -DMXB_SHARE_LIBM makes them one shared copy each; measured on C2 / C3
+// (r01) the calls cost 1-3 % more than the instruction-cache pressure they remove, so inline is the default.
+#ifdef MXB_SHARE_LIBM
+#define MXB_LIBM __device__ __noinline__
+#else
+#define MXB_LIBM __device__ __forceinline__     // measured: calls in the hot loop cost more than the code they save
+#endif
+MXB_LIBM double m_acos(double x) { return acos(x); }
+MXB_LIBM double m_asin(double x) { return asin(x); }
+MXB_LIBM double m_sin(double x) { return sin(x); }
+MXB_LIBM double m_log(double x) { return log(x); }
+MXB_LIBM double m_exp(double x) { return exp(x); }
+MXB_LIBM double m_pow(double x, double y) { return pow(x, y); }
+MXB_LIBM double m_atan2(double y, double x) { return atan2(y, x); }
+MXB_LIBM void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 
 constexpr double kEnergy2Wave = 1.2398419292004202e-06;  // marxs/__init__.py:14 (keV -> mm)
 constexpr double kHcKevNm = 1.2398419843320026;          // astropy u.spectral(): keV -> nm
@@ -91,7 +115,7 @@ MXB_DEV void sincos_small(double x, double* s, double* c) {
         return;
     }
 #endif
-    sincos(x, s, c);
+    m_sincos(x, s, c);
 }
 
 MXB_DEV double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }  // NaN propagates like np.clip
@@ -142,8 +166,8 @@ MXB_DEV V3 normalize_unless(bool unit, const V3& a) {
 // ---------------------------------------------------------------------------
 // math/polarization.py:90-170 parallel_transport (identity when |d1 x d2| <= 1e-8)
 // ---------------------------------------------------------------------------
-MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol, bool old_unit = false,
-                              bool new_unit = false) {
+MXB_DEV_BIG V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol, bool old_unit = false,
+                                  bool new_unit = false) {
     const V3 d1 = normalize_unless(old_unit, dir_old);
     const V3 d2 = normalize_unless(new_unit, dir_new);
     V3 s = cross(d1, d2);
@@ -165,7 +189,7 @@ MXB_DEV V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& po
 }
 
 // math/rotations.py:50-87 axangle2mat applied TRANSPOSED (scatter.py:60,68)
-MXB_DEV V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
+MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
     const V3 a = normalize(axis);  // axes / np.linalg.norm(axes): true division in strict build
     double s, c;
     sincos_small(angle, &s, &c);
@@ -232,7 +256,8 @@ MXB_DEV double u01_from_bits(uint32_t hi, uint32_t lo) {
     return (double)(b >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
 }
 
-// kind 0: uniform [0,1); kind 1: standard normal (Box-Muller)
+// kind 0: uniform [0,1); kind 1: standard normal (Box-Muller; the fast build evaluates it with the fp32
+// SFU intrinsics like device_draw_normal_pair below, the extreme tail and the strict build in fp64)
 MXB_DEV double device_draw(uint64_t seed, uint64_t photon_id, int slot, int kind) {
     uint32_t r[4];
     philox4x32_10((uint32_t)photon_id, (uint32_t)(photon_id >> 32), (uint32_t)slot, 0u,
@@ -240,7 +265,16 @@ MXB_DEV double device_draw(uint64_t seed, uint64_t photon_id, int slot, int kind
     const double u1 = u01_from_bits(r[0], r[1]);
     if (kind == 0) return u1;
     const double u2 = u01_from_bits(r[2], r[3]);
-    return sqrt(-2.0 * log(1.0 - u1)) * cos(kTwoPi * u2);
+    const double v = 1.0 - u1;
+#ifdef MXB_FAST
+    if (v > 9.5367431640625e-07) {
+        const float rad = sqrtf(-2.0f * __logf((float)v));
+        return (double)(rad * __cosf(6.2831853f * ((float)u2 - 0.5f)));
+    }
+#endif
+    double s, c;
+    m_sincos(kTwoPi * u2, &s, &c);
+    return sqrt(-2.0 * m_log(v)) * c;
 }
 
 // two independent standard normals from ONE Philox call (both Box-Muller branches).
@@ -264,9 +298,9 @@ MXB_DEV void device_draw_normal_pair(uint64_t seed, uint64_t photon_id, int slot
         return;
     }
 #endif
-    const double rad = sqrt(-2.0 * log(v));
+    const double rad = sqrt(-2.0 * m_log(v));
     double s, c;
-    sincos(kTwoPi * u2, &s, &c);
+    m_sincos(kTwoPi * u2, &s, &c);
     z0 = rad * c;
     z1 = rad * s;
 }

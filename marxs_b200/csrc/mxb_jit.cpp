@@ -512,7 +512,7 @@ struct Gen {
         if (nF < 0 || stride < 14 || !range_ok(rows_off, (long long)std::max(nF, 1) * stride)) return fail("array rows outside the blob");
         if (mode == 1 && (!range_ok(cs_off, ((long long)nu * nv + 2) / 2) || !range_ok(cand_off, 0))) return fail("culling grid outside the blob");
         need_blob = true;
-        const std::string H = S(o.pg, 16);
+        const std::string H = S(o.pg, 17);
         out("            // ---- ops %d..%d: array of %d facets, stride %d, mode %d (%d x %d cells)", pc, end_pc, nF, stride, mode, nu, nv);
         out("            {");
         out("            ArrayIter it;");
@@ -520,7 +520,8 @@ struct Gen {
         out("            bool init_round = true;");
         out("            array_open(it, %s, (B + %d), %d, %d, %d, %d, ph, active, st_sm);", H.c_str(), mode == 1 ? cs_off : 0, nF, mode, nu, nv);
         out("            for (;;) {");
-        out("            const bool found = array_search(it, B, (B + %d), %d, %d, ph, row);", mode == 1 ? cand_off : 0, rows_off, stride);
+        out("            const bool found = array_search(it, B, %s, (B + %d), (B + %d), %d, %d, %d, %d, %d, ph, row);", H.c_str(),
+            mode == 1 ? cs_off : 0, mode == 1 ? cand_off : 0, rows_off, stride, nF, nu, nv);
         out("            ph.hit = found;");
         out("            nhit += found ? 1 : 0;");
         out("            const unsigned m = __ballot_sync(0xffffffffu, found);");
@@ -565,7 +566,7 @@ struct Gen {
 
     bool run() {
         if (!parse()) return false;
-        staged = (size_t)stage_words * 8 <= 200 * 1024;
+        staged = true;   // decided after the body is known (needs the static shared memory of the hot-pixel cache)
         geom = "SRef{P.s}";
         for (int pc = 0; pc < n_ops; ++pc) {
             const Op& o = ops[pc];
@@ -575,6 +576,8 @@ struct Gen {
             else if (!gen_op(pc)) return false;
         }
         if (!err.empty()) return false;
+        // one CTA per SM may use 227 KB of dynamic shared memory minus the kernel's static arrays
+        staged = (size_t)stage_words * 8 <= (size_t)(232448 - 1024 - (need_hot ? 8192 : 0));
         keyi(need_blob ? 1 : 0);
         if (!emit) return true;
         std::string body;
@@ -838,6 +841,16 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
     opts.push_back("-DJIT_THREADS=" + std::to_string(env_int("MXB_JIT_THREADS", 640)));
     opts.push_back("-DJIT_MINBLOCKS=" + std::to_string(env_int("MXB_JIT_MINBLOCKS", 1)));
     opts.push_back("-DJIT_PREFETCH=" + std::to_string(env_int("MXB_JIT_PREFETCH", 1)));
+    if (const char* extra = getenv("MXB_JIT_DEFINES")) {      // experiments: space separated -D options
+        std::string e(extra);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t sp = e.find(' ', pos);
+            if (sp == std::string::npos) sp = e.size();
+            if (sp > pos) opts.push_back(e.substr(pos, sp - pos));
+            pos = sp + 1;
+        }
+    }
     if (env_int("MXB_JIT_MAXREG", 0) > 0) opts.push_back("--maxrregcount=" + std::to_string(env_int("MXB_JIT_MAXREG", 0)));
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -861,11 +874,13 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
 }
 
 std::string options_tag(bool fast_build) {
-    char b[128];
+    char b[160];
     snprintf(b, sizeof(b), "%s t%d b%d r%d p%d f%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 640),
              env_int("MXB_JIT_MINBLOCKS", 1), env_int("MXB_JIT_MAXREG", 0), env_int("MXB_JIT_PIPE", 0),
              env_int("MXB_JIT_PREFETCH", 1));
-    return b;
+    std::string tag(b);
+    if (const char* extra = getenv("MXB_JIT_DEFINES")) tag += std::string(" ") + extra;
+    return tag;
 }
 
 // source -> cubin through the disk cache

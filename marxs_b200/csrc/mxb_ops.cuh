@@ -162,9 +162,12 @@ MXB_DEV void st_global(long long* p, long long v) {
     asm volatile("st.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// status counters are bumped on rare paths from many sites: one shared routine
+MXB_DEV void count_status(unsigned long long* st_sm, int which) { atomicAdd(&st_sm[which], 1ULL); }
+
 // optics/base.py:43-47: probability factors multiply and must lie in [0,1]
 MXB_DEV void mul_prob(unsigned long long* st_sm, Photon& ph, double f) {
-    if (f < 0.0 || f > 1.0) atomicAdd(&st_sm[MXB_ST_PROB_RANGE], 1ULL);
+    if (f < 0.0 || f > 1.0) count_status(st_sm, MXB_ST_PROB_RANGE);
     ph.prob *= f;
 }
 
@@ -289,7 +292,7 @@ MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, doubl
     const V3 perp = cross(pdir, guess);
     if (flags & 1) {   // L2Diffraction (mitsnl/catgrating.py:280-285): Airy-disk sigma of the L2 mesh, p[0] = innerfree
         const double wave = div(kHcKevNm * 1e-6, ph.energy);   // astropy u.spectral(): keV -> mm
-        const double sigma = (1.22 * 0.4) * asin(div(wave, p[0]));
+        const double sigma = (1.22 * 0.4) * m_asin(div(wave, p[0]));
         ang = zn * sigma;
     } else {
         ang = p[0] * zn;
@@ -310,7 +313,7 @@ MXB_DEV double filter_value(unsigned long long* st_sm, PP p, double energy, int 
     PP xp = p + 1;
     PP fp = p + 1 + n;
     if ((flags & 1) && (energy < xp[0] || energy > xp[n - 1]))
-        atomicAdd(&st_sm[MXB_ST_FILTER_BOUNDS], 1ULL);
+        count_status(st_sm, MXB_ST_FILTER_BOUNDS);
     return interp_clamped(xp, fp, n, energy);
 }
 
@@ -370,21 +373,67 @@ MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy
         const double* t10 = t00 + (long long)nt * no;
         const double* t01 = t00 + no;
         const double* t11 = t10 + no;
+#ifdef MXB_FAST
+        // Fast build: interpolation is linear, so the interpolated running sum over orders equals the
+        // running sum of the interpolated efficiencies up to rounding.  With the cumulative table the
+        // total is ONE bilinear lookup and the order a bisection over k (5 lookups for 28 orders)
+        // instead of 2 x 28 lookups; the order can only differ from the reference when u sits within
+        // ~1e-16 of a bin boundary.
+        {
+            const double* c00 = t00 + (long long)nw * nt * no;
+            const double* c10 = c00 + (long long)nt * no;
+            const double* c01 = c00 + no;
+            const double* c11 = c10 + no;
+            auto cum = [&](int k) {
+                const double a00 = __ldg(c00 + k), a10 = __ldg(c10 + k), a01 = __ldg(c01 + k), a11 = __ldg(c11 + k);
+                const double f0 = a00 + tx * (a10 - a00);
+                const double f1 = a01 + tx * (a11 - a01);
+                return f0 + ty * (f1 - f0);
+            };
+            const double total = cum(no - 1);
+            psel = total;
+            int lo = 0, hi = no - 1;
+            if (!(total / total > u)) {
+                lo = 0;                         // no cumulative fraction exceeds u: np.argmax of all-False is 0
+            } else {
+                const double rt = fast_rcp(total);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cum(mid) * rt > u) hi = mid; else lo = mid + 1;
+                }
+            }
+            return ord[lo];
+        }
+#endif
+        // first pass: interpolated efficiency of every order (kept in local memory for the second pass
+        // when there are at most 32 orders) and their sum; second pass: first order whose cumulative
+        // fraction exceeds u
+        constexpr int kMaxCached = 32;
+        double fv[kMaxCached];
+        const bool cached = no <= kMaxCached;
         double total = 0.0;
         for (int k = 0; k < no; ++k) {
             const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
             const double f0 = a00 + tx * (a10 - a00);
             const double f1 = a01 + tx * (a11 - a01);
-            total = total + (f0 + ty * (f1 - f0));
+            const double f = f0 + ty * (f1 - f0);
+            if (cached) fv[k] = f;
+            total = total + f;
         }
         psel = total;
         double run = 0.0;
         int oi = 0;
         for (int k = 0; k < no; ++k) {
-            const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
-            const double f0 = a00 + tx * (a10 - a00);
-            const double f1 = a01 + tx * (a11 - a01);
-            run = run + (f0 + ty * (f1 - f0));
+            double f;
+            if (cached) {
+                f = fv[k];
+            } else {
+                const double a00 = __ldg(t00 + k), a10 = __ldg(t10 + k), a01 = __ldg(t01 + k), a11 = __ldg(t11 + k);
+                const double f0 = a00 + tx * (a10 - a00);
+                const double f1 = a01 + tx * (a11 - a01);
+                f = f0 + ty * (f1 - f0);
+            }
+            run = run + f;
             if (run / total > u) { oi = k; break; }   // argmax(cumprob > u): first True, 0 if none
         }
         return ord[oi];
@@ -401,7 +450,7 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
     const double wave = div(kEnergy2Wave, ph.energy);
     const double p_l = dot(pn, l);
     const V3 pp = normalize(V3{pn.x - p_l * l.x, pn.y - p_l * l.y, pn.z - p_l * l.z});
-    blaze = acos(clip01(fabs(dot(pp, n))));
+    blaze = m_acos(clip01(fabs(dot(pp, n))));
     if (flags & 4) blaze = blaze + (p[7] + ph.l0 * p[8]);  // NonParallelCATGrating blaze_angle_modifier
     double psel;
     order = select(ph.energy, blaze, psel);
@@ -434,7 +483,7 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
 // mitsnl/catgrating.py:147-161  params: factor
 template <typename PP>
 MXB_DEV void op_qfactor(unsigned long long* st_sm, Photon& ph, PP p) {
-    mul_prob(st_sm, ph, pow(p[0], ph.last_order * ph.last_order));
+    mul_prob(st_sm, ph, m_pow(p[0], ph.last_order * ph.last_order));
 }
 
 // mitsnl/catgrating.py:222-259  params: openfraction, bardepth * innerfree, totalarea ; n = e_x of the geometry
@@ -442,8 +491,8 @@ template <typename PP, typename GP>
 MXB_DEV void op_l2abs(unsigned long long* st_sm, Photon& ph, PP p, GP geom) {
     const V3 p3 = normalize_unless(ph.unit, ph.dir);
     const V3 en = ld3(geom + 3);
-    const double angle = acos(fabs(dot(p3, en)));   // no clip in the reference: NaN above 1
-    mul_prob(st_sm, ph, p[0] - div(p[1] * sin(angle), p[2]));
+    const double angle = m_acos(fabs(dot(p3, en)));   // no clip in the reference: NaN above 1
+    mul_prob(st_sm, ph, p[0] - div(p[1] * m_sin(angle), p[2]));
 }
 
 // multiLayerMirror.py:44-91  params: Pinv[9] P[9] ex[3]
@@ -464,7 +513,7 @@ MXB_DEV void op_brewster(unsigned long long* st_sm, Photon& ph, PP p) {
     const double pvs = dot(ph.pol, v_s), pvp = dot(ph.pol, v_p);
     const double Es2 = 1. * (pvs * pvs), Ep2 = 0. * (pvp * pvp);
     const double inten = Es2 + Ep2;
-    if (inten > 1.001) atomicAdd(&st_sm[MXB_ST_INTENSITY], 1ULL);
+    if (inten > 1.001) count_status(st_sm, MXB_ST_INTENSITY);
     const V3 nvp = cross(nd, v_s);
     const V3 np_{-Es2 * v_s.x + Ep2 * nvp.x, -Es2 * v_s.y + Ep2 * nvp.y, -Es2 * v_s.z + Ep2 * nvp.z};
     const double nn = sqrt(dot(np_, np_));
@@ -495,7 +544,7 @@ MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
     double refl = 0.0;
     if (c2 != 0.0) {
         const double dw = wavelength - peak_w;
-        refl = max_refl * exp(-(dw * dw) / (2 * c2));
+        refl = max_refl * m_exp(-(dw * dw) / (2 * c2));
     }
     mul_prob(st_sm, ph, refl / 100);
 }
@@ -540,7 +589,7 @@ MXB_DEV bool cylinder_intersect(P g, const V3& pos, const V3& dir, V3& ip, doubl
     const double a1 = (-b + sq) / denom, a2 = (-b - sq) / denom;
     const double x1 = x + a1 * dl[0], y1 = y + a1 * dl[1], z1 = z + a1 * dl[2];
     const double x2 = x + a2 * dl[0], y2 = y + a2 * dl[1], z2 = z + a2 * dl[2];
-    const double phi1 = atan2(y1, x1), phi2 = atan2(y2, x2);
+    const double phi1 = m_atan2(y1, x1), phi2 = m_atan2(y2, x2);
     bool hit1 = real && (a1 >= 0) && (fabs(z1) <= 1.) && angle_between(phi1, g[32], g[33]);
     bool hit2 = real && (a2 >= 0) && (fabs(z2) <= 1.) && angle_between(phi2, g[32], g[33]);
     hit1 = hit1 && !(hit2 && (a2 < a1));   // both valid: the closer one
@@ -584,7 +633,7 @@ MXB_DEV void op_aperture(unsigned long long* st_sm, Photon& ph, PP pr, int flags
         const double phi = pr[12] + pr[13] * u0;
         const double r = sqrt(pr[14] + (1. - pr[14]) * u1);
         double sn, cs;
-        sincos(phi, &sn, &cs);
+        m_sincos(phi, &sn, &cs);
         x = r * cs;
         y = r * sn;
     } else {  // RectangleAperture :92-95
@@ -630,7 +679,7 @@ MXB_DEV V3 polarization_vector(const V3& dir, double angle) {
     v1 = V3{v1.x / n1, v1.y / n1, v1.z / n1};
     const V3 v2 = cross(r, v1);
     double s, c;
-    sincos(angle, &s, &c);
+    m_sincos(angle, &s, &c);
     return V3{v1.x * c + v2.x * s, v1.y * c + v2.y * s, v1.z * c + v2.z * s};
 }
 
@@ -660,8 +709,8 @@ MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_
                          double z_jitter) {
     const double ra = ra_deg * (3.141592653589793 / 180.), dec = dec_deg * (3.141592653589793 / 180.);   // np.deg2rad
     double sr, cr, sd, cd;
-    sincos(ra, &sr, &cr);
-    sincos(dec, &sd, &cd);
+    m_sincos(ra, &sr, &cr);
+    m_sincos(dec, &sd, &cd);
     const V3 v{cd * cr, cd * sr, sd};
     const V3 o{p[0] * v.x + p[1] * v.y + p[2] * v.z, p[3] * v.x + p[4] * v.y + p[5] * v.z,
                p[6] * v.x + p[7] * v.y + p[8] * v.z};
@@ -678,12 +727,12 @@ MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_
     nin = V3{nin.x / nn, nin.y / nn, nin.z / nn};
     const V3 ein = cross(d, nin);
     double sp, cp;
-    sincos(polangle, &sp, &cp);
+    m_sincos(polangle, &sp, &cp);
     V3 pol{cp * nin.x + sp * ein.x, cp * nin.y + sp * ein.y, cp * nin.z + sp * ein.z};
     if ((flags & 1) && p[21] > 0.0) {
         const double randang = u_axis * 2. * 3.141592653589793;
         double sa, ca;
-        sincos(randang, &sa, &ca);
+        m_sincos(randang, &sa, &ca);
         const V3 ax{0., sa, ca};
         const double ang = 0. + p[21] * z_jitter;
         d = axangle_rotate_T(ax, ang, d);
@@ -699,10 +748,10 @@ template <typename PP>
 MXB_DEV void op_labcone(Photon& ph, PP p, double u_theta, double u_v, double polangle) {
     const double theta = 0. + (kTwoPi - 0.) * u_theta;
     const double v = 0. + (p[12] - 0.) * u_v;
-    const double phi = acos(1 - 2 * v);
+    const double phi = m_acos(1 - 2 * v);
     double st, ct, sp, cp;
-    sincos(theta, &st, &ct);
-    sincos(phi, &sp, &cp);
+    m_sincos(theta, &st, &ct);
+    m_sincos(phi, &sp, &cp);
     const V3 d{ct * sp, st * sp, cp};
     PP R = p + 3;
     ph.dir = V3{R[0] * d.x + R[1] * d.y + R[2] * d.z, R[3] * d.x + R[4] * d.y + R[5] * d.z,
@@ -730,7 +779,8 @@ MXB_DEV void op_farlab(Photon& ph, PP p, double u_y, double u_z, double polangle
 // ---------------------------------------------------------------------------
 struct ArrayIter {
     int cur, end;
-    bool brute;
+    bool brute;   // candidates are facet indices cur..end-1 themselves (no culling grid, or the steep-ray path)
+    bool seg;     // steep ray: every round scans the cells under the ray's footprint (array_scan_segment)
 };
 
 // true when `dir` lies inside the cone for which the culling grid is conservative
@@ -747,6 +797,7 @@ template <typename HP, typename IP>
 MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int nu, int nv, const Photon& ph,
                         bool active, unsigned long long* st_sm) {
     it.brute = true;
+    it.seg = false;
     it.cur = 0;
     it.end = active ? F : 0;
     if (mode == 1 && active) {
@@ -770,14 +821,91 @@ MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int
                 it.cur = it.end = 0;
             }
         } else {
-            atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
+            it.seg = true;   // outside the cone: footprint scan instead of the single cell
+            count_status(st_sm, MXB_ST_BRUTE);
         }
     }
 }
 
+// Steep rays (outside the cone the single-cell lookup is proven for, or after a second redirection).
+// Every facet point lies in the slab |h| <= Hs around the reference plane, so the ray can only hit
+// facets while it is inside the slab; the projection of that ray segment is a straight line on the
+// grid, and a facet is listed in every cell its footprint touches: scanning the cells of the
+// segment's bounding box finds every possible hit, for ANY direction.  Returns the smallest facet
+// index > after that the ray hits from (pos, dir), or -1.
+#ifdef MXB_OUTLINE_SCAN
+#define MXB_SCAN_ATTR __device__ __noinline__
+#else
+#define MXB_SCAN_ATTR __device__ __forceinline__   // measured (C2, r01): a call site in the search loop costs 18 %
+#endif
+template <typename BP, typename HP, typename IP>
+MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int rows_off, int stride, int F,
+                                               int nu, int nv, V3 pos, V3 dir, int after) {
+    const V3 nb = ld3(H + 3), O = ld3(H);
+    const double Hs = H[16];
+    const V3 rel{pos.x - O.x, pos.y - O.y, pos.z - O.z};
+    const double h0 = dot(rel, nb), dn = dot(dir, nb);
+    if (!(dn == dn) || !(h0 == h0)) return -1;
+    int iu0 = 0, iu1 = nu - 1, iv0 = 0, iv1 = nv - 1;
+    if (dn == 0.0) {
+        if (fabs(h0) > Hs) return -1;          // parallel to the slab and outside of it
+    } else {
+        const double ta = (-Hs - h0) / dn, tb = (Hs - h0) / dn;
+        const double t_lo = fmax(fmin(ta, tb), 0.0), t_hi = fmax(ta, tb);
+        if (t_hi < 0.0) return -1;             // the slab lies behind the photon
+        const V3 uu = ld3(H + 6), vv = ld3(H + 9);
+        const V3 qa{rel.x + t_lo * dir.x, rel.y + t_lo * dir.y, rel.z + t_lo * dir.z};
+        const V3 qb{rel.x + t_hi * dir.x, rel.y + t_hi * dir.y, rel.z + t_hi * dir.z};
+        const double fua = (dot(qa, uu) - H[12]) * H[14], fub = (dot(qb, uu) - H[12]) * H[14];
+        const double fva = (dot(qa, vv) - H[13]) * H[14], fvb = (dot(qb, vv) - H[13]) * H[14];
+        const double ulo = floor(fmin(fua, fub)), uhi = floor(fmax(fua, fub));
+        const double vlo = floor(fmin(fva, fvb)), vhi = floor(fmax(fva, fvb));
+        if (ulo == ulo && uhi == uhi && vlo == vlo && vhi == vhi) {   // NaN / inf: keep the whole grid
+            if (uhi < 0.0 || vhi < 0.0 || ulo > (double)(nu - 1) || vlo > (double)(nv - 1)) return -1;
+            iu0 = (int)fmax(ulo, 0.0);
+            iv0 = (int)fmax(vlo, 0.0);
+            iu1 = (int)fmin(uhi, (double)(nu - 1));
+            iv1 = (int)fmin(vhi, (double)(nv - 1));
+        }
+    }
+    V3 ipt;
+    double a0, a1;
+    if ((long long)(iu1 - iu0 + 1) * (iv1 - iv0 + 1) > 256) {
+        // a footprint this long touches most of the array: one ordered pass over the facets is cheaper
+        for (int j = after + 1; j < F; ++j)
+            if (plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1)) return j;
+        return -1;
+    }
+    int best = 0x7fffffff;
+    for (int iv = iv0; iv <= iv1; ++iv)
+        for (int iu = iu0; iu <= iu1; ++iu) {
+            const int cell = iv * nu + iu;
+            const int k1 = cell_start.i32(cell + 1);
+            for (int k = cell_start.i32(cell); k < k1; ++k) {
+                const int j = cand.i32(k);
+                if (j > after && j < best && plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1))
+                    best = j;
+            }
+        }
+    return best == 0x7fffffff ? -1 : best;
+}
+
 // next facet (ascending index) the photon hits from its CURRENT state; row = word offset of its row
-template <typename BP, typename IP>
-MXB_DEV bool array_search(ArrayIter& it, BP B, IP cand, int rows_off, int stride, Photon& ph, int& row) {
+template <typename BP, typename HP, typename IP>
+MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int rows_off, int stride, int F, int nu,
+                          int nv, Photon& ph, int& row) {
+    if (it.seg) {
+        if (it.cur >= it.end) return false;
+        const int j = array_scan_segment(B, H, cell_start, cand, rows_off, stride, F, nu, nv, ph.pos, ph.dir, it.cur - 1);
+        if (j < 0) {
+            it.cur = it.end;
+            return false;
+        }
+        row = rows_off + j * stride;
+        it.cur = j + 1;
+        plane_intersect(B + row, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1);
+        return true;
+    }
     while (it.cur < it.end) {
         const int j = it.brute ? it.cur : cand.i32(it.cur);
         ++it.cur;
@@ -803,9 +931,10 @@ MXB_DEV void array_revalidate(ArrayIter& it, HP H, const Photon& ph, int nhit, i
         if (nhit >= 2 || (dn == dn && !ok)) {
             const int j = (row - rows_off) / stride;
             it.brute = true;
+            it.seg = true;     // footprint scan from the new state, valid for any number of redirections
             it.cur = j + 1;
             it.end = F;
-            atomicAdd(&st_sm[MXB_ST_BRUTE], 1ULL);
+            count_status(st_sm, MXB_ST_BRUTE);
         }
     }
 }

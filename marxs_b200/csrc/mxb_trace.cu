@@ -208,7 +208,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
 
         // array iteration state
         int arr_nhit = 0, arr_pc = -1;
-        ArrayIter arr{0, 0, false};
+        ArrayIter arr{0, 0, false, false};
         ctx.init_round = true;
         int row = 0;    // word offset of the current facet row (0 = the blob itself outside arrays)
         int geom = 0;   // word offset of the current geometry block
@@ -462,7 +462,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                     array_open(arr, H, B + c.c[6], c.c[0], c.c[3], c.c[4], c.c[5], ph, ctx.active, st_sm);
                 }
                 // search the next facet (ascending index) this photon hits from its CURRENT state
-                const bool found = array_search(arr, B, B + c.c[7], c.c[2], c.c[1], ph, row);
+                const bool found = array_search(arr, B, H, B + c.c[6], B + c.c[7], c.c[2], c.c[1], c.c[0], c.c[4], c.c[5],
+                                                ph, row);
                 if (found) geom = row;
                 ph.hit = found;
                 arr_nhit += found ? 1 : 0;

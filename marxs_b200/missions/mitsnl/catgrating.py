@@ -88,7 +88,9 @@ class InterpolateEfficiencyTable:
         nw, nt, no = self.prob.shape
         block = np.concatenate([[SEL_INTERPTABLE, nw, nt, no, -1.], self.wave, self.theta,
                                 self.orders.astype(float)])
-        return block, self.prob
+        # global table: the efficiencies, then their running sums over the order axis (the fast build
+        # bisects the interpolated cumulative curve instead of summing all orders: mxb_ops.cuh select_order)
+        return block, np.concatenate([self.prob.ravel(), np.cumsum(self.prob, axis=2).ravel()])
 
 
 class NonParallelCATGrating(CATGrating):

@@ -362,6 +362,8 @@ class Lowering:
         self.op('CYLINDER', pg=self.params(np.concatenate([np.linalg.inv(p).ravel(), p.ravel(), [b1, b2, zoom[2]]])))
         self.last_order_col = None
 
+    HOISTABLE = tuple(OP[t] for t in ('QFACTOR', 'L2ABS', 'GSCATTER', 'LENS', 'RSCATTER', 'BREWSTER', 'PROPAGATE'))
+
     FOLDABLE = ('PLANE', 'LENS', 'RSCATTER', 'GSCATTER', 'FILTER', 'GRATING', 'DETPIX', 'BREWSTER', 'MLEFF')
     COMMIT_BIT, COMMIT_ROW_ID = 256, 512
 
@@ -407,7 +409,9 @@ class Lowering:
             return self.params(values)
         a = self.array
         pf = 14 + len(a['row'])
-        a['row'].extend(float(x) for x in np.asarray(values, dtype=float).ravel())
+        vals = [float(x) for x in np.asarray(values, dtype=float).ravel()]
+        a['row'].extend(vals)
+        a['block_len'][pf] = len(vals)
         return pf
 
     # ---- arrays -------------------------------------------------------------------------
@@ -415,7 +419,7 @@ class Lowering:
         if self.array is not None:
             raise NotFusable('nested Parallel containers are not fused')
         self.array = dict(facet=-1, body=[], rows=[], geoms=[], ids=[], slots=[], init=[], colrefs=[],
-                          folds=[], begin=self.op('ARRAY_BEGIN'))
+                          folds=[], block_len={}, begin=self.op('ARRAY_BEGIN'))
         # the ARRAY_BEGIN op itself is not part of the per-facet body
         self.array['body'] = []
 
@@ -447,6 +451,27 @@ class Lowering:
         nper = len(a['rows'][0]) if F else 0
         if any(len(r) != nper for r in a['rows']):
             raise NotFusable('facets of a Parallel carry different parameter counts')
+        # Parameter blocks that are identical for every facet (quality factor, L2 dimensions, scatter
+        # widths ...) move out of the facet rows into one shared block: smaller rows = more facets
+        # per staged program.  Only for ops whose `pg` field is otherwise unused.
+        if F > 1 and nper:
+            rows_arr = np.array(a['rows'])
+            keep = np.ones(nper, dtype=bool)
+            for rec in a['body']:
+                pf = rec['pf']
+                if (rec['type'] in self.HOISTABLE and rec['pg'] < 0 and pf >= 14 and pf in a['block_len']):
+                    cols = slice(pf - 14, pf - 14 + a['block_len'][pf])
+                    if np.all(rows_arr[:, cols] == rows_arr[0, cols]):
+                        rec['pg'] = self.params(rows_arr[0, cols])
+                        rec['pf'] = -1
+                        keep[cols] = False
+            if not keep.all():
+                new_index = np.cumsum(keep) - 1
+                for rec in a['body']:
+                    if rec['pf'] >= 14:
+                        rec['pf'] = 14 + int(new_index[rec['pf'] - 14])
+                a['rows'] = [list(r) for r in rows_arr[:, keep]]
+                nper = int(keep.sum())
         width = 14 + nper + 1
         stride = width + (width % 2)
         if (stride // 2) % 2 == 0:
@@ -464,6 +489,7 @@ class Lowering:
         if grid is not None:
             head[0:3], head[3:6], head[6:9], head[9:12] = grid['O'], grid['nbar'], grid['u'], grid['v']
             head[12], head[13], head[14], head[15] = grid['u0'], grid['v0'], grid['inv_cell'], grid['T2']
+            head[16] = grid['H'] * (1. + 1e-9) + 1e-6      # half thickness of the slab that holds every facet point
             ints[3] = 1
             ints[4], ints[5] = grid['nu'], grid['nv']
             ints[6] = self.params(_pack_i32(grid['start']))

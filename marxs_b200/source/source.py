@@ -90,7 +90,8 @@ class Source(SimulationSequenceElement):
         return _val(self.flux) * _val(self.geomarea)
 
     def n_photons(self, exposuretime):
-        return len(np.arange(0, _val(exposuretime, 's'), 1. / self._rate()))
+        # len(np.arange(0, T, dt)) without materialising it: numpy computes ceil((stop - start) / step)
+        return max(int(np.ceil((_val(exposuretime, 's') - 0.) / (1. / self._rate()))), 0)
 
     def _energy_spec(self):
         e = self.energy
@@ -322,7 +323,7 @@ def _run_born(elements, photons, check=True):
     return prog
 
 
-def observe(source, pointing, elements, exposuretime, device=None, id0=0, n=None, check=True):
+def observe(source, pointing, elements, exposuretime, device=None, id0=0, n=None, check=True, out=None):
     """One observation as ONE kernel launch: source -> pointing -> elements (aperture, mirror, gratings,
     detectors ...) lowered into a single born-on-device program.  ``pointing`` may be None for lab
     sources.  ``n`` overrides the photon count (e.g. the size of this rank's shard; ``id0`` is then the
@@ -331,7 +332,11 @@ def observe(source, pointing, elements, exposuretime, device=None, id0=0, n=None
     from ..simulator import _lowerable, Sequence
     chain = [source] + ([pointing] if pointing is not None else []) + list(elements)
     n_tot = source.n_photons(exposuretime) if n is None else int(n)
-    photons = _empty_batch(n_tot, device, id0)
+    if out is not None and len(out) == n_tot:
+        photons = out                      # reuse the table (and its memory) of a previous observation
+        photons.id0 = id0
+    else:
+        photons = _empty_batch(n_tot, device, id0)
     photons.meta['EXTNAME'] = 'EVENTS'
     photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
     if all(_lowerable(e) or isinstance(e, (Source, FixedPointing)) for e in chain):
