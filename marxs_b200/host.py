@@ -7,6 +7,7 @@ transposed view).  ``trace_host`` is the end-to-end call: H2D of the photon
 record, the fused kernel, D2H of the full result, chunked and overlapped inside
 the C library."""
 import ctypes
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -114,7 +115,7 @@ def _struct(prog, table, which, draws=None):
     return cols
 
 
-def trace_host(instrument, table, out=None, draws=None, chunk=1 << 21, check=True, program=None):
+def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, program=None):
     """Trace a HOST photon table through ``instrument`` (an element or list of elements).
 
     In place by default (reference semantics); with ``out`` (another HostPhotonTable of
@@ -143,7 +144,7 @@ def trace_host(instrument, table, out=None, draws=None, chunk=1 << 21, check=Tru
     cout = _struct(prog, dst, 'both')
     status = np.zeros(_lib.MXB_STATUS_WORDS, dtype=np.uint64)
     rc = lib.mxb_trace_host(prog.blob.ctypes.data, prog.blob.size, ctypes.byref(cin), ctypes.byref(cout),
-                            len(table), int(chunk), int(table.id0), rng.next_launch_seed(),
+                            len(table), int(chunk if chunk else os.environ.get('MXB_HOST_CHUNK', 0)), int(table.id0), rng.next_launch_seed(),
                             status.ctypes.data)
     _lib.check(lib, rc, 'mxb_trace_host')
     dst.meta.update(prog.meta_updates)

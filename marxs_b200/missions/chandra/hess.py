@@ -14,6 +14,8 @@ class HETG(Parallel):
     """High-Energy Transmission Grating: 192 MEG + 144 HEG facets, orders -3..3 with
     equal probability (the reference's placeholder efficiency)."""
 
+    _fingerprint_skip = Parallel._fingerprint_skip + ('hess',)     # the design table the facets were built from
+
     id_col = 'facet'
 
     def __init__(self, **kwargs):

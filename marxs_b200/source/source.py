@@ -313,11 +313,22 @@ def _empty_batch(n, device, id0):
     return photons
 
 
+_born_cache = {}
+
+
 def _run_born(elements, photons, check=True):
-    lw = Lowering([], meta=photons.meta)
-    for e in elements:
-        e._lower(lw)
-    prog = lw.finish()
+    """Lower (cached under the fingerprint of the element trees, like simulator._lower_run) and launch."""
+    from ..simulator import fingerprint
+    key = fingerprint(elements, ('born', photons.meta))
+    prog = _born_cache.get(key)
+    if prog is None:
+        lw = Lowering([], meta=photons.meta)
+        for e in elements:
+            e._lower(lw)
+        prog = lw.finish()
+        if len(_born_cache) >= 32:
+            _born_cache.pop(next(iter(_born_cache)))
+        _born_cache[key] = prog
     draws = _rng.take_injected(len(prog.slot_kinds))
     prog.run(photons, draws=draws, seed=_rng.next_launch_seed(), id0=getattr(photons, 'id0', 0), check=check)
     return prog

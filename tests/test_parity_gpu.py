@@ -966,6 +966,37 @@ def test_steep_rays_footprint_scan(mode):
     assert ((want['facet'] >= 63) & (one['facet'] >= 0)).mean() > 0.1
 
 
+def test_plan_cache_and_compiled_instrument():
+    """Lowered programs are cached under a digest of the element tree: a second call does not
+    re-lower, a moved element does; compile_instrument() skips even the digest."""
+    mb = _mb()
+    from marxs_b200 import optics, simulator
+    rng = np.random.default_rng(SEED + 71)
+    table = make_photons(rng, 5000)
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    seq = simulator.Sequence(elements=[optics.Baffle(zoom=[1, 30, 30], position=[10., 0, 0]), det])
+    h0, m0 = simulator.plan_cache_stats['hit'], simulator.plan_cache_stats['miss']
+    a = seq(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    b = seq(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    assert simulator.plan_cache_stats['miss'] == m0 + 1 and simulator.plan_cache_stats['hit'] == h0 + 1
+    for c in a:
+        assert np.array_equal(a[c], b[c], equal_nan=True), c
+    det.geometry.pos4d[1, 3] += 0.5                      # move the detector: the cached program must not be used
+    c_ = seq(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    assert simulator.plan_cache_stats['miss'] == m0 + 2
+    assert not np.array_equal(a['det_x'], c_['det_x'], equal_nan=True)
+    want = mo.Sequence([mo.Baffle(zoom=[1, 30, 30], position=[10., 0, 0]), mo.FlatDetector(pixsize=0.1, pos4d=det.pos4d)])(table.copy())
+    np.testing.assert_allclose(c_['det_x'], want['det_x'], rtol=1e-12, atol=1e-12, equal_nan=True)
+    run = simulator.compile_instrument(seq, mb.PhotonBatch(table, device='cuda'))
+    d = run(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    for c in c_:
+        assert np.array_equal(c_[c], d[c], equal_nan=True), c
+    src = mb.PhotonBatch(table, device='cuda')
+    out = run.trace_from(src, src.copy()).to_numpy()
+    for c in c_:
+        assert np.array_equal(c_[c], out[c], equal_nan=True), c
+
+
 def test_event_compaction():
     """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
     mb = _mb()
