@@ -266,6 +266,7 @@ def run_engine(args):
         raise SystemExit('launch with torchrun --nproc-per-node {0} (WORLD_SIZE={1})'.format(args.gpus, world))
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    numa = mdist.bind_to_gpu_numa(local) if world > 1 else None     # pinned e2e buffers local to the GPU's socket
     lib = _lib.load()
     n = args.photons
     K, W = args.steps, args.warmup
@@ -353,6 +354,7 @@ def run_engine(args):
         e2e = dict(value=world * ne * ke / e2e_s, unit='photons/s', h2d_bytes_per_step=h2d * world,
                    d2h_bytes_per_step=d2h * world, steps=ke, photons_per_gpu_per_step=ne,
                    ms_per_step=1e3 * e2e_s / ke,
+                   numa_node=numa,
                    api='marxs_b200.host.trace_host -> mxb_trace_host (pinned host SoA planes, chunked 3-stream pipeline)')
 
     if world > 1:

@@ -36,6 +36,32 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(device_index):
+    """Best effort: pin this process (and so the first-touch placement of the pinned host buffers it
+    allocates afterwards) to the CPUs of the NUMA node the GPU hangs off.  With one process per GPU the
+    host<->device copies of all ranks then run against local memory instead of crossing the socket
+    interconnect.  Returns the node number or None."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = '{0:04x}:{1:02x}:{2:02x}.0'.format(props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open('/sys/bus/pci/devices/{0}/numa_node'.format(bus)) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node{0}/cpulist'.format(node)) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 def allreduce_images(tensors):
     """In-place sum over ranks of detector images / histograms (one collective per tensor)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
