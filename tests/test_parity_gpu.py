@@ -997,6 +997,39 @@ def test_plan_cache_and_compiled_instrument():
         assert np.array_equal(c_[c], out[c], equal_nan=True), c
 
 
+def test_born_photons_are_independent_of_sharding():
+    """Born-on-device observation (device Philox keyed by the GLOBAL photon id): one launch of N photons
+    == shards of any size launched separately with id0 offsets, bit for bit; plus the invariants of a
+    trace (|dir| = 1, polarization perpendicular to dir, probability in [0, 1])."""
+    mb = _mb()
+    from marxs_b200 import source
+    from marxs_b200.missions import chandra
+    n = 300000
+    src = source.PointSource(coords=(30., 10.), flux=float(n), energy={'energy': np.array([0.3, 0.5, 1., 2., 4., 8.]),
+                                                                          'fluxdensity': np.array([0., 5., 3., 2., 1., .5])})
+    pnt = source.JitterPointing(coords=(30.002, 10.001), jitter=np.deg2rad(0.3 / 3600.))
+    elements = [chandra.Aperture(), chandra.HRMA(), chandra.HETG(),
+                chandra.ACIS(chips=[4, 5, 6, 7, 8, 9], aimpoint=chandra.AIMPOINTS['ACIS-S'])]
+    mb.set_seed(5)
+    whole = source.observe(src, pnt, elements, 1., device='cuda').to_numpy()
+    parts = []
+    for lo, hi in ((0, 70001), (70001, 70002), (70002, 250000), (250000, n)):
+        mb.set_seed(5)
+        parts.append(source.observe(src, pnt, elements, 1., device='cuda', n=hi - lo, id0=lo).to_numpy())
+    for c in whole:
+        got = np.concatenate([p[c] for p in parts])
+        assert np.array_equal(got, whole[c], equal_nan=True), c
+    assert np.array_equal(whole['time'], np.arange(n) * (1. / n))
+    d, p = whole['dir'][:, :3], whole['polarization'][:, :3]
+    assert np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-12)
+    # parallel transport through ~1e-6 rad scatter / jitter angles is only defined to ~1e-10 / angle
+    perp = np.abs(np.einsum('ij,ij->i', d, p))
+    assert np.isfinite(perp).all() and perp.max() < 1e-6 and np.median(perp) < 1e-12, (perp.max(), np.median(perp))
+    assert np.all((whole['probability'] >= 0) & (whole['probability'] <= 1))
+    assert 0.6 < (whole['CCD_ID'] >= 0).mean() < 0.95
+    assert 0.5 < whole['energy'].mean() < 3. and whole['energy'].min() >= 0.3 and whole['energy'].max() <= 8.
+
+
 def test_event_compaction():
     """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
     mb = _mb()
