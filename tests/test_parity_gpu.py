@@ -1030,6 +1030,62 @@ def test_born_photons_are_independent_of_sharding():
     assert 0.5 < whole['energy'].mean() < 3. and whole['energy'].min() >= 0.3 and whole['energy'].max() <= 8.
 
 
+def test_analysis_callers():
+    """the analysis drivers run on device-resident photons (reductions in torch,
+    every trial detector one launch)."""
+    mb = _mb()
+    from marxs_b200 import analysis, optics, simulator
+    rng = np.random.default_rng(SEED + 81)
+    # sigma clipping == the astropy algorithm restated in numpy
+    x = np.concatenate([rng.normal(3., 0.5, 20000), rng.uniform(-50, 50, 300), [np.nan] * 5])
+
+    def clip_np(a, sigma=3., maxiters=5):
+        a = a[np.isfinite(a)]
+        for _ in range(maxiters):
+            med, std = np.median(a), a.std()
+            keep = (a >= med - sigma * std) & (a <= med + sigma * std)
+            if keep.all():
+                break
+            a = a[keep]
+        return a.mean(), np.median(a), a.std()
+    got = analysis.sigma_clipped_stats(torch.as_tensor(x, device='cuda'))
+    np.testing.assert_allclose(got, clip_np(x), rtol=1e-12)
+    # best focus of an ideal lens: f = 1000 behind a lens at x = 1000 -> x = 0
+    n = 20000
+    pos = np.ones((n, 4))
+    pos[:, 0] = 1100.
+    pos[:, 1:3] = rng.uniform(-20, 20, (n, 2))
+    d = np.zeros((n, 4))
+    d[:, 0] = -1.
+    table = mo.PhotonTable(pos=pos, dir=d, energy=np.ones(n), polarization=np.tile([0., 1., 0., 0.], (n, 1)), probability=np.ones(n))
+    lens = simulator.Sequence(elements=[optics.PerfectLens(focallength=1000., position=[1000., 0, 0], zoom=[1, 50, 50]),
+                                        optics.RadialMirrorScatter(inplanescatter=1e-5, perpplanescatter=1e-5,
+                                                                   position=[1000., 0, 0], zoom=[1, 50, 50])])
+    ph = lens(mb.PhotonBatch(table, device='cuda'))
+    before = ph.to_numpy()
+    opt = analysis.find_best_detector_position(ph, bracket=(-50., 50.))
+    assert abs(opt.x) < 2., opt
+    after = ph.to_numpy()
+    assert set(before) == set(after) and all(np.array_equal(before[c], after[c], equal_nan=True) for c in before)
+    assert analysis.mean_width_2d(optics.FlatDetector(zoom=1e5, pixsize=1.)(ph.copy())) < 0.05
+    # detected fraction per label
+    ph['order'] = rng.integers(-2, 3, n).astype(float)
+    ph['probability'] = rng.uniform(0, 1, n)
+    o, p = ph.to_numpy()['order'], ph.to_numpy()['probability']
+    want = [p[o == k].sum() / n for k in (-1, 0, 2)]
+    np.testing.assert_allclose(analysis.detected_fraction(ph, [-1, 0, 2]), want, rtol=1e-12)
+    # resolving power per order of a small transmission-grating spectrograph
+    ph = lens(mb.PhotonBatch(table, device='cuda'))
+    gr = simulator.Parallel(elem_class=optics.FlatGrating, id_col='facet',
+                            elem_pos={'position': [[900., y, z] for y in (-15., 0., 15.) for z in (-15., 0., 15.)]},
+                            elem_args=dict(d=1e-3, zoom=[1, 7.4, 7.4], order_selector=optics.OrderSelector([0])))
+    res, fwhm, info = analysis.resolvingpower_per_order(gr, ph, [1, 2], detector=optics.FlatDetector(zoom=1e5, pixsize=1.),
+                                                        colname='det_x')
+    assert np.all(np.isfinite(res)) and res[1] > 1.5 * res[0] > 0      # dispersion doubles, the blur does not
+    res2, fwhm2, info2 = analysis.resolvingpower_per_order(gr, ph, [1], detector=None)
+    assert info2['fit_results'] and abs(info2['fit_results'][0].x) < 20.
+
+
 def test_event_compaction():
     """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
     mb = _mb()
