@@ -1086,6 +1086,66 @@ def test_analysis_callers():
     assert info2['fit_results'] and abs(info2['fit_results'][0].x) < 20.
 
 
+def test_edge_cases_and_error_semantics(mode):
+    """Empty, single and ragged tables; elements nothing hits add no columns; the reference's error
+    behaviour (ValueError for probabilities outside [0, 1], interp1d bounds, OrderSelector setup);
+    user plug-in elements and KeepCol steps keep working between fused launches."""
+    mb = _mb()
+    from marxs_b200 import optics, simulator
+    rng = np.random.default_rng(SEED + 91)
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    odet = mo.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    for n in (0, 1, 31, 33, 641):
+        table = make_photons(rng, n) if n else mo.PhotonTable(pos=np.zeros((0, 4)), dir=np.zeros((0, 4)), energy=np.zeros(0),
+                                                               polarization=np.zeros((0, 4)), probability=np.zeros(0))
+        got = det(mb.PhotonBatch(table, device='cuda'))
+        if n == 0:
+            assert len(got) == 0 and set(got.colnames) == set(table.colnames)
+            continue
+        compare(got, odet(table.copy()))
+    # nothing is hit -> no columns are added (optics/base.py:176-177)
+    table = make_photons(rng, 500)
+    far = optics.FlatDetector(pixsize=0.1, zoom=[1, 2, 2], position=[0., 5000., 0.])
+    assert set(far(mb.PhotonBatch(table, device='cuda')).colnames) == set(table.colnames)
+    # probability factors outside [0, 1]
+    with pytest.raises(ValueError):
+        optics.EnergyFilter(filterfunc=1.5, zoom=[1, 50, 50])(mb.PhotonBatch(table, device='cuda'))
+    with pytest.raises(ValueError):
+        optics.EnergyFilter(filterfunc=lambda e: e * 0 + 2., zoom=[1, 50, 50])(mb.PhotonBatch(table, device='cuda'))
+    bad_sel = optics.OrderSelector([0, 1], p=np.array([0.5, 0.5]))
+    bad_sel.p = np.array([0.9, 0.9])            # total probability 1.8: caught by the kernel's range check
+    with pytest.raises(ValueError, match='0..1'):
+        optics.FlatGrating(d=1e-3, order_selector=bad_sel, zoom=[1, 50, 50])(mb.PhotonBatch(table, device='cuda'))
+    with pytest.raises(ValueError):
+        optics.OrderSelector([0, 1], p=np.array([0.9, 0.9]))
+    # scipy interp1d semantics: energies outside the table raise
+    tab = optics.Tabulated1D([0.5, 1., 2.], [0.2, 0.5, 0.9])
+    with pytest.raises(ValueError, match='interpolation range'):
+        optics.EnergyFilter(filterfunc=tab, zoom=[1, 50, 50])(mb.PhotonBatch(table, device='cuda'))
+    ok = optics.EnergyFilter(filterfunc=optics.Tabulated1D([0.1, 1., 9.], [0.2, 0.5, 0.9]), zoom=[1, 50, 50])
+    want = mo.EnergyFilter(filterfunc=mo.Tabulated1D([0.1, 1., 9.], [0.2, 0.5, 0.9]), zoom=[1, 50, 50])(table.copy())
+    compare(ok(mb.PhotonBatch(table, device='cuda')), want)
+    # unknown keyword, zero zoom (base/base.py:85-86, 292-336)
+    with pytest.raises(ValueError):
+        optics.FlatDetector(pixsize=0.1, nonsense=3)
+    with pytest.raises(ValueError):
+        optics.FlatDetector(pixsize=0.1, zoom=[1, 0, 1])
+
+    # a user element with a Python hook runs between two fused launches, on device tensors
+    class Dimmer(optics.FlatOpticalElement):
+        def specific_process_photons(self, photons, intersect, interpos, intercoos):
+            return {'probability': 0.5 * torch.ones(int(intersect.sum()), dtype=torch.float64, device=photons.device),
+                    'seen': torch.ones(int(intersect.sum()), dtype=torch.float64, device=photons.device)}
+    keep = simulator.KeepCol('probability')
+    seq = simulator.Sequence(elements=[optics.Baffle(zoom=[1, 30, 30], position=[10., 0, 0]), Dimmer(zoom=[1, 5, 30], position=[5., 0, 0]), det],
+                             postprocess_steps=[keep])
+    out = seq(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    ref = mo.Sequence([mo.Baffle(zoom=[1, 30, 30], position=[10., 0, 0])])(table.copy())
+    hit = mo.plane_intersect(mo.PlaneConsts(mo.compose([5., 0, 0], np.eye(3), [1, 5, 30])), ref['dir'], ref['pos'])[0]
+    np.testing.assert_allclose(out['probability'], ref['probability'] * np.where(hit, 0.5, 1.), rtol=1e-14)
+    assert np.array_equal(np.isfinite(out['seen']), hit) and len(keep.data) == 3
+
+
 def test_event_compaction():
     """mxb_compact_events == boolean indexing, order preserved, ragged sizes around the block size."""
     mb = _mb()
