@@ -10,6 +10,10 @@ Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function
 here against (a) the known-answer vectors transcribed from the reference's own
 tests and (b) ``tests/golden/*.npz`` produced by running the unmodified
 reference under ``oracle/standin`` (script: ``oracle/gen_golden.py``).
+One exception, stated in its docstring and in DESIGN.md: the sky-pointing rotation
+(``skyoffset_matrix`` / ``FixedPointing``) restates astropy's SkyOffsetFrame, which cannot be
+installed or run here; it is pinned by the known answers of the reference's own
+``source/tests/test_pointing.py`` only ("pinned to the reference's tests", not to a reference run).
 
 Arithmetic contract (what "bit-exact" means for the CUDA kernels):
   * every dot product / norm is an explicit left-to-right sum over x, y, z
