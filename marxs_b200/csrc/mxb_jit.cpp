@@ -552,7 +552,19 @@ struct Gen {
         in_array = false;
         new_hit();
         out("            // ---- op %d: ARRAY_END", end_pc);
-        out("            array_revalidate(it, %s, ph, nhit, row, %d, %d, %d, st_sm);", H.c_str(), rows_off, stride, nF);
+        {
+            // the cone only has to be re-validated when the body can change the photon's direction
+            bool redirects = false;
+            for (int k = bpc + 1; k < end_pc; ++k) {
+                const int t = ops[k].type;
+                redirects |= (t == MXB_OP_LENS || t == MXB_OP_RSCATTER || t == MXB_OP_GSCATTER || t == MXB_OP_GRATING ||
+                              t == MXB_OP_BREWSTER);
+            }
+            if (redirects)
+                out("            array_revalidate(it, %s, ph, nhit, row, %d, %d, %d, st_sm);", H.c_str(), rows_off, stride, nF);
+            else
+                out("            // (body does not redirect photons: the candidate list stays valid)");
+        }
         out("            init_round = false;               // later rounds only store for photons that hit");
         out("            if (!__any_sync(0xffffffffu, ph.hit && it.cur < it.end)) break;");
         out("            if (!ph.hit) it.cur = it.end;     // lanes that found nothing are done with this array");
