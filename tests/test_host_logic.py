@@ -270,3 +270,81 @@ def test_cull_grid_is_conservative(case):
             nhit += 1
     assert nhit > 5000
     assert g['mean_candidates'] < 6
+
+
+# ---------------------------------------------------------------------------
+# later additions: row hoisting, plan-cache digest, sources / pointing host logic
+# ---------------------------------------------------------------------------
+def test_facet_invariant_blocks_leave_the_rows():
+    """Blocks that are identical for every facet (quality factor, L2 dimensions, L2 scatter) are lowered
+    once as shared parameters; per-facet blocks (grating vectors) stay in the rows."""
+    from marxs_b200 import optics, simulator
+    from marxs_b200.missions import mitsnl
+    from marxs_b200.program import Lowering, OP
+    sel = optics.OrderSelector([0, 1])
+    pos = [[0., y, z] for y in (-16., 0., 16.) for z in (-17., 0., 17.)]
+    par = simulator.Parallel(elem_class=mitsnl.CATL1L2Stack, elem_pos={'position': pos}, id_col='facet',
+                             elem_args=dict(zoom=[1, 7.5, 8.], order_selector=sel))
+    lw = Lowering(['pos', 'dir', 'polarization', 'energy', 'probability'])
+    par._lower(lw)
+    prog = lw.finish()
+    by_type = {}
+    for o in prog.ops:
+        by_type.setdefault(o['type'], []).append(o)
+    for t in ('QFACTOR', 'L2ABS', 'GSCATTER'):
+        (o,) = by_type[OP[t]]
+        assert o['pf'] == -1 and o['pg'] > 0, t
+    g0, g1 = by_type[OP['GRATING']]
+    assert (g0['pf'], g1['pf']) == (14, 23) and g1['flags'] & 8           # membrane, then L1 support
+    F, stride = prog.ops[0]['cols'][0], prog.ops[0]['cols'][1]
+    assert F == 9 and stride == 34                                         # 14 geometry + 2 x 9 grating + id, padded
+    # a facet with a different quality factor keeps the block in the rows
+    par.elements[3].elements[1].factor = 0.5
+    lw = Lowering(['pos', 'dir', 'polarization', 'energy', 'probability'])
+    par._lower(lw)
+    q = [o for o in lw.finish().ops if o['type'] == OP['QFACTOR']][0]
+    assert q['pf'] >= 14 and q['pg'] == -1
+
+
+def test_fingerprint_tracks_what_lowering_reads():
+    from marxs_b200 import optics, simulator
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    flt = optics.EnergyFilter(filterfunc=lambda e: e * 0 + 0.5, zoom=[1, 20, 20])
+    seq = simulator.Sequence(elements=[flt, det])
+    f0 = simulator.fingerprint([seq], ('a',))
+    assert f0 == simulator.fingerprint([seq], ('a',)) and f0 != simulator.fingerprint([seq], ('b',))
+    det.geometry.pos4d[2, 3] += 1e-12
+    f1 = simulator.fingerprint([seq], ('a',))
+    assert f1 != f0
+    det.pixsize = 0.2
+    f2 = simulator.fingerprint([seq], ('a',))
+    assert f2 != f1
+    flt.filterfunc = lambda e: e * 0 + 0.5          # a different function object, same text
+    assert simulator.fingerprint([seq], ('a',)) != f2
+    det.name = 'renamed'                             # labels do not matter
+    flt.filterfunc = seq.elements[0].filterfunc
+    assert simulator.fingerprint([seq], ('a',)) == simulator.fingerprint([seq], ('a',))
+
+
+def test_source_and_pointing_host_logic():
+    from marxs_b200 import source
+    from marxs_b200.source.source import skyoffset_matrix, RandomArbitraryPdfTable
+    for T, rate in ((10., 100.), (10., 2000.), (1., 1e6), (5., 0.7), (3.3, 7.7)):
+        s = source.PointSource(coords=(1., 2.), flux=rate)
+        assert s.n_photons(T) == len(np.arange(0, T, 1. / rate))
+    x = np.array([0.3, 0.5, 0.9, 1.4, 2.2, 3.5, 6.0, 10.])
+    pdf = np.array([0., 3., 1., 5., 0.2, 4., 0.05, 1.])
+    t = RandomArbitraryPdfTable(x, pdf).table()
+    o = mo.RandomArbitraryPdf(x, pdf)
+    n = len(x)
+    assert t[0] == n and np.array_equal(t[1:1 + n], o.cdf) and np.array_equal(t[1 + n:1 + 2 * n], o.sortindex)
+    assert np.array_equal(t[1 + 2 * n:1 + 3 * n], x) and np.array_equal(t[1 + 3 * n:], o.bin_width)
+    np.testing.assert_array_equal(skyoffset_matrix(0.3, -0.2, 0.1), mo.skyoffset_matrix(0.3, -0.2, 0.1))
+    p = source.JitterPointing(coords=(25., -10.), roll=0.3, jitter=1e-5)._params()
+    op = mo.FixedPointing((25., -10.), roll=0.3)
+    np.testing.assert_array_equal(p[:9].reshape(3, 3), op.matrix())
+    north = op._apply_ref(op.sky_to_offset(np.array([0.]), np.array([90.])))[0, :3]
+    np.testing.assert_array_equal(p[18:21], north)
+    assert p[21] == 1e-5
+    with pytest.raises(source.SourceSpecificationError):
+        source.PointSource(coords=(1., 2.), flux=lambda t, a: t).n_photons(1.)
