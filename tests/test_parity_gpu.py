@@ -1196,6 +1196,87 @@ def test_fused_detector_image():
     assert ref_counts.sum() > 0.9 * ok.sum()
 
 
+def test_config4_full_size_born_on_device():
+    """Config-4 size (1e8 photons): LabPointSourceCone -> MultiLayerMirror -> FlatBrewsterMirror ->
+    FlatDetector, photons born on the device, through size-independent properties."""
+    mb = _mb()
+    from marxs_b200 import optics, source
+    n = 100_000_000
+    g = load('mlmirror')
+    refl = {'X(mm)': g['ml_x_mm'], 'Peak lambda': g['ml_peak_lambda'], 'Peak': g['ml_peak'], 'FWHM(nm)': g['ml_fwhm']}
+    polt = {'Photon energy': g['ml_pol_energy_ev'], 'Polarization': g['ml_pol']}
+    a = 2 ** -0.5
+    elements = [optics.MultiLayerMirror(reflFile=refl, testedPolarization=polt, orientation=np.array([[a, 0, -a], [0, 1, 0], [a, 0, a]]),
+                                        zoom=[1, 24.5, 12.]),
+                optics.FlatBrewsterMirror(orientation=np.array([[0, 0, 1.], [a, a, 0], [-a, a, 0]]), position=[0., 0., 30.], zoom=[1, 10., 30.]),
+                optics.FlatDetector(pixsize=0.05, position=[0., 50., 30.], orientation=np.array([[0, -1., 0], [1., 0, 0], [0, 0, 1.]]),
+                                    zoom=[1, 20., 20.])]
+    src = source.LabPointSourceCone(position=[200., 0, 0], direction=[-1., 0, 0], half_opening=0.02, flux=float(n), energy=0.31)
+    mb.set_seed(3)
+    whole = source.observe(src, None, elements, 1., device='cuda')
+    assert len(whole) == n
+    # any sharding of the global photon ids gives the same photons
+    lo, hi = 37_000_001, 37_400_000
+    mb.set_seed(3)
+    part = source.observe(src, None, elements, 1., device='cuda', n=hi - lo, id0=lo)
+    for c in ('pos', 'dir', 'polarization', 'probability', 'det_x', 'detpix_y', 'time'):
+        assert torch.equal(torch.nan_to_num(whole[c][lo:hi], nan=-9.), torch.nan_to_num(part[c], nan=-9.)), c
+    det = torch.isfinite(whole['det_x'])
+    assert 0.9 < float(det.double().mean()) <= 1.0
+    d, p = whole['dir'][det][:, :3], whole['polarization'][det][:, :3]
+    assert float((d.norm(dim=1) - 1).abs().max()) < 1e-12
+    assert float((p.norm(dim=1) - 1).abs().max()) < 1e-9
+    assert float((d * p).sum(dim=1).abs().max()) < 1e-9           # Brewster mirrors re-build the polarization vector
+    pr = whole['probability']
+    assert float(pr.min()) >= 0. and float(pr.max()) <= 1.
+    assert torch.equal(whole['energy'], torch.full_like(whole['energy'], 0.31))
+    # unpolarised source on two crossed Brewster mirrors: the first passes cos^2, the second the remaining s-component;
+    # azimuthal symmetry of the cone: mean detector coordinate perpendicular to the plane of incidence ~ 0
+    assert abs(float(whole['det_y'][det].mean())) < 0.01
+
+
+def test_config3_full_size_properties():
+    """Config-3 size (1e8 photons): lens + scatter -> 529 CATL1L2Stack facets (135 x 25 x 28 efficiency
+    table) -> 16 CCDs, through size-independent properties (the instrument of tools/bench_configs.py)."""
+    import importlib.util
+    mb = _mb()
+    from marxs_b200 import simulator
+    spec = importlib.util.spec_from_file_location('bench_configs', os.path.join(os.path.dirname(__file__), '..', 'tools', 'bench_configs.py'))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    n = 100_000_000
+    elements, b, n_facets = bc.c3_setup(n)
+    assert n_facets == 529
+    inst = simulator.Sequence(elements=elements)
+    run = simulator.compile_instrument(inst, b)
+    mb.set_seed(9)
+    whole = run.trace_from(b, b.copy())
+    lo, hi = 61_000_003, 61_500_000
+    part_in = b[torch.arange(lo, hi, device='cuda')]
+    part_in.id0 = lo
+    mb.set_seed(9)
+    part = run.trace_from(part_in, part_in.copy())
+    for c in ('pos', 'dir', 'polarization', 'probability', 'order', 'order_L1', 'facet', 'CCD_ID', 'detpix_x', 'L2Diffraction'):
+        assert torch.equal(torch.nan_to_num(whole[c][lo:hi].double(), nan=-9.), torch.nan_to_num(part[c].double(), nan=-9.)), c
+    on_facet = whole['facet'] >= 0
+    assert 0.7 < float(on_facet.double().mean()) < 0.85
+    assert float((whole['CCD_ID'] >= 0).double().mean()) > 0.2
+    # untouched photons keep probability 1, everything else can only lose
+    pr = whole['probability']
+    assert float(pr.max()) <= 1. and float(pr[torch.isfinite(pr)].min()) >= 0.
+    assert torch.equal(pr[~on_facet], torch.ones_like(pr[~on_facet]))
+    # L1 support: 18 % of the facet photons go through a bar (order_L1 = 0 there, plus the 86 % zeroth order)
+    o1 = whole['order_L1'][on_facet]
+    assert 0.87 < float((o1 == 0).double().mean()) < 0.90
+    # blazed table: the mean diffraction order follows -2 sin(blaze) d / lambda
+    o, e = whole['order'][on_facet], b['energy'][on_facet]
+    soft = e < 0.5
+    assert float(o[soft].mean()) > float(o[~soft].mean())          # longer wavelengths -> orders closer to zero
+    d = whole['dir'][on_facet][:, :3]
+    ok = torch.isfinite(d).all(dim=1)
+    assert float(ok.double().mean()) > 0.999 and float((d[ok].norm(dim=1) - 1).abs().max()) < 1e-12
+
+
 def test_chandra_full_size_properties():
     """Config-2 size (1e7 photons) through size-independent properties: device RNG,
     results independent of how the batch is split, physical invariants."""

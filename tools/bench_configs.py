@@ -90,11 +90,10 @@ def c1(scale, steps):
                  lambda o: dict(on_detector=float(torch.isfinite(o['det_x']).double().mean())))
 
 
-def c3(scale, steps):
+def c3_setup(n, seed=3):
     """CAT-grating spectrograph: lens + scatter -> ~560 CATL1L2Stack facets on a sphere around the focus
     -> strip of 16 CCDs; efficiency table 135 x 25 x 28 (synthetic numbers, real shape)."""
-    n = int(1e8 * scale)
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(seed)
     wave = np.linspace(0.5, 7.5, 135)
     theta = np.deg2rad(np.linspace(0.2, 4.0, 25))
     orders = np.arange(-20, 8)[::-1]
@@ -137,7 +136,13 @@ def c3(scale, steps):
     p[1] = 1.
     b.new_column('energy', torch.float64)[...] = 0.3 + 1.2 * torch.rand(n, device='cuda', generator=g, dtype=torch.float64)
     b.new_column('probability', torch.float64, fill=1.)
-    run_resident('C3 CAT spectrograph: lens+scatter -> {0} CATL1L2Stack facets -> 16 CCDs'.format(len(pos4ds)), elements, b, n,
+    return elements, b, len(pos4ds)
+
+
+def c3(scale, steps):
+    n = int(1e8 * scale)
+    elements, b, n_facets = c3_setup(n)
+    run_resident('C3 CAT spectrograph: lens+scatter -> {0} CATL1L2Stack facets -> 16 CCDs'.format(n_facets), elements, b, n,
                  19, steps, lambda o: dict(on_facet=float((o['facet'] >= 0).double().mean()),
                                            on_ccd=float((o['CCD_ID'] >= 0).double().mean()),
                                            mean_order=float(torch.nanmean(o['order']))))
