@@ -705,6 +705,40 @@ def case_sources(marxs, rng):
     save('sources', **arrays)
 
 
+def case_rowland(marxs, rng):
+    """Facet placement on a Rowland torus (design/rowland.py): the Config-3 grating array (561 facets) and
+    CCD strip (16), a tilted torus with a partial ring of facets, torus normals and parametrisation."""
+    from marxs.design.rowland import RowlandTorus, GratingArrayStructure, RectangularGrid, design_tilted_torus
+    from marxs.optics import CATGrating, FlatDetector, OrderSelector
+    from transforms3d.axangles import axangle2mat
+    arrays = {}
+    rt = RowlandTorus(6000., 6000.)
+    gas = GratingArrayStructure(rowland=rt, d_element=[30., 30.], radius=[300., 500.], elem_class=CATGrating,
+                                elem_args={'d': 2e-4, 'zoom': [1, 13.5, 13.5], 'order_selector': OrderSelector([0]),
+                                           'orientation': axangle2mat([0, 0, 1], np.deg2rad(1.91))})
+    arrays['gas_pos4d'] = np.array([e.pos4d for e in gas.elements])
+    arrays['gas_elem_pos'] = np.array(gas.elem_pos)
+    det = RectangularGrid(rowland=rt, d_element=[49.652, 49.652], y_range=[-50, 700], elem_class=FlatDetector,
+                          elem_args={'zoom': [1, 24.576, 12.288], 'pixsize': 0.024}, id_col='CCD_ID', guess_distance=25.)
+    arrays['det_pos4d'] = np.array([e.pos4d for e in det.elements])
+    R, r, pos4d = design_tilted_torus(9e3, np.deg2rad(3.8), np.deg2rad(7.6))
+    arrays['tilt_Rr'] = np.array([R, r])
+    arrays['tilt_pos4d'] = pos4d
+    rt2 = RowlandTorus(R, r, pos4d=pos4d)
+    gas2 = GratingArrayStructure(rowland=rt2, d_element=[25., 40.], radius=[200., 420.], phi=[-0.5 + np.pi / 2, 0.5 + np.pi / 2],
+                                 elem_class=CATGrating, normal_spec=np.array([0, 0, 0, 1.]),
+                                 elem_args={'d': 2e-4, 'zoom': [1, 10., 18.], 'order_selector': OrderSelector([0])})
+    arrays['gas2_pos4d'] = np.array([e.pos4d for e in gas2.elements])
+    th, ph = rng.uniform(-3, 3, 50), rng.uniform(-3, 3, 50)
+    pts = rt2.parametric(th, ph)
+    arrays['par_theta'], arrays['par_phi'], arrays['par_xyzw'] = th, ph, pts
+    arrays['par_normal'] = rt2.normal(pts)
+    t2, p2 = rt2.xyzw2parametric(pts)
+    arrays['par_theta_back'], arrays['par_phi_back'] = t2, p2
+    arrays['quartic_offsurface'] = rt2.quartic(pts[:, :3] + 1.)
+    save('rowland', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -714,7 +748,7 @@ def main():
     for i, case in enumerate([case_intersect, case_parallel_transport, case_gratings,
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
-                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources]):
+                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue
