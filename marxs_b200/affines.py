@@ -79,6 +79,20 @@ def axangle2mat(axis, angle):
                      [z * x * C - y * s, y * z * C + x * s, z * z * C + c]])
 
 
+def euler2mat(ai, aj, ak, axes='sxyz'):
+    """Rotation matrix from Euler angles.  Only the convention MARXS uses is provided: ``'sxyz'`` = rotate about
+    the static x axis by ``ai``, then static y by ``aj``, then static z by ``ak`` (R = Rz Ry Rx, as
+    transforms3d.euler.euler2mat; reference call sites design/tolerancing.py:76-78,102-104,
+    design/uncertainties.py:37)."""
+    if axes != 'sxyz':
+        raise NotImplementedError("only the 'sxyz' convention is available")
+    si, sj, sk = math.sin(ai), math.sin(aj), math.sin(ak)
+    ci, cj, ck = math.cos(ai), math.cos(aj), math.cos(ak)
+    return np.array([[cj * ck, sj * si * ck - ci * sk, sj * ci * ck + si * sk],
+                     [cj * sk, sj * si * sk + ci * ck, sj * ci * sk - si * ck],
+                     [-sj, cj * si, cj * ci]])
+
+
 def ex2vec_fix(e1, efix):
     """Rotation taking x to ``e1`` keeping the new y coplanar with ``efix``
     (reference math/rotations.py:8-47)."""

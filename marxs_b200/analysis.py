@@ -14,7 +14,10 @@ from .geometry import Cylinder
 from .simulator import trace_from
 
 __all__ = ['sigma_clipped_stats', 'sigma_clipped_std', 'mean_width_2d', 'find_best_detector_position',
-           'detected_fraction', 'resolvingpower_per_order', 'AnalysisError']
+           'detected_fraction', 'resolvingpower_per_order', 'AnalysisError',
+           'resolvingpower_from_photonlist', 'resolvingpower_from_photonlist_robust', 'effectivearea_from_photonlist',
+           'average_R_Aeff', 'weighted_per_order', 'identify_photon_in_subaperture',
+           'CaptureResAeff', 'CaptureResAeff_CCDgaps']
 
 
 class AnalysisError(Exception):
@@ -129,3 +132,144 @@ def resolvingpower_per_order(gratings, photons, orders, detector=None, colname='
         fwhm[i] = 2.3548 * stdpos
         res[i] = np.abs((meanpos - zeropos) / fwhm[i])
     return res, fwhm, info
+
+
+# ---------------------------------------------------------------------------------------------
+# figures of merit read off a traced photon list (reference analysis/gratings.py:133-549): the
+# ``analyzefunc`` of the tolerancing loops.  Selections are boolean device tensors; nothing but
+# the per-order scalars leaves the GPU.
+# ---------------------------------------------------------------------------------------------
+def resolvingpower_from_photonlist(photons, orders, col='proj_x', zeropos=None, ordercol='order', ind=None):
+    """Resolving power, mean position and width of column ``col`` for every order in ``orders`` (reference
+    analysis/gratings.py:211-269).  Orders with 20 photons or fewer give NaN; ``zeropos=None`` measures the
+    position of order 0 (AnalysisError below 20 photons).  ``ind`` (bool mask) restricts the list without
+    materialising a sub-table."""
+    o, x = _column(photons, ordercol), _column(photons, col)
+    if ind is not None:
+        o, x = o[ind], x[ind]
+    if zeropos is None:
+        zero = o == 0.
+        if int(zero.sum()) < 20:
+            raise AnalysisError('Too few photons in list to determine position of order 0 automatically.')
+        zeropos = sigma_clipped_stats(x[zero])[0]
+    orders = np.asarray(orders)
+    pos = np.zeros(orders.shape, dtype=float)
+    std = np.zeros(orders.shape, dtype=float)
+    for i, order in enumerate(orders):
+        sel = o == float(order)
+        if int(sel.sum()) > 20:
+            pos[i], _, std[i] = sigma_clipped_stats(x[sel])
+        else:
+            pos[i], std[i] = np.nan, np.nan
+    with np.errstate(divide='ignore', invalid='ignore'):
+        res = np.abs(pos - zeropos) / (std * 2.3548)
+    return res, pos, std
+
+
+def resolvingpower_from_photonlist_robust(lphotons, orders, cols, zeropositions, ordercol='order'):
+    """Worst case over several (photon list, column, zero position) triples, per order (reference :272-330)."""
+    if len(cols) != len(zeropositions):
+        raise ValueError('Number of elements in cols and zeropositions is not the same.')
+    if len(cols) != len(lphotons):
+        raise ValueError('Number of elements in cols and photon lists is not the same.')
+    allres = [resolvingpower_from_photonlist(p, orders, col=c, zeropos=z, ordercol=ordercol)
+              for p, c, z in zip(lphotons, cols, zeropositions)]
+    res, pos, std = (np.array([a[k] for a in allres]) for k in range(3))
+    worst = np.argmin(res, axis=0)
+    k = np.arange(res.shape[1])
+    return res[worst, k], pos[worst, k], std[worst, k]
+
+
+def effectivearea_from_photonlist(photons, orders, n_photons, A_geom=1., ordercol='order', ind=None):
+    """Effective area per order: summed probability of the photons of that order / n_photons x A_geom
+    (reference :333-362).  One pass: orders are binned with a scatter-add on the device."""
+    o, p = _column(photons, ordercol), _column(photons, 'probability')
+    if ind is not None:
+        o, p = o[ind], p[ind]
+    orders = np.asarray(orders)
+    aeff = np.zeros(len(orders))
+    for i, order in enumerate(orders):
+        aeff[i] = float(p[o == float(order)].sum())
+    return aeff / n_photons * A_geom
+
+
+def identify_photon_in_subaperture(angle, max_ang, ang_0=np.pi / 2):
+    """Photons in two mirrored sectors of half-width ``max_ang`` around ``ang_0`` and ``-ang_0`` (reference :365-386)."""
+    a = torch.as_tensor(angle)
+    a = torch.remainder(a, 2 * np.pi)
+    tol = max_ang + 1e-5 * abs(ang_0)               # np.isclose(a, b, atol): |a - b| <= atol + rtol |b|, rtol = 1e-5
+    tol2 = max_ang + 1e-5 * abs(2 * np.pi - ang_0)
+    return ((a - ang_0).abs() <= tol) | ((a - (2 * np.pi - ang_0)).abs() <= tol2)
+
+
+def average_R_Aeff(r, aeff, axis=None):
+    """Sum of Aeff and the Aeff-weighted mean of R, ignoring non-finite R (reference :181-208).
+    Returns (res_avg, aeff_sum)."""
+    r, aeff = np.asarray(r, dtype=float), np.asarray(aeff, dtype=float)
+    return np.ma.average(np.ma.masked_invalid(r), weights=aeff, axis=axis), aeff.sum(axis=axis)
+
+
+def weighted_per_order(data, orders, energy, gratingeff):
+    """Mean over orders of ``data`` (orders x energies) weighted with the tabulated probability of each
+    order at each energy (reference :133-178)."""
+    data = np.asarray(data)
+    if len(orders) != data.shape[0]:
+        raise ValueError('First dimension of "data" must match length of "orders".')
+    if len(energy) != data.shape[1]:
+        raise ValueError('Second dimension of "data" must match length of "energy".')
+    weights = np.zeros_like(data, dtype=float)
+    en_sort = np.argsort(gratingeff.energy)
+    for i, o in enumerate(orders):
+        k = np.nonzero(np.asarray(gratingeff.orders) == o)[0]
+        if len(k) != 1:
+            raise KeyError('No data for order {0} in gratingeff'.format(o))
+        weights[i] = np.interp(energy, gratingeff.energy[en_sort], gratingeff.prob[:, k[0]][en_sort])
+    return np.ma.average(data, axis=0, weights=weights)
+
+
+class CaptureResAeff:
+    """Resolving power and effective area per order of one traced photon list, plus the totals of the
+    dispersed orders and of order 0 (reference :389-500); the usual ``analyzefunc`` of
+    ``marxs_b200.design.tolerancing.run_tolerances``.  Subclass and override ``aeff_filter`` /
+    ``res_filter`` (bool device masks) to change which photons count."""
+
+    def __init__(self, A_geom=1, order_col='order', orders=np.arange(-10, 11), dispersion_coord='det_x', zeropos=None):
+        self.A_geom = A_geom
+        self.order_col = order_col
+        self.orders = np.asanyarray(orders)
+        self.dispersion_coord = dispersion_coord
+        self.zeropos = zeropos
+
+    def aeff_filter(self, photons):
+        return None                                             # all photons
+
+    def res_filter(self, photons):
+        return torch.isfinite(_column(photons, self.dispersion_coord)) & (_column(photons, 'probability') > 0)
+
+    def __call__(self, photons, n_photons=None):
+        if n_photons is None:
+            n_photons = len(photons)
+        aeff = effectivearea_from_photonlist(photons, self.orders, n_photons, self.A_geom, self.order_col,
+                                             ind=self.aeff_filter(photons))
+        try:
+            if self.dispersion_coord not in photons.colnames or self.order_col not in photons.colnames:
+                raise AnalysisError('no photon reached the detector')
+            res = resolvingpower_from_photonlist(photons, self.orders, col=self.dispersion_coord, zeropos=self.zeropos,
+                                                 ordercol=self.order_col, ind=self.res_filter(photons))[0]
+        except AnalysisError:
+            res = np.nan * np.ones(len(self.orders))
+        disp = self.orders != 0
+        avggratres, aeffgrat = average_R_Aeff(res[disp], aeff[disp])
+        return {'Aeff0': np.sum(aeff[~disp]), 'Aeffgrat': aeffgrat, 'Aeff': aeff, 'Rgrat': avggratres, 'R': res}
+
+
+class CaptureResAeff_CCDgaps(CaptureResAeff):
+    """As CaptureResAeff, but only photons with ``photons[aeff_filter_col] >= 0`` (e.g. a CCD_ID) count
+    towards the effective area, while R ignores chip gaps (reference :503-549)."""
+
+    def __init__(self, aeff_filter_col='CCD_ID', **kwargs):
+        super().__init__(**kwargs)
+        self.aeff_filter_col = aeff_filter_col
+
+    def aeff_filter(self, photons):
+        return _column(photons, self.aeff_filter_col) >= 0

@@ -144,10 +144,32 @@ def run_fused(elements, photons, check=True):
         if needs_pos and 'pos' not in photons:
             import torch
             photons.new_column('pos', torch.float64, fill=0., vector=True)[3] = 1.
+        drop_pos = _create_core_for_pointing(prog, photons)
         draws = rng.take_injected(len(prog.slot_kinds))
         prog.run(photons, draws=draws, seed=rng.next_launch_seed(), id0=getattr(photons, 'id0', 0), check=check)
+        if drop_pos:
+            photons.remove_column('pos')        # no aperture in this run: the reference adds pos there (aperture.py:19-27)
         i = j
     return photons
+
+
+def _create_core_for_pointing(prog, photons):
+    """A fused run that starts with a pointing model works on a freshly generated list (time, energy, polangle,
+    ra, dec): the POINTING op writes dir and polarization, so those columns are created here (reference
+    pointing.py:131-133).  Returns True when a placeholder pos column was added that must go again."""
+    from .program import OP
+    if ('dir' in photons and 'polarization' in photons) or not any(o['type'] == OP['POINTING'] for o in prog.ops):
+        return False
+    import torch
+    n = len(photons)
+    for name in ('dir', 'polarization'):
+        if name not in photons:
+            photons.new_column(name, torch.float64, fill=0., vector=True, n=n)
+    if 'pos' not in photons:
+        t = photons.new_column('pos', torch.float64, fill=float('nan'), vector=True, n=n)
+        t[3] = 1.
+        return True
+    return False
 
 
 def trace_from(instrument, source, out=None, check=True):

@@ -739,6 +739,97 @@ def case_rowland(marxs, rng):
     save('rowland', **arrays)
 
 
+def case_tolerancing(marxs, rng):
+    """Tolerancing drivers (design/tolerancing.py, design/uncertainties.py) and the figure-of-merit class they
+    are used with (analysis/gratings.py CaptureResAeff): facet pos4d after each mutator (np.random seeded for
+    the Gaussian ones), the 6-dof parameter lists, CaptureResAeff on a synthetic event list, and a full
+    run_tolerances loop (moveglobal of a grating array in front of a detector, single-order selector so the
+    trace is deterministic)."""
+    import astropy.units as u
+    from astropy.table import Table
+    from marxs.design import RowlandTorus, GratingArrayStructure
+    from marxs.design import tolerancing as tol
+    from marxs.optics import FlatGrating, OrderSelector, FlatDetector
+    from marxs.simulator import Sequence
+    from marxs.analysis.gratings import CaptureResAeff, CaptureResAeff_CCDgaps, resolvingpower_from_photonlist
+    arrays = {}
+    torus = RowlandTorus(0.5, 0.5, position=[1.5, 0, -3])        # design/tests/test_tolerancing.py:36-48
+
+    def gsa():
+        return GratingArrayStructure(rowland=torus, d_element=[0.1, 0.1], radius=[0.1, .2], elem_class=FlatGrating,
+                                     elem_args={'zoom': 0.2, 'd': 0.002, 'order_selector': OrderSelector([1])})
+
+    def stack(g):
+        return np.array([e.pos4d for e in g.elements])
+    arrays['gsa_pos4d'] = stack(gsa())
+    g = gsa()
+    np.random.seed(1234)
+    tol.wiggle(g, dx=0.01, dy=0.02, dz=0.03, rx=0.01, ry=0.02, rz=0.03)
+    arrays['wiggle_pos4d'] = stack(g)
+    g = gsa()
+    tol.moveglobal(g, dx=0.1, dy=-0.2, dz=0.3, rx=0.1, ry=-0.2, rz=0.3)
+    arrays['moveglobal_pos4d'] = stack(g)
+    g = gsa()
+    tol.moveindividual(g, dx=0.1, dy=-0.2, dz=0.3, rx=0.1, ry=-0.2, rz=0.3)
+    arrays['moveindividual_pos4d'] = stack(g)
+    det = FlatDetector(zoom=[1, 100, 50], position=[3., 2., 1.])
+    tol.moveelem(det, dx=1., dz=5., ry=0.3)
+    tol.moveelem(det, dy=2., rx=-0.2, rz=0.1)                       # relative to pos4d_orig, not cumulative
+    arrays['moveelem_pos4d'] = det.geometry.pos4d
+    np.random.seed(99)
+    g = gsa()
+    tol.varyperiod(g.elements, 2e-3, 1e-4)
+    arrays['varyperiod_d'] = np.array([e._d for e in g.elements])
+    cglob, cind = tol.generate_6d_wigglelist([0., .1, .2, .4] * u.cm, [0., 2., 5., 10.] * u.arcmin)
+    names = ['dx', 'dy', 'dz', 'rx', 'ry', 'rz']
+    arrays['wigglelist_global'] = np.array([[d[k] for k in names] for d in cglob])
+    arrays['wigglelist_individual'] = np.array([[d[k] for k in names] for d in cind])
+    # figure of merit on a synthetic event list
+    n = 6000
+    order = rng.integers(-3, 4, n).astype(float)
+    order[rng.random(n) < 0.1] = np.nan
+    det_x = order * 12.5 + rng.normal(0, 0.05, n) + (rng.random(n) < 0.02) * rng.normal(0, 3., n)
+    det_x[rng.random(n) < 0.05] = np.nan
+    prob = rng.random(n) * (rng.random(n) > 0.1)
+    ccd = rng.integers(-1, 4, n)
+    ev = Table({'order': order, 'det_x': det_x, 'probability': prob, 'CCD_ID': ccd})
+    arrays.update(ev_order=order, ev_det_x=det_x, ev_probability=prob, ev_ccd=ccd)
+    orders = np.array([-3, -2, -1, 0, 1, 2, 3, 7])
+    arrays['ev_orders'] = orders
+    for tag, cap in (('cap', CaptureResAeff(A_geom=5., orders=orders)),
+                     ('capz', CaptureResAeff(A_geom=5., orders=orders, zeropos=0.3)),
+                     ('gaps', CaptureResAeff_CCDgaps(A_geom=5., orders=orders))):
+        out = cap(ev, n_photons=8000)
+        for k, v in out.items():
+            arrays[tag + '_' + k] = np.ma.filled(np.ma.asarray(v, dtype=float), np.nan)
+    ok = np.isfinite(det_x)
+    res, pos, std = resolvingpower_from_photonlist(ev[ok], orders, col='det_x')
+    arrays.update(rp_res=res, rp_pos=pos, rp_std=std)
+    # a tolerancing loop: 40 gratings 12 m from a detector, moved as a whole
+    n = 20000
+    p = make_photons(rng, n, spread=0.0, lateral=1., x0=13000., e_lo=0.5, e_hi=0.5)
+    p['pos'][:, 1:3] = rng.uniform(-250., 250., (n, 2))
+    focus = np.array([0., 0., 0.])
+    d = focus - p['pos'][:, :3]
+    p['dir'][:, :3] = d / np.linalg.norm(d, axis=1)[:, None]
+    p['probability'] = 1.
+    pos = [[12000., y, z] for y in np.arange(-200, 201, 100.) for z in np.arange(-200, 201, 100.)]
+    from marxs.simulator import Parallel
+    gratings = Parallel(elem_class=FlatGrating, elem_pos={'position': pos}, id_col='facet',
+                        elem_args={'d': 2e-3, 'zoom': [1, 40., 40.], 'order_selector': OrderSelector([1])})
+    detector = FlatDetector(zoom=[1, 500, 500], pixsize=0.024)
+    instrum = Sequence(elements=[gratings, detector])
+    pars = [{'dx': 0., 'rz': 0.}, {'dx': 30., 'rz': 0.}, {'dx': 0., 'rz': 0.002}, {'dx': -50., 'rz': -0.004, 'ry': 0.01}]
+    cap = CaptureResAeff(A_geom=2., orders=np.array([0, 1]), dispersion_coord='det_x', zeropos=0.)
+    out = tol.run_tolerances(p, instrum, tol.moveglobal, gratings, pars, cap)
+    arrays.update({'loop_' + k: np.asarray(p[k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability')})
+    arrays['loop_grating_pos'] = np.array(pos)
+    arrays['loop_pars'] = np.array([[q.get(k, 0.) for k in names] for q in pars])
+    for k in ('Aeff0', 'Aeffgrat', 'Aeff', 'Rgrat', 'R'):
+        arrays['loop_' + k] = np.array([np.ma.filled(np.ma.asarray(o[k], dtype=float), np.nan) for o in out])
+    save('tolerancing', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -748,7 +839,7 @@ def main():
     for i, case in enumerate([case_intersect, case_parallel_transport, case_gratings,
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
-                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland]):
+                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

@@ -90,45 +90,49 @@ def c1(scale, steps):
                  lambda o: dict(on_detector=float(torch.isfinite(o['det_x']).double().mean())))
 
 
-def c3_setup(n, seed=3):
-    """CAT-grating spectrograph: lens + scatter -> ~560 CATL1L2Stack facets on a sphere around the focus
-    -> strip of 16 CCDs; efficiency table 135 x 25 x 28 (synthetic numbers, real shape)."""
+def c3_elements(seed=3):
+    """CAT-grating spectrograph: lens + scatter -> 561 CATL1L2Stack facets on a Rowland torus -> strip of
+    16 CCDs; efficiency table 135 x 25 x 28 (synthetic numbers, real shape).  Host only (no GPU needed)."""
     rng = np.random.default_rng(seed)
     wave = np.linspace(0.5, 7.5, 135)
     theta = np.deg2rad(np.linspace(0.2, 4.0, 25))
     orders = np.arange(-20, 8)[::-1]
     # blazed efficiencies: a Gaussian in order around m0 = -2 sin(theta) d / lambda (d = 200 nm) + some zero order
     m0 = -2. * np.sin(theta)[None, :, None] * 200. / wave[:, None, None]
-    prob = 0.3 * np.exp(-0.5 * ((orders[None, None, :] - m0) / 1.2) ** 2) + 0.03 * (orders == 0)[None, None, :]
+    # amplitude chosen so that the summed probability stays below 1 in every cell (0.25 x 3.01 x 1.1 + 0.033 = 0.86)
+    prob = 0.25 * np.exp(-0.5 * ((orders[None, None, :] - m0) / 1.2) ** 2) + 0.03 * (orders == 0)[None, None, :]
     prob = prob * rng.uniform(0.9, 1.1, prob.shape)
     sel = mitsnl.InterpolateEfficiencyTable(wave, theta, prob, orders)
-    ys, zs = np.meshgrid(np.arange(-480, 481, 30.), np.arange(300, 801, 30.))
-    c, s = np.cos(np.deg2rad(1.91)), np.sin(np.deg2rad(1.91))
-    blaze = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.]])
-    pos4ds = []
-    for y, z in zip(ys.ravel(), zs.ravel()):
-        if not (300. <= np.hypot(y, z) <= 830.):
-            continue
-        x = np.sqrt(6000. ** 2 - y ** 2 - z ** 2)
-        nrm = np.array([x, y, z]) / 6000.
-        ey = np.cross([0, 0, 1.], nrm)
-        ey /= np.linalg.norm(ey)
-        R = np.column_stack([nrm, ey, np.cross(nrm, ey)])
-        from marxs_b200.affines import compose
-        pos4ds.append(compose([x, y, z], R @ blaze, [1., 13.5, 13.5]))
-    det_pos = [[0., y, 0.] for y in np.arange(-50, 700, 49.652)]
+    # facet placement as SURVEY 8(d): 561 facets on RowlandTorus(6000, 6000), blazed by 1.91 deg; 16 CCDs on the
+    # Rowland circle (marxs_b200.design.rowland, pinned to the reference's placement in tests/test_rowland.py)
+    from marxs_b200.design import RowlandTorus, GratingArrayStructure, RectangularGrid
+    from marxs_b200.affines import axangle2mat
+    rt = RowlandTorus(6000., 6000.)
+    gas = GratingArrayStructure(rowland=rt, d_element=[30., 30.], radius=[300., 500.], elem_class=mitsnl.CATL1L2Stack,
+                                elem_args={'zoom': [1, 13.5, 13.5], 'order_selector': sel,
+                                           'orientation': axangle2mat([0, 0, 1], np.deg2rad(1.91))})
+    det = RectangularGrid(rowland=rt, d_element=[49.652, 49.652], y_range=[-50, 700], elem_class=optics.FlatDetector,
+                          elem_args={'zoom': [1, 24.576, 12.288], 'pixsize': 0.024}, id_col='CCD_ID', guess_distance=25.)
+    n_facets = len(gas.elements)
     elements = [
         optics.FlatStack(position=[12000., 0, 0], zoom=[1, 2000, 2000], elements=[optics.PerfectLens, optics.RadialMirrorScatter],
                          keywords=[{'focallength': 12000.}, {'inplanescatter': 1e-5, 'perpplanescatter': 1e-6}]),
-        simulator.Parallel(elem_class=mitsnl.CATL1L2Stack, elem_pos=pos4ds, id_col='facet', elem_args=dict(order_selector=sel)),
-        simulator.Parallel(elem_class=optics.FlatDetector, elem_pos={'position': det_pos},
-                           elem_args={'pixsize': 0.024, 'zoom': [1, 24.576, 12.288]}, id_col='CCD_ID')]
+        gas, det]
+    return elements, n_facets
+
+
+def c3_setup(n, seed=3):
+    """The C3 instrument and n photons on the lens, resident on the GPU."""
+    elements, n_facets = c3_elements(seed)
     g = torch.Generator(device='cuda').manual_seed(5)
     b = mb.PhotonBatch(device='cuda')
     pos = b.new_column('pos', torch.float64, vector=True, n=n)
     pos[0] = 12100.
-    pos[1] = (torch.rand(n, device='cuda', generator=g, dtype=torch.float64) * 2 - 1) * 960.
-    pos[2] = 600. + torch.rand(n, device='cuda', generator=g, dtype=torch.float64) * 1000.
+    # the facets sit 4-20 mm behind the lens (RowlandTorus(6000, 6000) reaches x = 12000): an annulus [285, 515] mm
+    rad = torch.sqrt(285. ** 2 + torch.rand(n, device='cuda', generator=g, dtype=torch.float64) * (515. ** 2 - 285. ** 2))
+    phi = torch.rand(n, device='cuda', generator=g, dtype=torch.float64) * (2 * np.pi)
+    pos[1] = rad * torch.cos(phi)
+    pos[2] = rad * torch.sin(phi)
     pos[3] = 1.
     d = b.new_column('dir', torch.float64, fill=0., vector=True)
     d[0] = -1.
@@ -136,7 +140,7 @@ def c3_setup(n, seed=3):
     p[1] = 1.
     b.new_column('energy', torch.float64)[...] = 0.3 + 1.2 * torch.rand(n, device='cuda', generator=g, dtype=torch.float64)
     b.new_column('probability', torch.float64, fill=1.)
-    return elements, b, len(pos4ds)
+    return elements, b, n_facets
 
 
 def c3(scale, steps):
