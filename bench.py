@@ -350,7 +350,7 @@ def run_engine(args):
             mhost.trace_host(inst_h, host_in, out=host_out, program=prog_h, check=True)
         barrier()
         e2e_s = mdist.max_over_ranks(time.perf_counter() - t0, device)
-        h2d, d2h = mhost.h2d_d2h_bytes(prog_h, ne)
+        h2d, d2h = mhost.h2d_d2h_bytes(prog_h, ne, in_place=False)
         e2e = dict(value=world * ne * ke / e2e_s, unit='photons/s', h2d_bytes_per_step=h2d * world,
                    d2h_bytes_per_step=d2h * world, steps=ke, photons_per_gpu_per_step=ne,
                    ms_per_step=1e3 * e2e_s / ke,

@@ -101,7 +101,8 @@ typedef struct MxbColumns {
 #define MXB_OP_ARRAY_BEGIN  3  /* simulator.py:42-49 over a Parallel: pg: array header (below). Body ops follow until ARRAY_END      */
 #define MXB_OP_ARRAY_END    4
 #define MXB_OP_BAFFLE       5  /* baffles.py:25-28: pos = interpos on hit, probability = 0 on miss                                  */
-#define MXB_OP_LENS         6  /* mirror.py:53-82 PerfectLens: params P[3] f                                                        */
+#define MXB_OP_LENS         6  /* mirror.py:53-82 PerfectLens: params P[3] f ; flags bit0: + nx ny table (reflectivity R(E, angle/4)^2,
+                                * table = x[nx] y[ny] z[nx][ny] in the global part of the blob, bilinear, clamped)                  */
 #define MXB_OP_RSCATTER     7  /* scatter.py:49-77 RadialMirrorScatter: params center[3] sig_in sig_perp; s0,s1 normals; c0,c1 cols   */
 #define MXB_OP_GSCATTER     8  /* scatter.py:109-145 RandomGaussianScatter: params sigma; s0 normal s1 uniform; c0 col.
                                   flags bit0: L2Diffraction (mitsnl/catgrating.py:262-285): params innerfree,

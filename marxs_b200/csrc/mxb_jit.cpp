@@ -97,6 +97,7 @@ struct Gen {
     bool born = false;            // header flag: the program creates the photons (no loads)
     int threads = 640;            // CTA size the kernel is compiled for
     bool pipe_wanted = true, pipe = false;
+    bool idx64 = false;      // photon indices as long long (launches of >= 2^31 photons)
     std::vector<Op> ops;
     // array context
     bool in_array = false;
@@ -292,7 +293,8 @@ struct Gen {
             out("            if (ph.hit) ph.pos = ph.ip; else ph.prob = 0.0;");
             break;
         case MXB_OP_LENS:
-            out("            if (ph.hit) op_lens(ph, %s);", PR(o, 4).c_str());
+            if (o.flags & 1) out("            if (ph.hit) op_lens_refl(st_sm, ph, %s, P.prog);", PR(o, 7).c_str());
+            else out("            if (ph.hit) op_lens(ph, %s);", PR(o, 4).c_str());
             break;
         case MXB_OP_RSCATTER: {
             const std::string p = PR(o, 5);
@@ -601,6 +603,10 @@ struct Gen {
         out("#ifndef JIT_THREADS\n#define JIT_THREADS 640\n#endif");
         out("#ifndef JIT_MINBLOCKS\n#define JIT_MINBLOCKS 1\n#endif");
         out("#ifndef JIT_PREFETCH\n#define JIT_PREFETCH 1\n#endif");
+        // photon index type: launches are sliced below 2^31 photons (mxbjit::launch), so plane addresses are one
+        // IMAD.WIDE.U32 off the pointer in the constant bank instead of 64-bit shift/add chains
+        out("#ifndef JIT_IDX32\n#define JIT_IDX32 %d\n#endif", idx64 ? 0 : 1);
+        out("#if JIT_IDX32\ntypedef unsigned idx_t;\n#else\ntypedef long long idx_t;\n#endif");
         out("#define JIT_STAGE_WORDS %d", need_blob && staged ? stage_words : 0);
         {   // per-warp TMA input pipeline (mxb_ops.cuh InputPipe) when its buffers fit beside the staged program
             const long long stage_b = need_blob && staged ? (long long)stage_words * 8 : 0;
@@ -618,8 +624,8 @@ struct Gen {
         out("    const double* d[%d];", (int)std::max<size_t>(dmap.size(), 1));
         out("    double s[%d];", (int)std::max<size_t>(smap.size(), 1));
         out("};");
-        out("MXB_DEV void jput(double* col, long long i, bool cond, bool hit, double v) { if (cond) st_global(col + i, hit ? v : nan64()); }");
-        out("MXB_DEV void jput_id(long long* col, long long i, bool cond, bool hit, long long v) { if (cond) st_global(col + i, hit ? v : -1LL); }");
+        out("MXB_DEV void jput(double* col, idx_t i, bool cond, bool hit, double v) { if (cond) st_global(col + i, hit ? v : nan64()); }");
+        out("MXB_DEV void jput_id(long long* col, idx_t i, bool cond, bool hit, long long v) { if (cond) st_global(col + i, hit ? v : -1LL); }");
         out("extern \"C\" __global__ void __launch_bounds__(JIT_THREADS, JIT_MINBLOCKS)");
         out("mxb_jit_kernel(const __grid_constant__ JitParams P) {");
         out("    __shared__ unsigned long long st_sm[MXB_ST_OPHITS];");
@@ -659,7 +665,8 @@ struct Gen {
             if (t == MXB_OP_PLANE || t == MXB_OP_LOADHIT || t == MXB_OP_APERTURE || t == MXB_OP_ARRAY_BEGIN || t == MXB_OP_CYLINDER) out("    unsigned h%d = 0u;", pc);
         }
         out("    const double kNaN = nan64();");
-        out("    const long long stride = (long long)gridDim.x * JIT_THREADS;");
+        out("    const idx_t stride = (idx_t)gridDim.x * JIT_THREADS;");
+        out("    const idx_t n_ph = (idx_t)P.n;");
         out("    const int lane = tid & 31;");
         out("    const bool tma_ok = JIT_PIPE && (P.flags & 1);   // host: all 11 core planes are 16-byte aligned");
         out("    InputPipe pipe;");
@@ -670,11 +677,11 @@ struct Gen {
         out("    pipe.buf = nullptr;");
         out("    pipe.bar = nullptr;");
         out("#endif");
-        out("    long long base = (long long)blockIdx.x * JIT_THREADS + (tid & ~31);   // whole warps");
+        out("    idx_t base = (idx_t)blockIdx.x * JIT_THREADS + (tid & ~31);   // whole warps");
         out("    pipe_start(pipe, P.in, base, P.n, tma_ok, lane);");
-        out("    for (; base < P.n; base += stride) {");
-        out("        const long long i = base + lane;");
-        out("        const bool active = i < P.n;");
+        out("    for (; base < n_ph; base += stride) {");
+        out("        const idx_t i = base + lane;");
+        out("        const bool active = i < n_ph;");
         out("        const unsigned long long gid = (unsigned long long)(P.id0 + i);");
         out("        (void)gid;");
         out("        Photon ph;");
@@ -682,11 +689,22 @@ struct Gen {
             out("        ph.pos = ph.dir = ph.pol = V3{kNaN, kNaN, kNaN};   // born by the program: nothing is read");
             out("        ph.energy = ph.prob = kNaN;");
         } else {
+            out("#if JIT_PIPE");
             out("        pipe_load(pipe, P.in, base, base + stride, P.n, tma_ok, lane, active, ph.pos, ph.dir, ph.pol, ph.energy, ph.prob);");
+            out("#else");
+            out("        {   // lanes past the end of the batch re-read the last photon (their results are never stored)");
+            out("            const idx_t il = active ? i : n_ph - 1;");
+            out("            ph.pos = V3{P.in[0][il], P.in[1][il], P.in[2][il]};");
+            out("            ph.dir = V3{P.in[3][il], P.in[4][il], P.in[5][il]};");
+            out("            ph.pol = V3{P.in[6][il], P.in[7][il], P.in[8][il]};");
+            out("            ph.energy = P.in[9][il];");
+            out("            ph.prob = P.in[10][il];");
+            out("        }");
+            out("#endif");
         }
         out("        photon_loaded(ph);");
         out("#if JIT_PREFETCH && !%d", born ? 1 : 0);
-        out("        if (i + stride < P.n) {   // next group's inputs -> L2 while this one is traced");
+        out("        if (i + stride < n_ph) {   // next group's inputs -> L2 while this one is traced");
         out("#pragma unroll");
         out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.in[k] + i + stride));");
         out("        }");
@@ -721,7 +739,11 @@ struct Gen {
 
 int env_int(const char* name, int dflt);
 
+// launches of 2^31 photons or more need 64-bit photon indices (set by launch() around its init_gen calls)
+thread_local bool tl_idx64 = false;
+
 void init_gen(Gen& g, const double* prog_host, size_t words, const MxbColumns* cols, bool emit) {
+    g.idx64 = tl_idx64;
     g.threads = env_int("MXB_JIT_THREADS", 0) > 0 ? env_int("MXB_JIT_THREADS", 0) : 640;
     g.pipe_wanted = env_int("MXB_JIT_PIPE", 0) != 0;
     g.W = prog_host;
@@ -963,6 +985,7 @@ int get_kernel(Gen& keygen, const double* prog_host, size_t words, const MxbColu
                Kernel** out, std::string* err) {
     std::string key = keygen.key;
     key += options_tag(fast_build);
+    if (tl_idx64) key += " i64";
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) { *out = it->second.get(); return MXB_OK; }
@@ -1048,6 +1071,10 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     (void)n_ops; (void)stage_words;
     *unavailable = false;
     if (!nvrtc().h) { *unavailable = true; *err = "NVRTC unavailable: " + nvrtc().why; return MXB_EJIT; }
+    struct Idx64Scope {
+        explicit Idx64Scope(bool v) { tl_idx64 = v; }
+        ~Idx64Scope() { tl_idx64 = false; }
+    } idx_scope(n >= (1LL << 31));
     Gen kg;
     init_gen(kg, prog_host, words, cols, false);
     if (!kg.run()) { *err = "specialisation failed: " + kg.err; return MXB_EJIT; }

@@ -250,6 +250,30 @@ MXB_DEV void op_lens(Photon& ph, PP p) {
     ph.unit = true;
 }
 
+// mirror.py:68-81  PerfectLens with a reflectivity_interpolator: probability *= R(energy, angle / 4)^2,
+// angle = arccos|d_new . d_old|, R = RectBivariateSpline(kx=ky=1).ev = bilinear with the query clamped to
+// the table.  params: P[3] f nx ny table ; table (global) = x[nx] y[ny] z[nx][ny]
+template <typename PP>
+MXB_DEV void op_lens_refl(unsigned long long* st_sm, Photon& ph, PP p, const double* gprog) {
+    const V3 nd = normalize_unless(ph.unit, ph.dir);
+    op_lens(ph, p);
+    const double angle = m_acos(fabs(dot(ph.dir, nd)));
+    const int nx = (int)p[4], ny = (int)p[5];
+    const PRef<false> xk{gprog, (int)p[6]};
+    const PRef<false> yk = xk + nx;
+    const PRef<false> z = yk + ny;
+    const double xq = fmin(fmax(ph.energy, xk[0]), xk[nx - 1]);
+    const double yq = fmin(fmax(angle / 4, yk[0]), yk[ny - 1]);
+    const int i = bracket(xk, nx, xq), j = bracket(yk, ny, yq);
+    const double tx = (xq - xk[i]) / (xk[i + 1] - xk[i]);
+    const double ty = (yq - yk[j]) / (yk[j + 1] - yk[j]);
+    const double a00 = z[i * ny + j], a10 = z[(i + 1) * ny + j], a01 = z[i * ny + j + 1], a11 = z[(i + 1) * ny + j + 1];
+    const double f0 = a00 + tx * (a10 - a00);
+    const double f1 = a01 + tx * (a11 - a01);
+    const double r = f0 + ty * (f1 - f0);
+    mul_prob(st_sm, ph, r * r);
+}
+
 // scatter.py:49-77  params: center[3] sig_in sig_perp ; z0, z1 standard normal draws
 template <typename PP>
 MXB_DEV void op_rscatter(Photon& ph, PP p, double z0, double z1, double& a, double& b) {

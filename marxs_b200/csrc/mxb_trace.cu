@@ -269,7 +269,10 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 break;
             }
             case MXB_OP_LENS: {
-                if (ph.hit) op_lens(ph, pr);
+                if (ph.hit) {
+                    if (op.flags & 1) op_lens_refl(st_sm, ph, pr, P.prog);
+                    else op_lens(ph, pr);
+                }
                 break;
             }
             case MXB_OP_RSCATTER: {

@@ -135,7 +135,8 @@ def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, 
         for name in ('energy', 'probability'):
             if name not in out:
                 out.new_column(name, np.float64)
-        out.planes('energy')[...] = table.planes('energy')
+        # (the energy plane of ``out`` is filled by the library: it comes back from the device with the
+        #  other results, which is cheaper than an 8 B/photon host memcpy here)
     keep = None
     if draws is not None:
         keep = [np.ascontiguousarray(d, dtype=np.float64) if d is not None else None
@@ -159,8 +160,9 @@ def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, 
     return dst, prog
 
 
-def h2d_d2h_bytes(prog, n):
-    """Bytes moved per call by mxb_trace_host for n photons (counted from the planes copied)."""
+def h2d_d2h_bytes(prog, n, in_place=True):
+    """Bytes moved per call by mxb_trace_host for n photons (counted from the planes copied).
+    Out of place (``out=`` another table) the unchanged energy plane is brought back too."""
     h2d = 11 * 8 * n
-    d2h = (10 + len(prog.out_f64) + len(prog.out_i64)) * 8 * n
+    d2h = (10 + (0 if in_place else 1) + len(prog.out_f64) + len(prog.out_i64)) * 8 * n
     return h2d, d2h

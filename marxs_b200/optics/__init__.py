@@ -2,7 +2,7 @@
 from .aperture import RectangleAperture, CircleAperture, MultiAperture
 from .detector import FlatDetector, CircularDetector
 from .grating import FlatGrating, CATGrating, OrderSelector, EfficiencyFile
-from .mirror import PerfectLens
+from .mirror import PerfectLens, ReflectivityTable
 from .baffles import Baffle, CircularBaffle
 from .scatter import RadialMirrorScatter, RandomGaussianScatter
 from .filter import EnergyFilter, GlobalEnergyFilter, Tabulated1D

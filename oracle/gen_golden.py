@@ -830,6 +830,30 @@ def case_tolerancing(marxs, rng):
     save('tolerancing', **arrays)
 
 
+def case_lens_reflectivity(marxs, rng):
+    """PerfectLens with a reflectivity_interpolator (mirror.py:31-36,68-81): the reference's own
+    RectBivariateSpline(kx=ky=1), queries inside the table, clamped below / above it, and strongly
+    off-axis rays (angle / 4 up to ~0.1 rad)."""
+    from marxs.optics import PerfectLens
+    from scipy.interpolate import RectBivariateSpline
+    n = 2000
+    egrid = np.concatenate([np.linspace(0.4, 2., 9), np.geomspace(2.5, 7., 6)])     # non-uniform on purpose
+    agrid = np.linspace(0.002, 0.08, 23)
+    eg, ag = np.meshgrid(egrid, agrid, indexing='ij')
+    refl = np.exp(-ag * eg * 9.) * (0.6 + 0.4 * np.cos(eg))
+    refl = np.clip(refl, 0., 1.)
+    interp = RectBivariateSpline(egrid, agrid, refl, kx=1, ky=1)
+    p = make_photons(rng, n, spread=0.25, x0=300., lateral=40., e_lo=0.2, e_hi=9.)
+    pos4d = rand_pos4d(rng, zoom=(1., 80., 80.), shift=2.)
+    lens = PerfectLens(focallength=150., d_center_optical_axis=-3., pos4d=pos4d, reflectivity_interpolator=interp)
+    inp = inputs_dict(p)
+    out = lens(p)
+    arrays = {'refl_' + k: v for k, v in inp.items()}
+    arrays.update({'refl_' + k: v for k, v in table_to_dict(out).items()})
+    arrays.update(refl_pos4d=pos4d, refl_egrid=egrid, refl_agrid=agrid, refl_table=refl)
+    save('lens_reflectivity', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -839,7 +863,8 @@ def main():
     for i, case in enumerate([case_intersect, case_parallel_transport, case_gratings,
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
-                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing]):
+                              case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing,
+                              case_lens_reflectivity]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

@@ -556,12 +556,15 @@ class NonParallelCATGrating(CATGrating):
 # mirrors, scatter  (optics/mirror.py, optics/scatter.py)
 # ---------------------------------------------------------------------------
 class PerfectLens(Element):
-    """mirror.py:12-82 (default reflectivity = 1)"""
+    """mirror.py:12-82.  ``reflectivity`` = None (the reference's default, R = 1) or a
+    (energy_grid, angle_grid, table) triple standing for RectBivariateSpline(kx=ky=1)
+    (bilinear, clamped: ``interp_bilinear_clamped``)."""
     loc_coos_name = ['mirror_x', 'mirror_y']
 
     def __init__(self, **kwargs):
         self.focallength = kwargs.pop('focallength')
         self.d_center_optax = kwargs.pop('d_center_optical_axis', 0)
+        self.reflectivity = kwargs.pop('reflectivity', None)
         super().__init__(**kwargs)
 
     def specific_process_photons(self, photons, hit, interpos, loc, draws):
@@ -573,8 +576,16 @@ class PerfectLens(Element):
         t = focus - interpos[hit, :3]
         newdir = e2h(normalize3(t), 0)
         pol = parallel_transport(dir_old, newdir, photons['polarization'][hit])
-        return {'dir': newdir, 'polarization': pol,
-                'probability': np.ones(int(hit.sum())) ** 2}
+        if self.reflectivity is None:
+            refl = np.ones(int(hit.sum()))
+        else:
+            # mirror.py:68-81: angle between the new direction and the normalised old one
+            d = newdir[:, 0] * nd[:, 0] + newdir[:, 1] * nd[:, 1] + newdir[:, 2] * nd[:, 2]
+            angle = np.arccos(np.abs(d))
+            xk, yk, tab = self.reflectivity
+            refl = interp_bilinear_clamped(np.asarray(xk, float), np.asarray(yk, float), np.asarray(tab, float),
+                                           photons['energy'][hit], angle / 4)
+        return {'dir': newdir, 'polarization': pol, 'probability': refl ** 2}
 
 
 def axangle_rotate_T(axis, angle, v):

@@ -265,6 +265,29 @@ def test_golden_gratings(tag):
     assert_cols(out, g, tag + '_', exact=('order',))
 
 
+def test_golden_lens_reflectivity():
+    """PerfectLens with the reference's RectBivariateSpline(kx=ky=1) reflectivity (mirror.py:68-81): queries
+    inside, below and above the table; also the reference's own known answer (test_mirror.py:62-80)."""
+    g = load('lens_reflectivity')
+    lens = mo.PerfectLens(focallength=150., d_center_optical_axis=-3., pos4d=g['refl_pos4d'],
+                          reflectivity=(g['refl_egrid'], g['refl_agrid'], g['refl_table']))
+    out = lens(table_from(g, 'refl_'))
+    assert_cols(out, g, 'refl_')
+    hit = np.isfinite(out['mirror_x'])
+    assert hit.mean() > 0.3 and out["probability"][hit].min() < 0.3 and out["probability"][hit].max() > 0.3
+    e_in = g['refl_in_energy'][hit]
+    assert (e_in < g['refl_egrid'][0]).any() and (e_in > g['refl_egrid'][-1]).any()      # clamped queries are covered
+    # reference known answer: exp(-sqrt((x/2)^2 + y^2)) on a 100 x 100 grid, 1 keV photon reflected at 0 deg
+    xarr = np.linspace(-3, 3, 100)
+    xg, yg = np.meshgrid(xarr, xarr, indexing='ij')
+    lens = mo.PerfectLens(focallength=123., reflectivity=(xarr, xarr, np.exp(-np.sqrt((xg / 2) ** 2 + yg ** 2))))
+    t = mo.PhotonTable(pos=np.array([[1., 0, 0, 1]]), dir=np.array([[-1., 0, 0, 0]]), energy=np.ones(1),
+                       polarization=np.array([[0., 1, 0, 0]]), probability=np.ones(1))
+    out = lens(t)
+    assert np.allclose(out['probability'], 0.367205)
+    assert np.allclose(out['polarization'], [0, 1, 0, 0])
+
+
 def test_golden_lens_scatter():
     g = load('lens_scatter')
     lens = mo.PerfectLens(focallength=250., d_center_optical_axis=7.5, pos4d=g['lens_pos4d'])

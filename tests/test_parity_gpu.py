@@ -319,6 +319,73 @@ def test_lens_scatter_golden(mode):
                                                {'filterfunc': 0.66}]), [g['stack_z0'], g['stack_z1']])
 
 
+def test_lens_reflectivity(mode):
+    """PerfectLens(reflectivity_interpolator=...) (mirror.py:68-81) on the device: against the unmodified
+    reference (tests/golden/lens_reflectivity.npz, RectBivariateSpline k=1 given as such), against the
+    oracle on a bigger batch, inside a FlatStack, and the reference's own known answer (test_mirror.py:62-80)."""
+    from scipy.interpolate import RectBivariateSpline
+    from marxs_b200 import optics
+    mb = _mb()
+    g = load('lens_reflectivity')
+    spline = RectBivariateSpline(g['refl_egrid'], g['refl_agrid'], g['refl_table'], kx=1, ky=1)
+    el = optics.PerfectLens(focallength=150., d_center_optical_axis=-3., pos4d=g['refl_pos4d'], reflectivity_interpolator=spline)
+    t = mo.PhotonTable((k, g['refl_in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+    out = el(mb.PhotonBatch(t, device='cuda')).to_numpy()
+    names = [k[len('refl_out_'):] for k in g if k.startswith('refl_out_')]
+    assert set(names) == set(out.keys())
+    for c in names:
+        np.testing.assert_allclose(out[c], g['refl_out_' + c], rtol=1e-12, atol=1e-11, equal_nan=True, err_msg=c)
+    # oracle, bigger batch, table object, standalone and as a FlatStack layer followed by a scatter layer
+    rng = np.random.default_rng(SEED + 40)
+    n = 30000
+    pos4d = rand_pos4d(rng, zoom=(1., 60., 60.))
+    table = make_photons(rng, n, spread=0.2)
+    egrid, agrid = np.linspace(0.5, 6., 12), np.geomspace(1e-3, 0.1, 17)
+    tab = rng.uniform(0.2, 1., (12, 17))
+    rt = optics.ReflectivityTable(egrid, agrid, tab)
+
+    def check_probability(got, want):
+        # angle = arccos|d_new . d_old| is ill-conditioned near 0 (like blaze): one ulp of the cosine moves it by
+        # 1.1e-16 / sin(angle).  Bound = change of R^2 when the cosine moves by +-4 ulp, + 1e-11 relative.
+        g, w = got.to_numpy()['probability'], want['probability']
+        hit = np.isfinite(want['mirror_x'])
+        d_old = table['dir'][hit, :3] / np.linalg.norm(table['dir'][hit, :3], axis=1)[:, None]
+        cosang = np.abs(np.sum(want['dir'][hit, :3] * d_old, axis=1))
+        r_lo = rt(table['energy'][hit], np.arccos(np.clip(cosang + 4.5e-16, 0, 1)) / 4) ** 2
+        r_hi = rt(table['energy'][hit], np.arccos(np.clip(cosang - 4.5e-16, 0, 1)) / 4) ** 2
+        tol = np.abs(r_hi - r_lo) * table['probability'][hit] + 1e-11 * np.abs(w[hit])
+        assert np.all(np.abs(g[hit] - w[hit]) <= tol), (np.abs(g[hit] - w[hit]) - tol).max()
+        assert np.array_equal(g[~hit], w[~hit])
+        assert (tol < 1e-9).all() and np.median(tol / w[hit]) < 2e-11          # the bound is tight, not a blank cheque
+
+    got, want = run_pair(optics.PerfectLens(focallength=200., pos4d=pos4d, reflectivity_interpolator=rt),
+                         mo.PerfectLens(focallength=200., pos4d=pos4d, reflectivity=(egrid, agrid, tab)), table,
+                         rtol=1e-11, skip=('probability',))
+    check_probability(got, want)
+    got, want = run_pair(optics.FlatStack(pos4d=pos4d, elements=[optics.PerfectLens, optics.RadialMirrorScatter],
+                                          keywords=[{'focallength': 200., 'reflectivity_interpolator': rt},
+                                                    {'inplanescatter': 3e-4, 'perpplanescatter': 1e-4}]),
+                         mo.FlatStack(pos4d=pos4d, elements=[mo.PerfectLens, mo.RadialMirrorScatter],
+                                      keywords=[{'focallength': 200., 'reflectivity': (egrid, agrid, tab)},
+                                                {'inplanescatter': 3e-4, 'perpplanescatter': 1e-4}]),
+                         table, [rng.standard_normal(n), rng.standard_normal(n)], rtol=1e-11, skip=('probability',))
+    np.testing.assert_allclose(got.to_numpy()['probability'], want['probability'], rtol=1e-9)   # same conditioning, loose
+    # the reference's test: silly reflectivity function, reflection at 0 deg
+    xarr = np.linspace(-3, 3, 100)
+    xg, yg = np.meshgrid(xarr, xarr, indexing='ij')
+    lens = optics.PerfectLens(focallength=123., reflectivity_interpolator=RectBivariateSpline(
+        xarr, xarr, np.exp(-np.sqrt((xg / 2) ** 2 + yg ** 2)), kx=1, ky=1))
+    one = mo.PhotonTable(pos=np.array([[1., 0, 0, 1]]), dir=np.array([[-1., 0, 0, 0]]), energy=np.ones(1),
+                         polarization=np.array([[0., 1, 0, 0]]), probability=np.ones(1))
+    out = lens(mb.PhotonBatch(one, device='cuda')).to_numpy()
+    assert np.allclose(out['energy'], 1)
+    assert np.allclose(out['polarization'], [0, 1, 0, 0])
+    assert np.allclose(out['probability'], 0.367205)
+    # anything that is not a bilinear table cannot run on the device: loud, not silent
+    with pytest.raises(TypeError):
+        optics.PerfectLens(focallength=1., reflectivity_interpolator=lambda e, a, grid=False: e)(mb.PhotonBatch(one, device='cuda'))
+
+
 def test_detector_baffle_vs_oracle(mode):
     from marxs_b200 import optics
     rng = np.random.default_rng(SEED + 4)
@@ -730,7 +797,7 @@ def test_host_buffer_path_matches_device_path(mode):
     dst = mhost.HostPhotonTable(n)
     mhost.trace_host(prod, src, out=dst, chunk=20000)
     got2 = dst.to_numpy()
-    for c in ('facet', 'order', 'CCD_ID', 'chipx', 'dir', 'probability'):
+    for c in ('facet', 'order', 'CCD_ID', 'chipx', 'dir', 'probability', 'energy'):
         assert np.array_equal(got2[c], dev2[c], equal_nan=True), c
     assert np.array_equal(src['pos'], table['pos'])              # inputs untouched
 

@@ -43,6 +43,44 @@ def timed(fn, steps):
     return float(np.median([a.elapsed_time(b) for a, b in ev]))
 
 
+def run_split(name, elements, split, table, n, diag_cols, steps, checks):
+    """Experiment: the same trace as TWO launches (elements[:split] out of place, elements[split:] in place on
+    the result).  Costs one more pass of the photon record through HBM but halves the code each kernel carries."""
+    import ctypes
+    base = mb.PhotonBatch(table, device='cuda')
+    out = base.copy()
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device='cuda')
+    stages = []
+    for k, els in enumerate((elements[:split], elements[split:])):
+        lw = Lowering(out.colnames, meta=out.meta)
+        simulator.Sequence(elements=els)._lower(lw)
+        prog = lw.finish()
+        cols, _ = prog.columns_struct(out)
+        stages.append((prog, cols, prog.device_blob(base.device), prog.source_planes(base, n) if k == 0 else None))
+    kk = [0]
+    infos = []
+
+    def step():
+        kk[0] += 1
+        for prog, cols, blob, src in stages:
+            if src is not None:
+                rc = lib.mxb_trace_from(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, src, ctypes.byref(cols), n, 0,
+                                        99 + kk[0], status.data_ptr(), stream)
+            else:
+                rc = lib.mxb_trace(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, ctypes.byref(cols), n, 0,
+                                   99 + kk[0], status.data_ptr(), stream)
+            assert rc == 0, lib.mxb_last_error()
+            if len(infos) < 2:
+                infos.append(lib.mxb_jit_info().decode())
+    ms = timed(step, steps)
+    nb = 240 + 8 * diag_cols
+    print(json.dumps(dict(config=name + ' [split into 2 launches at element %d]' % split, photons=n, kernel_ms=ms,
+                          photons_per_s=n / ms * 1e3, algorithmic_bytes_per_photon=nb, achieved_gbs=nb * n / ms / 1e6,
+                          frac_of_measured_hbm=nb * n / ms / 1e6 / PEAK, kernel=infos, checks=checks(out))), flush=True)
+
+
 def run_resident(name, elements, table, n, diag_cols, steps, checks):
     """Out-of-place trace of a resident input table (like bench.py)."""
     inst = simulator.Sequence(elements=elements)
@@ -143,9 +181,14 @@ def c3_setup(n, seed=3):
     return elements, b, n_facets
 
 
-def c3(scale, steps):
+def c3(scale, steps, split=0):
     n = int(1e8 * scale)
     elements, b, n_facets = c3_setup(n)
+    chk = lambda o: dict(on_facet=float((o['facet'] >= 0).double().mean()),   # noqa: E731
+                         on_ccd=float((o['CCD_ID'] >= 0).double().mean()), mean_order=float(torch.nanmean(o['order'])))
+    if split:
+        run_split('C3 CAT spectrograph', elements, split, b, n, 19, steps, chk)
+        return
     run_resident('C3 CAT spectrograph: lens+scatter -> {0} CATL1L2Stack facets -> 16 CCDs'.format(n_facets), elements, b, n,
                  19, steps, lambda o: dict(on_facet=float((o['facet'] >= 0).double().mean()),
                                            on_ccd=float((o['CCD_ID'] >= 0).double().mean()),
@@ -189,12 +232,16 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the full photon counts')
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--only', default='')
+    ap.add_argument('--split', type=int, default=0, help='experiment (c3): two launches, split before this element')
     a = ap.parse_args()
     for name, fn in (('c1', c1), ('c3', c3), ('c4', c4)):
         if a.only and name not in a.only.split(','):
             continue
         t0 = time.time()
-        fn(a.scale, a.steps)
+        if name == 'c3' and a.split:
+            fn(a.scale, a.steps, a.split)
+        else:
+            fn(a.scale, a.steps)
         torch.cuda.empty_cache()
         print('# {0} done in {1:.1f} s'.format(name, time.time() - t0), file=sys.stderr)
 
