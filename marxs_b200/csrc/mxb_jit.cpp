@@ -571,7 +571,7 @@ struct Gen {
         out("            if (!__any_sync(0xffffffffu, ph.hit && it.cur < it.end)) break;");
         out("            if (!ph.hit) it.cur = it.end;     // lanes that found nothing are done with this array");
         out("            }");
-        out("            if (nhit >= 2) atomicAdd(&st_sm[MXB_ST_MULTI_HIT], 1ULL);");
+        out("            if (nhit >= 2) count_status(st_sm, MXB_ST_MULTI_HIT);");
         out("            ph.hit = false;");
         out("            }");
         pc = end_pc;
@@ -841,6 +841,15 @@ const char* kStdintStub =
     "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;\n";
 const char* kStddefStub = "#pragma once\ntypedef unsigned long size_t;\n";
 
+// "ptxas info    : Used N registers, ..." of the kernel in the NVRTC log (-1: not found)
+int regs_in_log(const std::string& log) {
+    const size_t p = log.find(" registers");
+    if (p == std::string::npos) return -1;
+    size_t b = p;
+    while (b > 0 && isdigit((unsigned char)log[b - 1])) --b;
+    return b < p ? atoi(log.substr(b, p - b).c_str()) : -1;
+}
+
 // ptxas -v line of the kernel in the NVRTC log: "... N bytes spill stores, M bytes spill loads"
 int spill_bytes_in_log(const std::string& log) {
     const size_t p = log.find(" bytes spill stores");
@@ -851,7 +860,7 @@ int spill_bytes_in_log(const std::string& log) {
 }
 
 int compile(const std::string& source, bool fast_build, const std::string& hash, int threads, std::string& cubin,
-            int* spill_bytes, std::string* err) {
+            int* spill_bytes, std::string* err, int* regs_used = nullptr) {
     Nvrtc& N = nvrtc();
     if (!N.h) { *err = "NVRTC unavailable: " + N.why; return MXB_EJIT; }
     const std::string dir = cache_dir();
@@ -917,6 +926,7 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
         std::string log(ls, '\0');
         if (ls) N.GetProgramLog(prog, &log[0]);
         *spill_bytes = spill_bytes_in_log(log);
+        if (regs_used) *regs_used = regs_in_log(log);
     }
     size_t cs = 0;
     N.GetCUBINSize(prog, &cs);
@@ -929,9 +939,9 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
 
 std::string options_tag(bool fast_build) {
     char b[160];
-    snprintf(b, sizeof(b), "%s t%d b%d r%d p%d f%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 0),
+    snprintf(b, sizeof(b), "%s t%d b%d r%d p%d f%d g%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 0),
              env_int("MXB_JIT_MINBLOCKS", 1), env_int("MXB_JIT_MAXREG", 0), env_int("MXB_JIT_PIPE", 0),
-             env_int("MXB_JIT_PREFETCH", 1));
+             env_int("MXB_JIT_PREFETCH", 1), env_int("MXB_JIT_GROW", 1));
     std::string tag(b);
     if (const char* extra = getenv("MXB_JIT_DEFINES")) tag += std::string(" ") + extra;
     return tag;
@@ -963,14 +973,22 @@ int get_cubin(Gen& g, bool fast_build, std::string& cubin, std::string& hash, st
         // and 128 registers (measured 14 % on B200).  The launch reads the size back from the cubin
         // (maxThreadsPerBlock = the __launch_bounds__ the kernel was compiled with).
         const int fixed = env_int("MXB_JIT_THREADS", 0);
-        int spill = -1;
-        int rc = compile(g.src, fast_build, hs, fixed > 0 ? fixed : 640, cubin, &spill, err);
+        int spill = -1, regs = -1;
+        int rc = compile(g.src, fast_build, hs, fixed > 0 ? fixed : 640, cubin, &spill, err, &regs);
         if (rc) return rc;
         if (fixed <= 0 && spill > kSpillBytesTolerated) {
             std::string alt, alt_err;
             int alt_spill = -1;
             if (compile(g.src, fast_build, hs, 512, alt, &alt_spill, &alt_err) == MXB_OK && alt_spill >= 0 && alt_spill < spill)
                 cubin.swap(alt);
+        } else if (fixed <= 0 && spill == 0 && regs > 0 && regs <= 80 && env_int("MXB_JIT_GROW", 1)) {
+            // short programs (C1, C4: <= 80 registers at 640 threads) leave register file unused: each SM
+            // sub-partition has 16384 registers, so 80 registers allow 6 warps (768 threads) and 64 allow 8
+            // (1024).  Recompile with the larger __launch_bounds__ and keep it if it still does not spill.
+            const int want = regs <= 64 ? 1024 : 768;
+            std::string alt, alt_err;
+            int alt_spill = -1;
+            if (compile(g.src, fast_build, hs, want, alt, &alt_spill, &alt_err) == MXB_OK && alt_spill == 0) cubin.swap(alt);
         }
         if (use_disk) {
             mkdirs(dir);

@@ -163,7 +163,13 @@ MXB_DEV void st_global(long long* p, long long v) {
 }
 
 // status counters are bumped on rare paths from many sites: one shared routine
-MXB_DEV void count_status(unsigned long long* st_sm, int which) { atomicAdd(&st_sm[which], 1ULL); }
+// (every call site passes a constant, so the lanes that arrive here together count the same word: one
+//  shared-memory atomic per converged group instead of one per lane - steep-ray photons of a strongly
+//  dispersing array would otherwise serialise on one address)
+MXB_DEV void count_status(unsigned long long* st_sm, int which) {
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31u) == __ffs(m) - 1) atomicAdd(&st_sm[which], (unsigned long long)__popc(m));
+}
 
 // optics/base.py:43-47: probability factors multiply and must lie in [0,1]
 MXB_DEV void mul_prob(unsigned long long* st_sm, Photon& ph, double f) {

@@ -215,7 +215,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
 
         // leave the array whose ARRAY_BEGIN is op `bpc`
         auto array_exit = [&]() {
-            if (arr_nhit >= 2) atomicAdd(&st_sm[MXB_ST_MULTI_HIT], 1ULL);
+            if (arr_nhit >= 2) count_status(st_sm, MXB_ST_MULTI_HIT);
             arr_pc = -1;
             row = 0;
             ph.hit = false;
