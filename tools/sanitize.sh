@@ -42,6 +42,13 @@ for jit in (2, 0):
     _lib.load().mxb_set_jit(jit)
     o = cat(mb.PhotonBatch(ph, device='cuda')).to_numpy()
     assert np.isfinite(o['det_phi']).sum() > 100
+# lens with a reflectivity table (global-memory table lookups) in both kernels
+rt = optics.ReflectivityTable(np.linspace(0.5, 2., 7), np.linspace(0., 0.2, 9), rng.uniform(0.3, 1., (7, 9)))
+lens = optics.PerfectLens(focallength=30., zoom=[1, 10, 10], reflectivity_interpolator=rt)
+for jit in (2, 0):
+    _lib.load().mxb_set_jit(jit)
+    o = lens(mb.PhotonBatch(ph, device='cuda')).to_numpy()
+    assert (o['probability'] < 1).sum() > 100
 _lib.load().mxb_set_jit(-1)
 print('sanitizer workload ok')
 PY
