@@ -193,6 +193,7 @@ MXB_DEV double draw_value(const double* inj, long long i, unsigned long long see
 // once at the end of the kernel.  Cold pixels go straight to global memory.
 // ---------------------------------------------------------------------------
 #define MXB_HOT_SLOTS 512
+static_assert(MXB_HOT_SLOTS == 512, "hot_add takes the top 9 bits of the pixel hash as the slot");
 struct HotCache {
     unsigned long long* keys;   // global address of the pixel, 0 = free
     double* vals;
@@ -207,10 +208,11 @@ MXB_DEV void hot_flush(HotCache hc, int tid, int nthreads) {   // after a __sync
     for (int k = tid; k < MXB_HOT_SLOTS; k += nthreads)
         if (hc.keys[k]) atomicAdd(reinterpret_cast<double*>(hc.keys[k]), hc.vals[k]);
 }
-MXB_DEV void hot_add(HotCache hc, double* addr, double w) {
+// pix = linear pixel index of addr in its image (the 32-bit key the lanes are matched on)
+MXB_DEV void hot_add(HotCache hc, double* addr, double w, unsigned pix) {
     const unsigned long long key = (unsigned long long)addr;
     const unsigned act = __activemask();
-    const unsigned peers = __match_any_sync(act, key);
+    const unsigned peers = __match_any_sync(act, pix);
     const int leader = __ffs(peers) - 1;
     double sum = w;
     unsigned rest = peers & ~(1u << leader);
@@ -220,7 +222,7 @@ MXB_DEV void hot_add(HotCache hc, double* addr, double w) {
         rest &= rest - 1;
     }
     if ((int)(threadIdx.x & 31) != leader) return;
-    const unsigned slot = (unsigned)(((key >> 3) * 0x9E3779B97F4A7C15ULL) >> 55) & (MXB_HOT_SLOTS - 1);
+    const unsigned slot = (pix * 0x9E3779B9u) >> 23;     // MXB_HOT_SLOTS = 512
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&hc.keys[slot]);
     if (cur == 0ULL && (peers & (peers - 1))) {   // free slot and the pixel looks hot: claim it
         cur = atomicCAS(&hc.keys[slot], 0ULL, key);
@@ -238,7 +240,8 @@ MXB_DEV void accumulate_image(HotCache hc, double* img, PP gp, long long idn, do
     if (plane < 0 || plane >= (long long)gp[3] || !(px == px) || !(py == py) || !(w == w)) return;
     const long long ix = llrint(px), iy = llrint(py);
     if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) return;
-    hot_add(hc, &img[(plane * ny + iy) * nx + ix], w);
+    const long long lin = (plane * ny + iy) * nx + ix;
+    hot_add(hc, &img[lin], w, (unsigned)lin);
 }
 
 // ---------------------------------------------------------------------------

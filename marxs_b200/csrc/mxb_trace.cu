@@ -614,7 +614,7 @@ hist2d_kernel(const double* x, const double* y, const double* w, const long long
         if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) continue;
         const long long bin = (plane * ny + iy) * nx + ix;
         const double wv = w ? w[i] : 1.0;
-        if (img && wv == wv) hot_add(hot, &img[bin], wv);
+        if (img && wv == wv) hot_add(hot, &img[bin], wv, (unsigned)bin);
         if (counts) atomicAdd(&counts[bin], 1ULL);
     }
     __syncthreads();
