@@ -113,7 +113,9 @@ typedef struct MxbColumns {
                                   flags bit3: L1 support (mitsnl/catgrating.py:170-219): s1 = second uniform, c2 = word offset
                                   (a plain integer, not a column) of the block  openfraction, table_off ; table (global):
                                   n, energy[n], transmission[n].  Photons with u1 > openfraction pass through the Si bar:
-                                  dir / polarization unchanged, order 0, probability *= interp1d(energy)                        */
+                                  dir / polarization unchanged, order 0, probability *= interp1d(energy)                        
+                                  flags bit4: grating constant per photon (grating.py:209-220, callable d): c3 = INPUT column holding
+                                  d(intercoos) for every photon the op acts on; the d word of the parameter block is ignored.  */
 #define MXB_OP_DETPIX      11  /* detector.py:73-75: params pixsize cp0 cp1; c0,c1 detpix cols.  flags bit0: id_num from the facet
                                   row; bit1: CircularDetector (detector.py:113-116): params pixsize cp0 cp1 R,
                                   detpix_x = phi * R / pixsize + cp0                                                             */

@@ -356,7 +356,9 @@ struct Gen {
                 out("                if (blocked) trans = filter_value(st_sm, PRef<false>{P.prog, (int)%s[1]}, ph.energy, 1);", lb.c_str());
             }
             out("                op_grating(st_sm, ph, %s, %s, %d,", PR(o, 9).c_str(), geom.c_str(), fl);
-            out("                           [&](double energy, double bl, double& psel) { return %s; }, order, blaze, blocked, trans);", select.c_str());
+            const std::string dcol = (fl & 16) ? F(o.c[3]) + "[i]" : std::string("0.0");   // callable d: per-photon column
+            out("                           [&](double energy, double bl, double& psel) { return %s; }, order, blaze, blocked, trans, %s);",
+                select.c_str(), dcol.c_str());
             out("            }");
             put(o.c[0], "order");
             put(o.c[1], "blaze");

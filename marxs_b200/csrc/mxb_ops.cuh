@@ -474,10 +474,12 @@ MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy
 }
 
 // grating.py:233-277  params: l[3] dd[3] d blaze0 dblaze ; n = e_x of the geometry.
+// flags: 1 CAT sign convention, 2 reflection, 4 blaze modifier, 8 L1 support bars, 16 per-photon d (column)
 // select(energy, blaze, psel) -> diffraction order (the caller binds the draw and the table)
 template <typename PP, typename GP, typename SELECT>
 MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, int flags, SELECT select,
-                        double& order, double& blaze, bool l1_blocked = false, double l1_trans = 0.0) {
+                        double& order, double& blaze, bool l1_blocked = false, double l1_trans = 0.0,
+                        double d_photon = 0.0) {
     const V3 pn = normalize_unless(ph.unit, ph.dir);
     const V3 l = ld3(p), dd = ld3(p + 3), n = ld3(geom + 3);
     const double wave = div(kEnergy2Wave, ph.energy);
@@ -489,7 +491,9 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
     order = select(ph.energy, blaze, psel);
     const double p_dd = dot(pn, dd);
     const double sign = (flags & 1) ? ((p_dd < 0.0) ? -1.0 : 1.0) : -1.0;  // CAT: grating.py:298-301
-    const double p_d = p_dd + div(sign * order * wave, p[6]);
+    // flags bit 4: the grating constant varies over the facet (grating.py:209-220, callable d): the caller
+    // passes the value d(intercoos) of this photon
+    const double p_d = p_dd + div(sign * order * wave, (flags & 16) ? d_photon : p[6]);
     const double p_n = sqrt(1. - p_d * p_d - p_l * p_l);
     const double pdn = dot(pn, n);
     double direction = (pdn > 0.0) ? 1.0 : ((pdn < 0.0) ? -1.0 : pdn);  // np.sign

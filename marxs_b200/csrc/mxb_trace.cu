@@ -327,7 +327,8 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                                [&](double energy, double bl, double& psel) {
                                    return select_order(sel, P.prog, u, energy, bl, psel);
                                },
-                               order, blaze, blocked, trans);
+                               order, blaze, blocked, trans,
+                               (op.flags & 16) ? P.cols.f64[c.c[3]][i] : 0.0);   // (input column: plain index)
                 }
                 put(ctx, wm, 0, c.cp[0], ph.hit, order);
                 put(ctx, wm, 1, c.cp[1], ph.hit, blaze);

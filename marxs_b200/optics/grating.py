@@ -118,20 +118,55 @@ class FlatGrating(FlatOpticalElement):
         """(blaze_center, d_blaze_mm) or None (reference blaze_angle_modifier :222-231)."""
         return None
 
+    _D_COLUMN = '_mxb_d'      # per-photon grating constant of a callable d (exists only during the launch)
+
+    def _can_lower(self):
+        # a callable d(intercoos) needs the intersect first: kernel intersect, d() on the device tensors, then
+        # the diffraction kernel with d read from a column (process_photons below)
+        return super()._can_lower() and not callable(self._d)
+
+    def process_photons(self, photons, intersect, interpos, intercoos):
+        if not callable(self._d) or not FlatOpticalElement._can_lower(self):
+            return super().process_photons(photons, intersect, interpos, intercoos)
+        import torch
+        hit = torch.as_tensor(intersect, device=photons.device)
+        loc = torch.as_tensor(intercoos, device=photons.device).as_subclass(torch.Tensor)[hit]
+        try:
+            d_hit = self._d(loc)
+        except (TypeError, RuntimeError, ValueError, AttributeError):
+            d_hit = self._d(loc.cpu().numpy())          # numpy-only user function: evaluate it on a host copy
+        d_full = torch.full((len(photons),), float('nan'), dtype=torch.float64, device=photons.device)
+        if isinstance(d_hit, torch.Tensor):
+            d_full[hit] = d_hit.to(device=photons.device, dtype=torch.float64)
+        else:
+            d_full[hit] = torch.as_tensor(np.asarray(d_hit, dtype=float), device=photons.device)
+        photons[self._D_COLUMN] = d_full
+        try:
+            return self._process_photons_kernel(photons, intersect, interpos, intercoos)
+        finally:
+            if self._D_COLUMN in photons:
+                photons.remove_column(self._D_COLUMN)
+
     def _lower_specific(self, lw):
-        if callable(self._d):
-            raise UnsupportedCallable('callable grating constant d(intercoos) is not supported on the device')
+        d_callable = callable(self._d)
+        if d_callable and self._D_COLUMN not in lw.existing:
+            raise UnsupportedCallable('a callable grating constant d(intercoos) cannot be fused: call the grating '
+                                      'on a photon table (kernel intersect, d(), diffraction kernel)')
         l, e_perp, n = self.e_groove_coos(np.zeros((1, 2)))
         dd = -e_perp[0]
         mod = self._blaze_modifier()
         flags = (1 if self._cat else 0) | (0 if self.transmission else 2) | (4 if mod is not None else 0)
-        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [self._d], list(mod) if mod is not None else [0., 0.]]))
+        pf = lw.eparams(np.concatenate([l[0][:3], dd[:3], [0. if d_callable else self._d],
+                                        list(mod) if mod is not None else [0., 0.]]))
         extra = self._lower_l1(lw)         # (flag, second draw slot, block offset) for the L1 support variant
         cols = [lw.fcol(self.order_name), lw.fcol(self.blaze_name)]
         s0 = lw.slot('uniform')
         if extra is not None:
             cols.append(extra[1])
             flags |= 8
+        if d_callable:
+            cols += [-1] * (3 - len(cols)) + [lw.fcol(self._D_COLUMN)]
+            flags |= 16
         lw.op('GRATING', flags=flags, pg=lower_selector(self.order_selector, lw), pf=pf, cols=cols, s0=s0,
               s1=lw.slot('uniform') if extra is not None else -1)
         lw.last_order_col = self.order_name

@@ -854,6 +854,33 @@ def case_lens_reflectivity(marxs, rng):
     save('lens_reflectivity', **arrays)
 
 
+def chirp_d(intercoos):
+    """Grating constant varying over the facet (grating.py:209-220); works on numpy arrays and torch tensors."""
+    return 2e-4 * (1. + 0.02 * intercoos[:, 0] + 0.001 * intercoos[:, 1] ** 2)
+
+
+def case_grating_callable_d(marxs, rng):
+    """FlatGrating / CATGrating with a callable grating constant d(intercoos) (grating.py:209-220, the
+    reference's test_grating_d_callable), orders -2..2."""
+    from marxs.optics import FlatGrating, CATGrating, OrderSelector
+    n = 2000
+    arrays = {}
+    for tag, cls in (('flat', FlatGrating), ('cat', CATGrating)):
+        p = make_photons(rng, n, spread=0.2, x0=60., lateral=8.)
+        pos4d = rand_pos4d(rng, zoom=(1., 9., 6.), shift=1.)
+        g = cls(d=chirp_d, order_selector=OrderSelector(np.arange(-2, 3)), pos4d=pos4d, groove_angle=0.3)
+        g._slots = [0]
+        u = rng.random(n)
+        inp = inputs_dict(p)
+        with Injector(marxs, [u]):
+            out = g(p)
+        arrays.update({'%s_%s' % (tag, k): v for k, v in inp.items()})
+        arrays.update({'%s_%s' % (tag, k): v for k, v in table_to_dict(out).items()})
+        arrays[tag + '_pos4d'] = pos4d
+        arrays[tag + '_u'] = u
+    save('grating_callable_d', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -864,7 +891,7 @@ def main():
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
                               case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing,
-                              case_lens_reflectivity]):
+                              case_lens_reflectivity, case_grating_callable_d]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

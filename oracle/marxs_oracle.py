@@ -517,7 +517,9 @@ class FlatGrating(Element):
         p_dd = dot3(p, dd)
         sign = self.order_sign(p_dd)
         with np.errstate(invalid='ignore'):
-            p_d = p_dd + sign * m * wave / self._d
+            # grating.py:209-220: d may be a callable of the local coordinates of the hits
+            d = self._d(loc[hit]) if callable(self._d) else self._d
+            p_d = p_dd + sign * m * wave / d
             p_n = np.sqrt(1. - p_d ** 2 - p_l ** 2)
         direction = np.sign(dot3(p, n))
         if not self.transmission:

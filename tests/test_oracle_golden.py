@@ -265,6 +265,22 @@ def test_golden_gratings(tag):
     assert_cols(out, g, tag + '_', exact=('order',))
 
 
+def _chirp_d(intercoos):      # same function as oracle/gen_golden.py chirp_d
+    return 2e-4 * (1. + 0.02 * intercoos[:, 0] + 0.001 * intercoos[:, 1] ** 2)
+
+
+@pytest.mark.parametrize('tag', ['flat', 'cat'])
+def test_golden_grating_callable_d(tag):
+    """Grating constant as a callable of the local coordinates (grating.py:209-220) vs the reference."""
+    g = load('grating_callable_d')
+    cls = {'flat': mo.FlatGrating, 'cat': mo.CATGrating}[tag]
+    el = cls(d=_chirp_d, order_selector=mo.OrderSelector(np.arange(-2, 3)), pos4d=g[tag + '_pos4d'], groove_angle=0.3)
+    mo.assign_slots(el)
+    out = el(table_from(g, tag + '_'), mo.Draws([g[tag + '_u']]))
+    assert np.isfinite(out['order']).sum() > 300
+    assert_cols(out, g, tag + '_', exact=('order',))
+
+
 def test_golden_lens_reflectivity():
     """PerfectLens with the reference's RectBivariateSpline(kx=ky=1) reflectivity (mirror.py:68-81): queries
     inside, below and above the table; also the reference's own known answer (test_mirror.py:62-80)."""

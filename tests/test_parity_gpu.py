@@ -319,6 +319,64 @@ def test_lens_scatter_golden(mode):
                                                {'filterfunc': 0.66}]), [g['stack_z0'], g['stack_z1']])
 
 
+def _chirp_d(intercoos):      # same function as oracle/gen_golden.py chirp_d; numpy arrays and torch tensors
+    return 2e-4 * (1. + 0.02 * intercoos[:, 0] + 0.001 * intercoos[:, 1] ** 2)
+
+
+def test_grating_callable_d(mode):
+    """Grating constant as a callable d(intercoos) (grating.py:209-220): kernel intersect, d() evaluated on
+    the hits, diffraction kernel with d read per photon.  Against the unmodified reference
+    (tests/golden/grating_callable_d.npz), the oracle, the reference's own test (test_grating.py:297-311,
+    numpy-only callable) and inside a Sequence between fused runs."""
+    from marxs_b200 import optics, simulator
+    mb = _mb()
+    g = load('grating_callable_d')
+    for tag, cls in (('flat', optics.FlatGrating), ('cat', optics.CATGrating)):
+        el = cls(d=_chirp_d, order_selector=optics.OrderSelector(np.arange(-2, 3)), pos4d=g[tag + '_pos4d'], groove_angle=0.3)
+        t = mo.PhotonTable((k, g[tag + '_in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+        with mb.inject_draws([g[tag + '_u']]):
+            out = el(mb.PhotonBatch(t, device='cuda')).to_numpy()
+        names = [k[len(tag) + 5:] for k in g if k.startswith(tag + '_out_')]
+        assert set(names) == set(out.keys()), (names, list(out.keys()))
+        assert np.array_equal(np.nan_to_num(out['order'], nan=-9), np.nan_to_num(g[tag + '_out_order'], nan=-9))
+        for c in names:
+            if c == 'blaze':
+                continue        # ill-conditioned arccos, checked against the oracle below with its bound
+            np.testing.assert_allclose(out[c], g[tag + '_out_' + c], rtol=1e-11, atol=1e-11, equal_nan=True, err_msg=c)
+    rng = np.random.default_rng(SEED + 41)
+    n = 20000
+    pos4d = rand_pos4d(rng, zoom=(1., 9., 6.))
+    table = make_photons(rng, n, spread=0.1)
+    sel_p, sel_o = optics.OrderSelector(np.arange(-3, 4)), mo.OrderSelector(np.arange(-3, 4))
+    run_pair(optics.CATGrating(d=_chirp_d, order_selector=sel_p, pos4d=pos4d),
+             mo.CATGrating(d=_chirp_d, order_selector=sel_o, pos4d=pos4d), table, [rng.random(n)], rtol=1e-11)
+    # in a Sequence: fused run, the callable-d grating on its own, fused run again
+    det_pos = pos4d.copy()
+    det_pos[:3, 3] -= 30. * pos4d[:3, 0] / np.linalg.norm(pos4d[:3, 0])
+    pos2 = pos4d.copy()           # 5 mm behind the first grating (two elements in ONE plane would make k = +-0)
+    pos2[:3, 3] -= 5. * pos4d[:3, 0] / np.linalg.norm(pos4d[:3, 0])
+    g2_p = optics.FlatGrating(d=_chirp_d, order_selector=sel_p, pos4d=pos2)
+    g2_o = mo.FlatGrating(d=_chirp_d, order_selector=sel_o, pos4d=pos2)
+    for g2 in (g2_p, g2_o):       # column names are instance-overridable (grating.py:136-143)
+        g2.order_name, g2.blaze_name, g2.loc_coos_name = 'order2', 'blaze2', ['g2_y', 'g2_z']
+    seq_p = simulator.Sequence(elements=[optics.FlatGrating(d=4e-4, order_selector=sel_p, pos4d=pos4d), g2_p,
+                                         optics.FlatDetector(pixsize=0.05, pos4d=det_pos)])
+    seq_o = mo.Sequence([mo.FlatGrating(d=4e-4, order_selector=sel_o, pos4d=pos4d), g2_o,
+                         mo.FlatDetector(pixsize=0.05, pos4d=det_pos)])
+    run_pair(seq_p, seq_o, table, [rng.random(n), rng.random(n)], rtol=1e-10, skip=('blaze2',))
+    # the reference's test: numpy-only callable (np.ones / np.where on the argument)
+    def dfunc(intercoos):
+        darr = np.ones(intercoos.shape[0]) * 2e-4
+        return np.where(np.asarray(intercoos)[:, 0] >= 0, darr, darr / 2.)
+    five = mo.PhotonTable(pos=np.tile([1., 0, 0, 1], (5, 1)), dir=np.tile([-1., 0, 0, 0], (5, 1)), energy=np.ones(5),
+                          polarization=np.tile([0., 1, 0, 0], (5, 1)), probability=np.ones(5))
+    five['pos'][0, 1] = 1.
+    five['pos'][1, 1] = -1.
+    p = optics.FlatGrating(order_selector=optics.OrderSelector([1]), zoom=2, d=dfunc)(mb.PhotonBatch(five, device='cuda')).to_numpy()
+    assert np.abs(p['dir'][1, 1] / p['dir'][0, 1] - 2) < 0.00001
+    assert '_mxb_d' not in p
+
+
 def test_lens_reflectivity(mode):
     """PerfectLens(reflectivity_interpolator=...) (mirror.py:68-81) on the device: against the unmodified
     reference (tests/golden/lens_reflectivity.npz, RectBivariateSpline k=1 given as such), against the
