@@ -106,7 +106,8 @@ typedef struct MxbColumns {
 #define MXB_OP_RSCATTER     7  /* scatter.py:49-77 RadialMirrorScatter: params center[3] sig_in sig_perp; s0,s1 normals; c0,c1 cols   */
 #define MXB_OP_GSCATTER     8  /* scatter.py:109-145 RandomGaussianScatter: params sigma; s0 normal s1 uniform; c0 col.
                                   flags bit0: L2Diffraction (mitsnl/catgrating.py:262-285): params innerfree,
-                                  sigma = 1.22 * 0.4 * asin(lambda / innerfree) per photon                                         */
+                                  sigma = 1.22 * 0.4 * asin(lambda / innerfree) per photon                                         
+                                  flags bit1: callable scatter (scatter.py:127-129): the angle is read from INPUT column c1, s0 unused  */
 #define MXB_OP_FILTER       9  /* filter.py:90-94 EnergyFilter: params n, x[n], y[n] (n==0: constant y[0]); flags bit0 bounds_error  */
 #define MXB_OP_GRATING     10  /* grating.py:233-277: params l[3] dd[3] d blaze0 dblaze ; flags bit0 CAT bit1 reflection
                                   bit2 blaze modifier; pg: selector block; s0 uniform; c0 order c1 blaze.

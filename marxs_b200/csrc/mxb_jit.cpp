@@ -315,7 +315,8 @@ struct Gen {
             out("            {");
             out("            double a = 0;");
             out("            if (ph.hit) {");
-            out("                const double zn = %s;", draw(o.s0, 1).c_str());
+            if (fl & 2) out("                const double zn = %s[i];   // callable scatter: angle column", F(o.c[1]).c_str());
+            else out("                const double zn = %s;", draw(o.s0, 1).c_str());
             out("                const double u = %s;", draw(o.s1, 0).c_str());
             out("                op_gscatter(ph, %s, %d, zn, u, a);", PR(o, 1).c_str(), fl);
             out("            }");

@@ -323,7 +323,9 @@ MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, doubl
     const V3 pdir = normalize_unless(ph.unit, ph.dir);
     const V3 guess = (fabs(pdir.x) < 0.99999) ? V3{1, 0, 0} : V3{0, 1, 0};
     const V3 perp = cross(pdir, guess);
-    if (flags & 1) {   // L2Diffraction (mitsnl/catgrating.py:280-285): Airy-disk sigma of the L2 mesh, p[0] = innerfree
+    if (flags & 2) {   // callable scatter (scatter.py:127-129): the caller passes the angle of this photon in zn
+        ang = zn;
+    } else if (flags & 1) {   // L2Diffraction (mitsnl/catgrating.py:280-285): Airy-disk sigma of the L2 mesh, p[0] = innerfree
         const double wave = div(kHcKevNm * 1e-6, ph.energy);   // astropy u.spectral(): keV -> mm
         const double sigma = (1.22 * 0.4) * m_asin(div(wave, p[0]));
         ang = zn * sigma;

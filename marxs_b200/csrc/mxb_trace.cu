@@ -294,7 +294,7 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 const int wm = store_mask(ctx, c.mode, ph.hit);
                 double a = 0;
                 if (ph.hit) {
-                    const double zn = draw(ctx, c.s0, 1);
+                    const double zn = (op.flags & 2) ? P.cols.f64[c.c[1]][i] : draw(ctx, c.s0, 1);   // callable scatter: angle column
                     const double u = draw(ctx, c.s1, 0);
                     op_gscatter(ph, pr, op.flags, zn, u, a);
                 }

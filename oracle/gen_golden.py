@@ -881,6 +881,31 @@ def case_grating_callable_d(marxs, rng):
     save('grating_callable_d', **arrays)
 
 
+def case_scatter_callable(marxs, rng):
+    """RandomGaussianScatter with a callable scatter (scatter.py:127-129; the reference's
+    test_scatteredfunction): the angle depends on energy and on where the photon hits."""
+    from marxs.optics import RandomGaussianScatter
+    import astropy.units as u
+    n = 2000
+
+    def anglefunc(photons, intersect, interpos, intercoos):
+        return (2e-3 * np.asarray(photons['energy'])[intersect] * np.sin(3. * intercoos[intersect, 0])) * u.rad
+
+    p = make_photons(rng, n, spread=0.1, x0=50., lateral=20.)
+    pos4d = rand_pos4d(rng, zoom=(1., 30., 30.), shift=1.)
+    sg = RandomGaussianScatter(scatter=anglefunc, pos4d=pos4d)
+    sg._slots = [0]
+    draws = [rng.random(n)]
+    inp = inputs_dict(p)
+    with Injector(marxs, draws):
+        out = sg(p)
+    arrays = {'cs_' + k: v for k, v in inp.items()}
+    arrays.update({'cs_' + k: v for k, v in table_to_dict(out).items()})
+    arrays['cs_pos4d'] = pos4d
+    arrays['cs_u'] = draws[0]
+    save('scatter_callable', **arrays)
+
+
 def main():
     marxs = tier_r.load_reference()
     import marxs.missions.chandra  # noqa: F401
@@ -891,7 +916,7 @@ def main():
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
                               case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing,
-                              case_lens_reflectivity, case_grating_callable_d]):
+                              case_lens_reflectivity, case_grating_callable_d, case_scatter_callable]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

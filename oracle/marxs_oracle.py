@@ -654,12 +654,13 @@ class RandomGaussianScatter(Element):
     scattername = 'scatter'
     n_slots = 2
     slot_kinds = ('normal', 'uniform')
+    uniform_slot = 1
 
     def __init__(self, **kwargs):
         self.scatter = float(kwargs.pop('scatter'))
         super().__init__(**kwargs)
 
-    def scatter_angle(self, photons, hit, draws):
+    def scatter_angle(self, photons, hit, draws, interpos=None, loc=None):
         return self.scatter * self.draw(draws, 0, hit, 'normal')
 
     def specific_process_photons(self, photons, hit, interpos, loc, draws):
@@ -672,12 +673,28 @@ class RandomGaussianScatter(Element):
         guess[ind, 0] = 1
         guess[~ind, 1] = 1
         perpvec = cross3(pdir, guess)
-        angle = self.scatter_angle(photons, hit, draws)
+        angle = self.scatter_angle(photons, hit, draws, interpos, loc)
         outdir = axangle_rotate_T(perpvec, angle, pdir)
-        angle2 = self.draw(draws, 1, hit, 'uniform') * 2 * np.pi
+        angle2 = self.draw(draws, self.uniform_slot, hit, 'uniform') * 2 * np.pi
         outdir = e2h(axangle_rotate_T(pdir, angle2, outdir), 0)
         pol = parallel_transport(dir_old, outdir, photons['polarization'][hit])
         return {'dir': outdir, 'polarization': pol, self.scattername: angle}
+
+
+class CallableGaussianScatter(RandomGaussianScatter):
+    """scatter.py:127-129: ``scatter`` is a function (photons, intersect, interpos, intercoos) -> one angle
+    [rad] per intersecting photon; no normal is drawn, only the uniform azimuth."""
+    n_slots = 1
+    slot_kinds = ('uniform',)
+    uniform_slot = 0
+
+    def __init__(self, **kwargs):
+        self.func = kwargs.pop('scatter')
+        Element.__init__(self, **kwargs)
+        self.scatter = 1.      # "not zero" (the reference compares the callable with 0: False)
+
+    def scatter_angle(self, photons, hit, draws, interpos=None, loc=None):
+        return np.asarray(self.func(photons, hit, interpos, loc), dtype=float)
 
 
 # ---------------------------------------------------------------------------

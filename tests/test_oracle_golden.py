@@ -281,6 +281,19 @@ def test_golden_grating_callable_d(tag):
     assert_cols(out, g, tag + '_', exact=('order',))
 
 
+def test_golden_scatter_callable():
+    """RandomGaussianScatter(scatter=callable) (scatter.py:127-129) vs the reference."""
+    g = load('scatter_callable')
+
+    def anglefunc(photons, hit, interpos, loc):
+        return 2e-3 * photons['energy'][hit] * np.sin(3. * loc[hit, 0])
+    el = mo.CallableGaussianScatter(scatter=anglefunc, pos4d=g['cs_pos4d'])
+    mo.assign_slots(el)
+    out = el(table_from(g, 'cs_'), mo.Draws([g['cs_u']]))
+    assert np.isfinite(out['scatter']).mean() > 0.9
+    assert_cols(out, g, 'cs_')
+
+
 def test_golden_lens_reflectivity():
     """PerfectLens with the reference's RectBivariateSpline(kx=ky=1) reflectivity (mirror.py:68-81): queries
     inside, below and above the table; also the reference's own known answer (test_mirror.py:62-80)."""

@@ -377,6 +377,42 @@ def test_grating_callable_d(mode):
     assert '_mxb_d' not in p
 
 
+def test_scatter_callable(mode):
+    """RandomGaussianScatter with a callable scatter(photons, intersect, interpos, intercoos) (scatter.py:127-129):
+    kernel intersect, the user function on the device table, rotation kernel with the angle read per photon.
+    Against the unmodified reference (tests/golden/scatter_callable.npz) and the reference's own
+    test_scatteredfunction (test_scatter.py:110-128, time-dependent scatter, all photons returned)."""
+    import torch
+    from marxs_b200 import optics
+    mb = _mb()
+    g = load('scatter_callable')
+
+    def anglefunc(photons, intersect, interpos, intercoos):      # torch in, torch out: one angle per hit
+        return 2e-3 * photons['energy'].data[intersect] * torch.sin(3. * intercoos[intersect, 0])
+    el = optics.RandomGaussianScatter(scatter=anglefunc, pos4d=g['cs_pos4d'])
+    t = mo.PhotonTable((k, g['cs_in_' + k]) for k in ('pos', 'dir', 'energy', 'polarization', 'probability'))
+    with mb.inject_draws([g['cs_u']]):
+        out = el(mb.PhotonBatch(t, device='cuda')).to_numpy()
+    names = [k[len('cs_out_'):] for k in g if k.startswith('cs_out_')]
+    assert set(names) == set(out.keys()), (names, list(out.keys()))
+    for c in names:
+        np.testing.assert_allclose(out[c], g['cs_out_' + c], rtol=1e-11, atol=1e-11, equal_nan=True, err_msg=c)
+    # the reference's test: scatter grows with the photon's time; the function returns one value per photon
+    n = 500
+    table = mo.PhotonTable(pos=np.tile([0., 1., 0., 1.], (n, 1)), dir=np.tile([-1., 0, 0, 0], (n, 1)), energy=np.ones(n),
+                           polarization=np.tile([0., 1, 0, 0], (n, 1)), probability=np.ones(n))
+    table['time'] = np.arange(n, dtype=float) / 500.
+    # (a numpy-only function: it is evaluated on a host copy of the table)
+    rms = optics.RandomGaussianScatter(scatter=lambda photons, intersect, interpos, intercoos: np.deg2rad(photons['time']))
+    det = optics.FlatDetector(position=[-1, 0, 0], zoom=1000)
+    p = det(rms(mb.PhotonBatch(table, device='cuda'))).to_numpy()
+    d = np.sqrt((p['det_x'] - np.mean(p['det_x'])) ** 2 + (p['det_y'] - np.mean(p['det_y'])) ** 2)
+    d = d * np.sign(p['det_x'] - np.mean(p['det_x']))
+    assert np.std(d[:200]) < 2 * np.std(d[:300])
+    assert np.allclose(p['scatter'], np.deg2rad(table['time']))
+    assert '_mxb_angle' not in p
+
+
 def test_lens_reflectivity(mode):
     """PerfectLens(reflectivity_interpolator=...) (mirror.py:68-81) on the device: against the unmodified
     reference (tests/golden/lens_reflectivity.npz, RectBivariateSpline k=1 given as such), against the
