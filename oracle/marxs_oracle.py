@@ -1023,7 +1023,7 @@ class L2Diffraction(RandomGaussianScatter):
         kwargs['scatter'] = 1.
         super().__init__(**kwargs)
 
-    def scatter_angle(self, photons, hit, draws):
+    def scatter_angle(self, photons, hit, draws, interpos=None, loc=None):
         wave = (HC_KEV_NM * 1e-6) / photons['energy'][hit]      # astropy u.spectral(): keV -> mm
         with np.errstate(invalid='ignore'):
             sigma = 1.22 * 0.4 * np.arcsin(wave / self.innerfree)
