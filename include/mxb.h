@@ -140,7 +140,10 @@ typedef struct MxbColumns {
                                   RandomArbitraryPdf table (math/random.py:80-95; draws s0, s1); polangle: mode 0 constant,
                                   1 uniform [0, 2 pi) (draw w14), 2 table (draws w14, w15); probability = 1.
                                   Tables live after the staged region: n, cdf[n], sortindex[n], x[n], bin_width[n].
-                                  c0 time, c1 polangle, c2 ra, c3 dec output columns (sky != 0: AstroSource)                  */
+                                  c0 time, c1 polangle, c2 ra, c3 dec output columns (sky != 0: AstroSource).
+                                  flags (callable flux / energy / polarization, basesources.py:169,181,203, evaluated by the host):
+                                  bit0 energy is read from the core energy plane, bit1 polangle is read from column c1,
+                                  bit2 the time column c0 is an input and is not written                                        */
 #define MXB_OP_POINTING    23  /* source/pointing.py:101-211 FixedPointing / JitterPointing: c0 ra, c1 dec, c2 polangle INPUT
                                   columns; pg: M[9] (ICRS -> offset frame), T[9] (reference_transform), north[3], jitter sigma;
                                   flags bit0: jitter (draws s0 uniform axis angle, s1 normal); all photons                   */

@@ -410,10 +410,17 @@ struct Gen {
             for (int sl : {o.s0, o.s1, o.w14, o.w15})
                 if (sl >= 0 && sl < MXB_MAX_SLOTS) out("                case %d: return %s;", sl, draw(sl, 0).c_str());
             out("                default: return 0.0;");
-            out("                } }, %d, %d, %d, %d, time, polangle);", o.s0, o.s1, o.w14, o.w15);
+            {
+                const int pidx = o.c[1] >= MXB_COL_INIT ? o.c[1] - MXB_COL_INIT : o.c[1];
+                const std::string e_in = (fl & 1) ? F(MXB_COL_ENERGY) + "[i]" : std::string("0.0");
+                const std::string p_in = ((fl & 2) && has_f(o.c[1])) ? F(pidx) + "[i]" : std::string("0.0");
+                out("                } }, %d, %d, %d, %d, time, polangle, %d, %s, %s);", o.s0, o.s1, o.w14, o.w15, fl, e_in.c_str(),
+                    p_in.c_str());
+            }
             for (int k = 0; k < 4; ++k) {
                 const char* val[] = {"time", "polangle", nullptr, nullptr};
                 if (!has_f(o.c[k])) continue;
+                if ((k == 0 && (fl & 4)) || (k == 1 && (fl & 2))) continue;      // input columns of callable specifications
                 const int idx = o.c[k] >= MXB_COL_INIT ? o.c[k] - MXB_COL_INIT : o.c[k];
                 if (k < 2) out("            jput(%s, i, active, true, %s);", F(idx).c_str(), val[k]);
                 else out("            jput(%s, i, active, true, %s[%d]);", F(idx).c_str(), p.c_str(), 6 + k);

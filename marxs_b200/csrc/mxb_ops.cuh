@@ -724,17 +724,23 @@ MXB_DEV V3 polarization_vector(const V3& dir, double angle) {
 
 // source/basesources.py:158-277: p = dt e_mode e_const e_table p_mode p_const p_table sky ra dec
 template <typename PP, typename DRAW>
+// flags: callable specifications (basesources.py:169,181,203) are evaluated by the host and arrive as columns:
+// bit0 energy = energy_in (the core energy plane), bit1 polangle = polangle_in, bit2 the time column is an input
 MXB_DEV void op_generate(Photon& ph, PP p, const double* gprog, unsigned long long gid, DRAW draw, int s0, int s1,
-                         int s2, int s3, double& time, double& polangle) {
+                         int s2, int s3, double& time, double& polangle, int flags = 0, double energy_in = 0.0,
+                         double polangle_in = 0.0) {
     time = (double)gid * p[0];                       // np.arange(0, T, dt)[i]
-    if ((int)p[1] == 1) {
+    if (flags & 1) {
+        ph.energy = energy_in;
+    } else if ((int)p[1] == 1) {
         const double u0 = draw(s0), u1 = draw(s1);
         ph.energy = arbitrary_pdf(gprog + (long long)p[3], u0, u1);
     } else {
         ph.energy = 1. * p[2];
     }
     const int pm = (int)p[4];
-    if (pm == 1) polangle = 0. + (kTwoPi - 0.) * draw(s2);      // np.random.uniform(0, 2 pi)
+    if (flags & 2) polangle = polangle_in;
+    else if (pm == 1) polangle = 0. + (kTwoPi - 0.) * draw(s2);      // np.random.uniform(0, 2 pi)
     else if (pm == 2) {
         const double u0 = draw(s2), u1 = draw(s3);
         polangle = arbitrary_pdf(gprog + (long long)p[6], u0, u1);

@@ -369,12 +369,16 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
             case MXB_OP_GENERATE: {
                 const OpCold& c = opc[pc];
                 double time = 0, polangle = 0;
-                if (ctx.active)
+                if (ctx.active) {
+                    const int pc1 = c.c[1] >= MXB_COL_INIT ? c.c[1] - MXB_COL_INIT : c.c[1];
                     op_generate(ph, pr, P.prog, (unsigned long long)(P.id0 + i), [&](int s) { return draw(ctx, s, 0); },
-                                c.s0, c.s1, c.w14, c.w15, time, polangle);
+                                c.s0, c.s1, c.w14, c.w15, time, polangle, op.flags,
+                                (op.flags & 1) ? P.cols.f64[MXB_COL_ENERGY][i] : 0.0,
+                                ((op.flags & 2) && pc1 >= 0) ? P.cols.f64[pc1][i] : 0.0);
+                }
                 const int wm = store_mask(ctx, c.mode, true);
-                put(ctx, wm, 0, c.cp[0], true, time);
-                put(ctx, wm, 1, c.cp[1], true, polangle);
+                if (!(op.flags & 4)) put(ctx, wm, 0, c.cp[0], true, time);
+                if (!(op.flags & 2)) put(ctx, wm, 1, c.cp[1], true, polangle);
                 put(ctx, wm, 2, c.cp[2], true, pr[8]);
                 put(ctx, wm, 3, c.cp[3], true, pr[9]);
                 break;

@@ -34,6 +34,34 @@ def _val(x, unit=None):
     return float(x)
 
 
+def _strip(x, unit):
+    """Array (numpy or torch) from an array or an astropy-like Quantity array (converted to ``unit`` first)."""
+    if hasattr(x, 'to') and hasattr(x, 'unit'):
+        import astropy.units as u
+        return x.to(getattr(u, unit)).value
+    return x
+
+
+def poisson_process(rate):
+    """Poisson distributed photon arrival times with expectation ``rate`` [1 / s / cm**2] (reference
+    basesources.py:15-62 ``poisson_process``), generated ON THE DEVICE: exponential waiting times (torch's
+    Philox stream) and their running sum, cut at the exposure time.  Returns the function
+    ``flux(exposuretime, geomarea)`` a source takes as its ``flux``."""
+    rate = _val(rate)
+
+    def poisson_rate(exposuretime, geomarea, device='cuda'):
+        full = rate * _val(geomarea)
+        t_exp = _val(exposuretime, 's')
+        # 10 % more numbers than expected (+ 5 sigma), more if that was not enough
+        n = int(t_exp * full * 1.1 + 5. * np.sqrt(t_exp * full) + 16)
+        times = torch.cumsum(torch.empty(n, dtype=torch.float64, device=device).exponential_(full), 0)
+        while float(times[-1]) < t_exp:
+            more = torch.cumsum(torch.empty(n, dtype=torch.float64, device=device).exponential_(full), 0) + times[-1]
+            times = torch.cat([times, more])
+        return times[times < t_exp]
+    return poisson_rate
+
+
 def _radec(coords):
     if hasattr(coords, 'ra') and hasattr(coords, 'dec'):
         c = coords.icrs if hasattr(coords, 'icrs') else coords
@@ -85,18 +113,71 @@ class Source(SimulationSequenceElement):
     # ---- specification -> numbers ---------------------------------------------------------
     def _rate(self):
         if callable(self.flux):
-            raise SourceSpecificationError('callable flux (e.g. a Poisson process) is not supported on the device: '
-                                           'only a constant flux')
+            return float('inf')      # dt = 0: the time column comes from the callable (GENERATE flag bit 2)
         return _val(self.flux) * _val(self.geomarea)
 
     def n_photons(self, exposuretime):
+        if callable(self.flux):
+            raise SourceSpecificationError('the photon count of a callable flux is only known after calling it: '
+                                           'use generate_photons() / observe()')
         # len(np.arange(0, T, dt)) without materialising it: numpy computes ceil((stop - start) / step)
         return max(int(np.ceil((_val(exposuretime, 's') - 0.) / (1. / self._rate()))), 0)
+
+    def has_callables(self):
+        return callable(self.flux) or callable(self.energy) or callable(self.polarization)
+
+    def evaluate_callables(self, exposuretime, device):
+        """Callable flux(exposuretime, geomarea), energy(times), polarization(times, energies) (reference
+        basesources.py:167-214) are user code: they are called once per observation, on the host or - when
+        they return torch tensors, like `poisson_process` here - on the device, and their results enter the
+        kernel as input columns.  Returns {'time': t, 'energy': e, 'polangle': p} (device tensors, only the
+        callable ones) and the photon count (None when the flux is constant)."""
+        out = {}
+
+        def as_dev(x, unit):
+            x = _strip(x, unit)
+            if isinstance(x, torch.Tensor):
+                return x.to(device=device, dtype=torch.float64)
+            return torch.as_tensor(np.asarray(x, dtype=float), device=device)
+
+        def for_user(t):      # user functions get what they can digest: numpy unless they produced tensors
+            return t if getattr(self, '_callables_take_tensors', False) else t.cpu().numpy()
+        n = None
+        if callable(self.flux):
+            t = self.flux(exposuretime, self.geomarea)
+            self._callables_take_tensors = isinstance(_strip(t, 's'), torch.Tensor)
+            out['time'] = as_dev(t, 's')
+            n = int(out['time'].shape[0])
+        if callable(self.energy) or callable(self.polarization):
+            if 'time' in out:
+                times = out['time']
+            else:
+                n_const = self.n_photons(exposuretime)
+                times = torch.arange(n_const, dtype=torch.float64, device=device) * (1. / self._rate())
+            if callable(self.energy):
+                e = self.energy(for_user(times))
+                out['energy'] = as_dev(e, 'keV')
+                if out['energy'].shape[0] != times.shape[0]:
+                    raise SourceSpecificationError('`energy` has to return an array of same size as input time array.')
+            if callable(self.polarization):
+                if 'energy' not in out and not (hasattr(self.energy, 'columns') or isinstance(self.energy, dict)):
+                    energies = torch.full_like(times, _val(self.energy, 'keV'))
+                elif 'energy' in out:
+                    energies = out['energy']
+                else:
+                    raise SourceSpecificationError('a callable polarization(times, energies) needs a constant or a '
+                                                   'callable energy: tabulated energies are drawn inside the kernel')
+                pol = self.polarization(for_user(times), for_user(energies))
+                out['polangle'] = as_dev(pol, 'rad')
+                if out['polangle'].shape[0] != times.shape[0]:
+                    raise SourceSpecificationError('`polarization` has to return an array of same size as input time '
+                                                   'and energy arrays.')
+        return out, n
 
     def _energy_spec(self):
         e = self.energy
         if callable(e):
-            raise SourceSpecificationError('callable energy is not supported on the device')
+            return 0, 0., None       # read from the energy plane (GENERATE flag bit 0)
         if hasattr(e, 'columns') or isinstance(e, dict):
             x = _column(e, 'energy')
             y = np.hstack(([0], _column(e, 'fluxdensity')[1:]))
@@ -106,7 +187,7 @@ class Source(SimulationSequenceElement):
     def _pol_spec(self):
         p = self.polarization
         if callable(p):
-            raise SourceSpecificationError('callable polarization is not supported on the device')
+            return 0, 0., None       # read from the polangle column (GENERATE flag bit 1)
         if p is None:
             return 1, 0., None
         if hasattr(p, 'columns') or isinstance(p, dict):
@@ -121,6 +202,7 @@ class Source(SimulationSequenceElement):
         lw.born = True
         e_mode, e_const, e_tab = self._energy_spec()
         p_mode, p_const, p_tab = self._pol_spec()
+        flags = (1 if callable(self.energy) else 0) | (2 if callable(self.polarization) else 0) | (4 if callable(self.flux) else 0)
         vals = [1. / self._rate(), e_mode, e_const, -1., p_mode, p_const, -1., 1. if self.sky else 0.,
                 getattr(self, 'ra', 0.), getattr(self, 'dec', 0.)]
         if e_tab is not None and p_tab is not None:
@@ -143,7 +225,7 @@ class Source(SimulationSequenceElement):
         cols = [lw.fcol('time'), lw.fcol('polangle')]
         if self.sky:
             cols += [lw.fcol('ra'), lw.fcol('dec')]
-        lw.op('GENERATE', pg=off, cols=cols, s0=s[0], s1=s[1], w14=s[2], w15=s[3])
+        lw.op('GENERATE', flags=flags, pg=off, cols=cols, s0=s[0], s1=s[1], w14=s[2], w15=s[3])
 
     def _drop_after_birth(self):
         return ('pos', 'dir', 'polarization')
@@ -151,11 +233,8 @@ class Source(SimulationSequenceElement):
     def generate_photons(self, exposuretime, device=None, id0=0):
         """Photon table born on the device (reference :234-277): columns time, energy, polangle,
         probability (+ ra, dec / pos, dir, polarization depending on the source)."""
-        n = self.n_photons(exposuretime)
-        photons = _empty_batch(n, device, id0)
-        photons.meta['EXTNAME'] = 'EVENTS'
-        photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
-        _run_born([self], photons)
+        photons, given = _born_table(self, exposuretime, device, id0, None, None)
+        _run_born([self], photons, given=given)
         for c in self._drop_after_birth():
             photons.remove_column(c)
         return photons
@@ -313,16 +392,50 @@ def _empty_batch(n, device, id0):
     return photons
 
 
+def _born_table(source, exposuretime, device, id0, n, out):
+    """Empty table for one observation; columns of callable source specifications already filled.
+    Returns (photons, names of the filled columns)."""
+    given = {}
+    n_call = None
+    if source.has_callables():
+        dev = torch.device(device if device is not None else 'cuda')
+        given, n_call = source.evaluate_callables(exposuretime, dev)
+    if n is not None:
+        n_tot = int(n)
+        given = {k: v[id0:id0 + n_tot] for k, v in given.items()}      # this rank's shard of the host-made columns
+    else:
+        n_tot = n_call if n_call is not None else source.n_photons(exposuretime)
+    if out is not None and len(out) == n_tot:
+        photons = out                      # reuse the table (and its memory) of a previous observation
+        photons.id0 = id0
+    else:
+        photons = _empty_batch(n_tot, device, id0)
+    photons.meta['EXTNAME'] = 'EVENTS'
+    photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
+    names = []
+    for k, v in given.items():
+        if v.shape[0] != n_tot:
+            raise SourceSpecificationError('callable source specifications returned {0} values for {1} photons'.format(
+                v.shape[0], n_tot))
+        if k == 'energy':
+            photons['energy'][...] = v
+        else:
+            photons[k] = v
+            names.append(k)
+    return photons, names
+
+
 _born_cache = {}
 
 
-def _run_born(elements, photons, check=True):
-    """Lower (cached under the fingerprint of the element trees, like simulator._lower_run) and launch."""
+def _run_born(elements, photons, check=True, given=()):
+    """Lower (cached under the fingerprint of the element trees, like simulator._lower_run) and launch.
+    ``given``: columns the host filled before the launch (results of callable source specifications)."""
     from ..simulator import fingerprint
-    key = fingerprint(elements, ('born', photons.meta))
+    key = fingerprint(elements, ('born', photons.meta, tuple(given)))
     prog = _born_cache.get(key)
     if prog is None:
-        lw = Lowering([], meta=photons.meta)
+        lw = Lowering(list(given), meta=photons.meta)
         for e in elements:
             e._lower(lw)
         prog = lw.finish()
@@ -342,17 +455,10 @@ def observe(source, pointing, elements, exposuretime, device=None, id0=0, n=None
     cannot be fused."""
     from ..simulator import _lowerable, Sequence
     chain = [source] + ([pointing] if pointing is not None else []) + list(elements)
-    n_tot = source.n_photons(exposuretime) if n is None else int(n)
-    if out is not None and len(out) == n_tot:
-        photons = out                      # reuse the table (and its memory) of a previous observation
-        photons.id0 = id0
-    else:
-        photons = _empty_batch(n_tot, device, id0)
-    photons.meta['EXTNAME'] = 'EVENTS'
-    photons.meta['EXPOSURE'] = (_val(exposuretime, 's'), 'total exposure time [s]')
+    photons, given = _born_table(source, exposuretime, device, id0, n, out)
     if all(_lowerable(e) or isinstance(e, (Source, FixedPointing)) for e in chain):
         try:
-            _run_born(chain, photons, check=check)
+            _run_born(chain, photons, check=check, given=given)
             return photons
         except NotFusable:
             pass

@@ -413,6 +413,66 @@ def test_scatter_callable(mode):
     assert '_mxb_angle' not in p
 
 
+def test_callable_source_specifications(mode):
+    """Callable flux(exposuretime, geomarea), energy(times), polarization(times, energies) (reference
+    basesources.py:167-214): evaluated once, then input columns of the birth kernel.  Callables that restate
+    constant specifications must reproduce the constant run bit for bit (same seed, same draws); arbitrary
+    callables must come through untouched; wrong lengths raise like the reference; poisson_process statistics."""
+    import torch
+    from marxs_b200 import optics, source
+    mb = _mb()
+    from scipy import stats
+    T, rate, area = 50., 40., 5.
+    apert = optics.RectangleAperture(position=[50., 0, 0], zoom=[1, 3, 2])
+    point = source.FixedPointing(coords=(30., 40.), roll=0.3)
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 10, 10])
+
+    def run(**kw):
+        src = source.PointSource(coords=(30.002, 40.001), geomarea=area, **kw)
+        mb.set_seed(11)
+        return source.observe(src, point, [apert, det], T, device='cuda').to_numpy()
+    base = run(flux=rate, energy=1.7, polarization=0.4)
+    n = len(base['time'])
+    assert n == int(np.ceil(T * rate * area))
+    same = run(flux=lambda exposuretime, geomarea: np.arange(0, exposuretime, 1. / (rate * geomarea)),
+               energy=lambda t: np.full(len(t), 1.7), polarization=lambda t, e: np.full(len(t), 0.4))
+    assert set(same.keys()) == set(base.keys())
+    for c in base:
+        assert np.array_equal(same[c], base[c], equal_nan=True), c
+    # arbitrary callables: values arrive untouched and are used by the trace (energy-dependent columns move)
+    tt = np.sort(np.random.default_rng(3).uniform(0, T, 5000))
+    out = run(flux=lambda exposuretime, geomarea: tt, energy=lambda t: 0.5 + 0.01 * t,
+              polarization=lambda t, e: 0.1 * e)
+    assert np.array_equal(out['time'], tt) and np.allclose(out['energy'], 0.5 + 0.01 * tt, rtol=0, atol=0)
+    assert np.array_equal(out['polangle'], 0.1 * (0.5 + 0.01 * tt))
+    assert np.isfinite(out['det_x']).mean() > 0.9
+    # ... also through generate_photons (the reference's call pattern) and a lab source (LABCONE reads polangle)
+    src = source.PointSource(coords=(30., 40.), flux=lambda exposuretime, geomarea: tt, energy=lambda t: 0.5 + 0.01 * t)
+    ph = src.generate_photons(T, device='cuda').to_numpy()
+    assert np.array_equal(ph['time'], tt) and np.array_equal(ph['energy'], 0.5 + 0.01 * tt) and (ph['probability'] == 1).all()
+    lab = source.LabPointSourceCone(position=[10., 0, 0], direction=[-1., 0, 0], half_opening=0.1, flux=100.,
+                                    polarization=lambda t, e: np.full(len(t), 0.5 * np.pi))
+    lp = lab.generate_photons(3., device='cuda').to_numpy()
+    assert len(lp['time']) == 300 and np.allclose(lp['polangle'], 0.5 * np.pi)
+    assert np.allclose(np.sum(lp['polarization'] * lp['dir'], axis=1), 0, atol=1e-12)
+    # wrong lengths raise like the reference (basesources.py:184-185, 206-207)
+    with pytest.raises(source.SourceSpecificationError):
+        source.PointSource(coords=(30., 40.), flux=10., energy=lambda t: np.ones(3)).generate_photons(5., device='cuda')
+    with pytest.raises(source.SourceSpecificationError):
+        source.PointSource(coords=(30., 40.), flux=10., polarization=lambda t, e: np.ones(3)).generate_photons(5., device='cuda')
+    # Poisson arrival times made on the device: count ~ Poisson(T rate area), waiting times ~ Exp, sorted, < T
+    torch.manual_seed(5)
+    big_t = 400.
+    src = source.PointSource(coords=(30., 40.), flux=source.poisson_process(rate), geomarea=area, energy=lambda t: 1. + 0. * t)
+    ph = src.generate_photons(big_t, device='cuda')
+    times = ph['time'].data.cpu().numpy()
+    mean = big_t * rate * area
+    assert abs(len(times) - mean) < 6 * np.sqrt(mean)
+    assert (np.diff(times) > 0).all() and times[-1] < big_t and times[0] > 0
+    assert stats.kstest(np.diff(times), 'expon', args=(0, 1. / (rate * area))).pvalue > 1e-3
+    assert (ph['energy'].data == 1.).all()
+
+
 def test_lens_reflectivity(mode):
     """PerfectLens(reflectivity_interpolator=...) (mirror.py:68-81) on the device: against the unmodified
     reference (tests/golden/lens_reflectivity.npz, RectBivariateSpline k=1 given as such), against the
