@@ -373,6 +373,7 @@ def run_engine(args):
                             l2='every step streams the 0.88 GB input table and 2.4 GB of outputs (>> 126 MB L2); no flush needed',
                             build=lib.mxb_build_info().decode(), parallelism='photon-range sharding x{0}'.format(world)),
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                              frac_of_nominal_8tbs=achieved / 8000.,      # BASELINE.json quotes the roofline against 8 TB/s
                               traffic=(traffic * n if traffic else None), peak_source=peak_src,
                               kernel=('mxb_jit_kernel (program-specialised, NVRTC sm_100a)'
                                       if kernel_path.startswith('jit') else 'mxb_trace_kernel<true> (interpreter)'),
