@@ -41,48 +41,72 @@ def fingerprint(objs, extra=()):
     import torch
     h = hashlib.blake2b(digest_size=16)
     seen = set()
+    parts = []               # byte strings, hashed in one go at the end (one update instead of ~10 per element)
+    add = parts.append
+    scalars = (bool, int, float, str, bytes, type(None))
+    opaque = (type, types.FunctionType, types.BuiltinFunctionType, types.MethodType, types.ModuleType)
 
     def feed(v, depth):
-        if v is None or isinstance(v, (bool, int, float, str, bytes)):
-            h.update(repr(v).encode())
-        elif isinstance(v, np.ndarray):
-            h.update(('A' + v.dtype.str + str(v.shape)).encode())
-            h.update(np.ascontiguousarray(v).view(np.uint8).tobytes() if v.dtype != object else repr(v.tolist()).encode())
-        elif isinstance(v, np.generic):
-            h.update(repr(v.item()).encode())
-        elif isinstance(v, torch.Tensor):
-            h.update('T{0}{1}{2}'.format(v.data_ptr(), tuple(v.shape), v.dtype).encode())
-        elif isinstance(v, (list, tuple)):
-            h.update(b'[')
+        t = type(v)
+        if t in scalars:                                  # exact types first: the common leaves
+            add(repr(v).encode())
+        elif t is np.ndarray:
+            add(('A' + v.dtype.str + str(v.shape)).encode())
+            add(np.ascontiguousarray(v).tobytes() if v.dtype != object else repr(v.tolist()).encode())
+        elif t is dict:
+            add(b'{')
+            for k in sorted(v, key=repr):
+                add(repr(k).encode())
+                feed(v[k], depth + 1)
+            add(b'}')
+        elif t is list or t is tuple:
+            add(b'[')
             for x in v:
                 feed(x, depth + 1)
-            h.update(b']')
+            add(b']')
+        elif isinstance(v, scalars):                      # subclasses (np.float64 is a float, enums ...)
+            add(repr(v).encode())
+        elif isinstance(v, np.ndarray):
+            add(('A' + v.dtype.str + str(v.shape)).encode())
+            add(np.ascontiguousarray(v).view(np.uint8).tobytes() if v.dtype != object else repr(v.tolist()).encode())
+        elif isinstance(v, np.generic):
+            add(repr(v.item()).encode())
+        elif isinstance(v, torch.Tensor):
+            add('T{0}{1}{2}'.format(v.data_ptr(), tuple(v.shape), v.dtype).encode())
+        elif isinstance(v, (list, tuple)):
+            add(b'[')
+            for x in v:
+                feed(x, depth + 1)
+            add(b']')
         elif isinstance(v, dict):
-            h.update(b'{')
+            add(b'{')
             for k in sorted(v, key=repr):
-                h.update(repr(k).encode())
+                add(repr(k).encode())
                 feed(v[k], depth + 1)
-            h.update(b'}')
-        elif isinstance(v, (type, types.FunctionType, types.BuiltinFunctionType, types.MethodType, types.ModuleType)):
-            h.update('F{0}{1}'.format(getattr(v, '__qualname__', ''), id(v)).encode())
+            add(b'}')
+        elif isinstance(v, opaque):
+            add('F{0}{1}'.format(getattr(v, '__qualname__', ''), id(v)).encode())
         else:
             d = getattr(v, '__dict__', None)
             if d is None or depth > 12:
-                h.update('O{0}{1}'.format(type(v).__qualname__, id(v)).encode())
+                add('O{0}{1}'.format(t.__qualname__, id(v)).encode())
             elif id(v) in seen:
-                h.update(b'@')
+                add(b'@')
             else:
                 seen.add(id(v))
-                h.update(type(v).__qualname__.encode())
+                add(t.__qualname__.encode())
                 skip = getattr(v, '_fingerprint_skip', ())
-                for k in sorted(d):
+                # attribute order = assignment order: objects built the same way agree; a different order can
+                # only cause a cache miss, never a false hit
+                for k, x in d.items():
                     if k in _FP_SKIP or k in skip:
                         continue
-                    h.update(k.encode())
-                    feed(d[k], depth + 1)
+                    add(k.encode())
+                    feed(x, depth + 1)
     for o in objs:
         feed(o, 0)
     feed(extra, 0)
+    h.update(b'\x00'.join(parts))
     return h.digest()
 
 
