@@ -6,5 +6,5 @@ from .mirror import PerfectLens, ReflectivityTable
 from .baffles import Baffle, CircularBaffle
 from .scatter import RadialMirrorScatter, RandomGaussianScatter
 from .filter import EnergyFilter, GlobalEnergyFilter, Tabulated1D
-from .base import OpticalElement, FlatOpticalElement, FlatStack
+from .base import OpticalElement, FlatOpticalElement, FlatStack, photonlocalcoords
 from .multiLayerMirror import FlatBrewsterMirror, MultiLayerEfficiency, MultiLayerMirror

@@ -18,7 +18,7 @@ from ..geometry import Geometry, FinitePlane, Cylinder
 from ..program import NotFusable
 from ..simulator import BaseContainer, run_fused
 
-__all__ = ['OpticalElement', 'FlatOpticalElement', 'FlatStack']
+__all__ = ['OpticalElement', 'FlatOpticalElement', 'FlatStack', 'photonlocalcoords']
 
 _PY_HOOKS = ('specific_process_photons', 'process_photons', 'process_photon', '__call__')
 
@@ -136,6 +136,25 @@ class OpticalElement(SimulationSequenceElement):
             photons[self.id_col][intersect] = self.id_num
         photons['pos'][intersect] = interpos[intersect]
         return photons
+
+
+def photonlocalcoords(f, colnames=['pos', 'dir']):
+    """Decorator for ``process_photons``-like methods of user elements that want to calculate in the LOCAL
+    coordinate system of the element (reference optics/base.py:284-316): the homogeneous columns ``colnames``
+    are multiplied by ``inv(self.pos4d)`` before the call and by ``self.pos4d`` after it, on the device."""
+    from functools import wraps
+
+    @wraps(f)
+    def wrapper(self, photons, *args, **kwargs):
+        inv = torch.as_tensor(np.linalg.inv(self.pos4d), dtype=torch.float64, device=photons.device)
+        fwd = torch.as_tensor(np.asarray(self.pos4d, dtype=float), dtype=torch.float64, device=photons.device)
+        for n in colnames:       # einsum('...ij,...j', M, v) = v @ M.T
+            photons[n] = photons[n].data.as_subclass(torch.Tensor) @ inv.T
+        photons = f(self, photons, *args, **kwargs)
+        for n in colnames:
+            photons[n] = photons[n].data.as_subclass(torch.Tensor) @ fwd.T
+        return photons
+    return wrapper
 
 
 class _LoadHitWrapper:

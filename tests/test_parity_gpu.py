@@ -473,6 +473,38 @@ def test_callable_source_specifications(mode):
     assert (ph['energy'].data == 1.).all()
 
 
+def test_photonlocalcoords_decorator():
+    """optics/base.py:284-316: a user element calculating in its local frame sees pos / dir transformed by
+    inv(pos4d) and gets them transformed back; the table round-trips to 1e-12."""
+    import torch
+    from marxs_b200 import optics
+    mb = _mb()
+    rng = np.random.default_rng(SEED + 50)
+    pos4d = rand_pos4d(rng, zoom=(1., 12., 9.))
+    table = make_photons(rng, 2000, spread=0.2)
+    seen = {}
+
+    class Local(optics.FlatOpticalElement):
+        @optics.photonlocalcoords
+        def process_photons(self, photons, intersect, interpos, intercoos):
+            seen['pos'] = photons['pos'].data.clone()
+            seen['dir'] = photons['dir'].data.clone()
+            photons['probability'][intersect] *= 0.5
+            return photons
+
+        def _can_lower(self):
+            return False
+
+    out = Local(pos4d=pos4d)(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    inv = np.linalg.inv(pos4d)
+    np.testing.assert_allclose(seen['pos'].cpu().numpy(), np.einsum('...ij,...j', inv, table['pos']), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(seen['dir'].cpu().numpy(), np.einsum('...ij,...j', inv, table['dir']), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out['pos'], table['pos'], rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(out['dir'], table['dir'], rtol=1e-12, atol=1e-12)
+    hit = out['probability'] < table['probability']
+    assert 0.05 < hit.mean() < 1 and np.allclose(out['probability'][hit], 0.5 * table['probability'][hit])
+
+
 def test_lens_reflectivity(mode):
     """PerfectLens(reflectivity_interpolator=...) (mirror.py:68-81) on the device: against the unmodified
     reference (tests/golden/lens_reflectivity.npz, RectBivariateSpline k=1 given as such), against the
