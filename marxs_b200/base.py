@@ -11,7 +11,7 @@ import torch
 
 from . import affines
 
-__all__ = ['GeometryError', 'MarxsElement', 'SimulationSequenceElement', '_parse_position_keywords']
+__all__ = ['GeometryError', 'MarxsElement', 'SimulationSequenceElement', 'TagVersion', '_parse_position_keywords']
 
 
 class GeometryError(Exception):
@@ -34,6 +34,29 @@ class MarxsElement:
 
     def describe(self):
         return OrderedDict(element=self.name)
+
+
+class TagVersion(MarxsElement):
+    """Tag a photon list with diagnostic information (reference base/base.py:100-139): every keyword given at
+    construction or at call time goes into ``photons.meta`` together with the date and the engine version.
+    Host-side bookkeeping only; the table stays on the device."""
+
+    def __init__(self, ORIGIN=('unkwown', 'Institution where file was created'),
+                 CREATOR=('MARXS', 'Person or program creating file'), **kwargs):
+        super().__init__(name=kwargs.pop('name', self.__class__))
+        from . import _lib
+        kwargs['ORIGIN'], kwargs['CREATOR'] = ORIGIN, CREATOR
+        kwargs['MARXSVER'] = ('marxs_b200 ABI {0}'.format(_lib.MXB_ABI_VERSION), 'MARXS code version')
+        self.tags = kwargs
+
+    def __call__(self, photons, *args, **kwargs):
+        from datetime import datetime
+        photons.meta['DATE'] = (datetime.now().isoformat()[:10], 'Date/time of computation')
+        for k, v in self.tags.items():
+            photons.meta[k] = v
+        for k, v in kwargs.items():
+            photons.meta[k] = v
+        return photons
 
 
 class SimulationSequenceElement(MarxsElement):

@@ -348,3 +348,14 @@ def test_source_and_pointing_host_logic():
     assert p[21] == 1e-5
     with pytest.raises(source.SourceSpecificationError):
         source.PointSource(coords=(1., 2.), flux=lambda t, a: t).n_photons(1.)
+
+
+def test_tagversion_writes_meta():
+    """base/base.py:100-139: TagVersion adds its keywords, the date and the code version to photons.meta."""
+    from marxs_b200.base import TagVersion
+
+    class Table:
+        meta = {}
+    t = TagVersion(OBSERVER=('me', 'who ran this'))(Table(), OBS_ID=5)
+    assert t.meta['OBSERVER'][0] == 'me' and t.meta['OBS_ID'] == 5
+    assert t.meta['CREATOR'][0] == 'MARXS' and 'MARXSVER' in t.meta and len(t.meta['DATE'][0]) == 10
