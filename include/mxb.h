@@ -14,6 +14,7 @@
  *                           + every specific_process_photons listed per op code below
  *   mxb_plane_intersect  <- math/geometry.py:211-261,376-380 FinitePlane/CircularHole.intersect
  *   mxb_parallel_transport <- math/polarization.py:151-170  parallel_transport
+ *   mxb_polarization_vectors <- math/polarization.py:12-62  polarization_vectors
  *   mxb_hist2d           <- (no reference analogue; detector image for the multi-GPU epilogue)
  *   mxb_trace_host       <- same call as mxb_trace for HOST-resident photon columns
  *
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 8
+#define MXB_ABI_VERSION 9
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -239,6 +240,11 @@ int mxb_plane_intersect(const double* geom14_host, int circular,
 int mxb_parallel_transport(const double* const dir_old[3], const double* const dir_new[3],
                            const double* const pol_old[3], double* const pol_new[3],
                            int64_t n, void* stream);
+
+/* polarization_vectors(dir_array, angles) -> polarization  (math/polarization.py:12-62): unit vector
+ * perpendicular to dir at angle `angle` from the direction closest to +y (closest to +x when dir is parallel to y) */
+int mxb_polarization_vectors(const double* const dir[3], const double* angle, double* const pol[3],
+                             int64_t n, void* stream);
 
 /* Detector images for the multi-GPU epilogue: photon i falls into plane p = sel[i] - sel_lo
  * (0 <= p < n_sel; sel == NULL: one plane) at pixel ix = round(x[i] - x0), iy = round(y[i] - y0)

@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 8
+MXB_ABI_VERSION = 9
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -71,6 +71,8 @@ def load(strict=None):
     lib.mxb_plane_intersect.argtypes = [vp, ci, vp, vp, vp, vp, vp, i64, vp]
     lib.mxb_parallel_transport.restype = ci
     lib.mxb_parallel_transport.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.mxb_polarization_vectors.restype = ci
+    lib.mxb_polarization_vectors.argtypes = [vp, vp, vp, i64, vp]
     lib.mxb_hist2d.restype = ci
     lib.mxb_hist2d.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, ci, ctypes.c_double, ctypes.c_double, i64, ci, ci, vp, vp, vp]
     lib.mxb_set_jit.restype = None
@@ -108,5 +110,5 @@ def check(lib, rc, what):
 
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
-                    'mxb_trace_from', 'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_hist2d',
+                    'mxb_trace_from', 'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
                     'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events']

@@ -598,6 +598,18 @@ parallel_transport_kernel(const double* ax, const double* ay, const double* az, 
 }
 
 __global__ void __launch_bounds__(256)
+polarization_vectors_kernel(const double* dx, const double* dy, const double* dz, const double* angle,
+                            double* ox, double* oy, double* oz, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const V3 r = polarization_vector(V3{dx[i], dy[i], dz[i]}, angle[i]);
+        ox[i] = r.x;
+        oy[i] = r.y;
+        oz[i] = r.z;
+    }
+}
+
+__global__ void __launch_bounds__(256)
 hist2d_kernel(const double* x, const double* y, const double* w, const long long* sel, long long sel_lo,
               int n_sel, double x0, double y0, long long n, int nx, int ny, double* img,
               unsigned long long* counts) {
@@ -979,6 +991,16 @@ int mxb_parallel_transport(const double* const dir_old[3], const double* const d
     parallel_transport_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         dir_old[0], dir_old[1], dir_old[2], dir_new[0], dir_new[1], dir_new[2], pol_old[0], pol_old[1],
         pol_old[2], pol_new[0], pol_new[1], pol_new[2], n);
+    CUDA_TRY(cudaGetLastError());
+    return MXB_OK;
+}
+
+int mxb_polarization_vectors(const double* const dir[3], const double* angle, double* const pol[3], int64_t n,
+                             void* stream) {
+    if (!dir || !angle || !pol) return fail(MXB_EINVAL, "null pointer");
+    if (n <= 0) return n == 0 ? MXB_OK : fail(MXB_EINVAL, "negative n");
+    polarization_vectors_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dir[0], dir[1], dir[2], angle,
+                                                                                      pol[0], pol[1], pol[2], n);
     CUDA_TRY(cudaGetLastError());
     return MXB_OK;
 }

@@ -194,6 +194,35 @@ def test_parallel_transport_golden(mode):
         assert np.array_equal(out.cpu().numpy(), mo.parallel_transport(g['dir_old'], g['dir_new'], g['pol_old']))
 
 
+def test_polarization_vectors_and_transport_matrix(mode):
+    """math/polarization.py:12-62 polarization_vectors against the unmodified reference (tests/golden/sources.npz)
+    and the oracle; :90-149 paralleltransport_matrix (identity Jones matrix) against the reference's defining
+    property M(dir1, dir2) @ pol == parallel_transport(dir1, dir2, pol) and the identity for unchanged rays."""
+    from marxs_b200.polarization import polarization_vectors, paralleltransport_matrix, parallel_transport
+    g = load('sources')
+    out = polarization_vectors(torch.tensor(g['polvec_dir'], device='cuda'), torch.tensor(g['polvec_angle'], device='cuda'))
+    np.testing.assert_allclose(out.cpu().numpy(), g['polvec_out'], rtol=1e-12, atol=1e-14)
+    rng = np.random.default_rng(SEED + 60)
+    n = 5000
+    d = np.zeros((n, 4))
+    d[:, :3] = rng.normal(size=(n, 3))
+    d[:5, :3] = [0., 2.5, 0.]                       # along y: the +x convention
+    ang = rng.uniform(-4, 4, n)
+    out = polarization_vectors(torch.tensor(d, device='cuda'), torch.tensor(ang, device='cuda')).cpu().numpy()
+    np.testing.assert_allclose(out, mo.polarization_vectors(d, ang), rtol=1e-12, atol=1e-14)
+    assert np.allclose(np.sum(out[:, :3] * d[:, :3], axis=1), 0, atol=1e-12) and np.allclose(np.linalg.norm(out, axis=1), 1)
+    d2 = np.zeros((n, 4))
+    d2[:, :3] = rng.normal(size=(n, 3))
+    d2[:10] = d[:10]                                # unchanged rays: identity
+    pol = mo.polarization_vectors(d, ang)
+    t1, t2, tp = (torch.tensor(x, device='cuda') for x in (d, d2, pol))
+    M = paralleltransport_matrix(t1[:, :3], t2[:, :3])
+    assert M.shape == (n, 3, 3)
+    got = torch.einsum('nij,nj->ni', M, tp[:, :3]).cpu().numpy()
+    np.testing.assert_allclose(got, parallel_transport(t1, t2, tp)[:, :3].cpu().numpy(), rtol=1e-12, atol=1e-13)
+    assert torch.equal(M[:10], torch.eye(3, dtype=torch.float64, device='cuda').expand(10, 3, 3))
+
+
 @pytest.mark.parametrize('kind', ['flat', 'cat', 'refl', 'nonparallel'])
 def test_grating_vs_oracle(mode, kind):
     from marxs_b200 import optics
