@@ -11,7 +11,8 @@ import torch
 
 from . import affines
 
-__all__ = ['GeometryError', 'MarxsElement', 'SimulationSequenceElement', 'TagVersion', '_parse_position_keywords']
+__all__ = ['GeometryError', 'MarxsElement', 'SimulationSequenceElement', 'TagVersion', 'check_meta_consistent',
+           'check_energy_consistent', '_parse_position_keywords']
 
 
 class GeometryError(Exception):
@@ -57,6 +58,30 @@ class TagVersion(MarxsElement):
         for k, v in kwargs.items():
             photons.meta[k] = v
         return photons
+
+
+def check_meta_consistent(meta1, meta2, keywords=['ORIGIN', 'CREATOR', 'MARXSVER', 'MARXSGIT', 'MARXSTIM'],
+                          allow_missing=True):
+    """Raise AssertionError / KeyError unless the two headers agree on ``keywords`` (reference
+    base/base.py:142-182): a keyword may be missing from both (``allow_missing``), never from only one."""
+    for k in keywords:
+        if (k in meta1) and (k in meta2):
+            assert meta1[k] == meta2[k]
+        else:
+            if not allow_missing:
+                raise KeyError('{0} not found in both dicts.'.format(k))
+            if (k in meta1) or (k in meta2):
+                raise KeyError('{0} found in one, but not both dicts.'.format(k))
+
+
+def check_energy_consistent(photons):
+    """Assert that all photons have the same energy (reference base/base.py:185-191); passes without an
+    energy column.  One reduction on the device."""
+    if 'energy' in photons.colnames:
+        e = photons['energy']
+        e = e.data if hasattr(e, 'data') and isinstance(getattr(e, 'data'), torch.Tensor) else torch.as_tensor(np.asarray(e))
+        if e.numel():
+            assert bool(torch.isclose(e, e[0], rtol=1e-05, atol=1e-08).all())
 
 
 class SimulationSequenceElement(MarxsElement):

@@ -6,5 +6,5 @@ exposuretime)`` lowers source + pointing + aperture + instrument into ONE progra
 observation is a single kernel launch that reads nothing and writes the event table.  Callable flux /
 energy / polarization specifications (user code) are evaluated once per observation and enter the kernel as
 input columns; ``poisson_process(rate)`` makes Poisson arrival times on the device."""
-from .source import (Source, PointSource, LabPointSourceCone, FarLabPointSource, FixedPointing,  # noqa: F401
+from .source import (Source, PointSource, LabPointSourceCone, FarLabPointSource, PointingModel, FixedPointing,  # noqa: F401
                      JitterPointing, RandomArbitraryPdfTable, observe, SourceSpecificationError, poisson_process)

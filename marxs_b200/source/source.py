@@ -319,7 +319,12 @@ def skyoffset_matrix(ra0, dec0, roll):
     return rot(-roll, 'x') @ rot(-dec0, 'y') @ rot(ra0, 'z')
 
 
-class FixedPointing(SimulationSequenceElement):
+class PointingModel(SimulationSequenceElement):
+    """Base class of the pointing models (reference pointing.py:14-42): a pointing turns ra / dec / polangle of
+    a photon list into ``dir`` and ``polarization`` in the spacecraft system."""
+
+
+class FixedPointing(PointingModel):
     """Photon directions and polarization vectors from ra, dec, polangle for a fixed pointing
     (reference pointing.py:45-177): x axis to the aimpoint, z axis North at roll 0."""
 

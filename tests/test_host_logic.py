@@ -359,3 +359,24 @@ def test_tagversion_writes_meta():
     t = TagVersion(OBSERVER=('me', 'who ran this'))(Table(), OBS_ID=5)
     assert t.meta['OBSERVER'][0] == 'me' and t.meta['OBS_ID'] == 5
     assert t.meta['CREATOR'][0] == 'MARXS' and 'MARXSVER' in t.meta and len(t.meta['DATE'][0]) == 10
+
+
+def test_check_meta_and_energy_consistent():
+    """base/base.py:142-191 semantics."""
+    import numpy as np
+    from marxs_b200.base import check_meta_consistent, check_energy_consistent
+    check_meta_consistent({'ORIGIN': 'a'}, {'ORIGIN': 'a'})
+    with pytest.raises(AssertionError):
+        check_meta_consistent({'ORIGIN': 'a'}, {'ORIGIN': 'b'})
+    with pytest.raises(KeyError):
+        check_meta_consistent({'ORIGIN': 'a'}, {})
+    with pytest.raises(KeyError):
+        check_meta_consistent({}, {}, allow_missing=False)
+
+    class T(dict):
+        colnames = ['energy']
+    check_energy_consistent(T(energy=np.ones(5)))
+    with pytest.raises(AssertionError):
+        check_energy_consistent(T(energy=np.array([1., 1.1])))
+    T2 = type('T2', (dict,), {'colnames': []})
+    check_energy_consistent(T2())
