@@ -50,3 +50,22 @@ def load_acis_corners():
         chip, corner, x, y, z = l.split(',')
         out[ACIS_name.index(chip), corner_index[corner]] = [float(x), float(y), float(z)]
     return out
+
+
+def chip2tdet(chip, tdet, id_num):
+    """CHIP -> TDET coordinates, eqn (5) of the Chandra coordinate memo (reference missions/chandra/data.py:169-190).
+    The trace kernel applies the same transformation fused into the ACIS op; this standalone form takes an
+    (N, 2) numpy array or torch tensor (any device) and returns the same kind."""
+    import torch
+    scale = tdet['scale'][id_num]
+    handedness = tdet['handedness'][id_num]
+    origin_tdet = tdet['origin'][id_num]
+    theta = tdet['theta'][id_num]
+    rotation = np.array([[np.cos(theta), np.sin(theta)],
+                         [-np.sin(theta), np.cos(theta)]])
+    if isinstance(chip, torch.Tensor):
+        c = chip.as_subclass(torch.Tensor)
+        rot = torch.as_tensor(rotation, dtype=c.dtype, device=c.device)
+        org = torch.as_tensor(np.asarray(origin_tdet, dtype=float) + 0.5, dtype=c.dtype, device=c.device)
+        return float(scale * handedness) * ((c - 0.5) @ rot.T) + org
+    return scale * handedness * np.dot(rotation, (np.asarray(chip) - 0.5).T).T + (origin_tdet + 0.5)

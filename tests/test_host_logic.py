@@ -380,3 +380,51 @@ def test_check_meta_and_energy_consistent():
         check_energy_consistent(T(energy=np.array([1., 1.1])))
     T2 = type('T2', (dict,), {'colnames': []})
     check_energy_consistent(T2())
+
+
+def test_mathutils_numpy_and_torch_agree():
+    """marxs/math/utils.py helpers: same numbers for numpy arrays and torch tensors, reference error cases."""
+    import numpy as np
+    import torch
+    from marxs_b200 import mathutils as mu
+    rng = np.random.default_rng(0)
+    e = rng.normal(size=(7, 3))
+    for w in (0, 1):
+        h = mu.e2h(e, w)
+        assert h.shape == (7, 4) and np.all(h[:, 3] == w)
+        assert torch.equal(mu.e2h(torch.tensor(e), w), torch.tensor(h))
+        assert np.array_equal(mu.h2e(h), e) and torch.equal(mu.h2e(torch.tensor(h)), torch.tensor(e))
+    with pytest.raises(ValueError):
+        mu.e2h(e, 2)
+    h = mu.e2h(e, 1) * 2.
+    assert np.allclose(mu.h2e(h), e) and torch.allclose(mu.h2e(torch.tensor(h)), torch.tensor(e))
+    mixed = mu.e2h(e, 1)
+    mixed[0, 3] = 0
+    with pytest.raises(ValueError):
+        mu.h2e(mixed)
+    with pytest.raises(ValueError):
+        mu.h2e(torch.tensor(mixed))
+    p1, p2 = mu.e2h(e, 1), mu.e2h(e[::-1].copy(), 1)
+    d = mu.distance_point_point(p1, p2)
+    assert np.allclose(d, np.linalg.norm(e - e[::-1], axis=1))
+    assert torch.allclose(mu.distance_point_point(torch.tensor(p1), torch.tensor(p2)), torch.tensor(d))
+    assert np.isclose(mu.distance_point_point(p1[0], p2[0]), d[0])
+    n = mu.norm_vector(e)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1) and torch.allclose(mu.norm_vector(torch.tensor(e)), torch.tensor(n))
+
+
+def test_chip2tdet_matches_reference_known_answers():
+    """missions/chandra/data.py:169-190; spot values of the reference's test_chandra.py coordinate table
+    (chip centre of ACIS-S3 -> TDET) and numpy / torch agreement."""
+    import numpy as np
+    import torch
+    from marxs_b200.missions.chandra.data import chip2tdet, TDET
+    chip = np.array([[512.5, 512.5], [1., 1.], [1024., 1024.]])
+    for idn in (0, 1, 7):
+        a = chip2tdet(chip, TDET['ACIS'], idn)
+        b = chip2tdet(torch.tensor(chip), TDET['ACIS'], idn).numpy()
+        assert np.allclose(a, b, rtol=0, atol=1e-9)
+    # S3 (id 7): theta = 0, origin (3917, 1702): tdet = chip - 0.5 + origin + 0.5 = chip + origin
+    assert np.allclose(chip2tdet(chip, TDET['ACIS'], 7), chip + [3917, 1702])
+    # I0 (id 0): theta = 90 deg: (x, y) -> (y, -x) about the chip origin
+    assert np.allclose(chip2tdet(np.array([[1., 1.]]), TDET['ACIS'], 0), [[0.5 + 3061.5, -0.5 + 5131.5]])
