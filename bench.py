@@ -397,7 +397,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--photons', type=int, default=N_PER_GPU, help='photons per GPU per step')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--e2e-photons', type=int, default=0)
     ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--no-e2e', action='store_true')
