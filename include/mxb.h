@@ -109,7 +109,7 @@ typedef struct MxbColumns {
                                   flags bit0: L2Diffraction (mitsnl/catgrating.py:262-285): params innerfree,
                                   sigma = 1.22 * 0.4 * asin(lambda / innerfree) per photon                                         
                                   flags bit1: callable scatter (scatter.py:127-129): the angle is read from INPUT column c1, s0 unused  */
-#define MXB_OP_FILTER       9  /* filter.py:90-94 EnergyFilter: params n, x[n], y[n] (n==0: constant y[0]); flags bit0 bounds_error  */
+#define MXB_OP_FILTER       9  /* filter.py:90-94 EnergyFilter: params n, x[n], y[n] [, fill_lo, fill_hi] (n==0: constant y[0]); flags: 1 bounds_error, 2 fill values outside the table, 4 extrapolate (interp1d modes) */
 #define MXB_OP_GRATING     10  /* grating.py:233-277: params l[3] dd[3] d blaze0 dblaze ; flags bit0 CAT bit1 reflection
                                   bit2 blaze modifier; pg: selector block; s0 uniform; c0 order c1 blaze.
                                   flags bit3: L1 support (mitsnl/catgrating.py:170-219): s1 = second uniform, c2 = word offset

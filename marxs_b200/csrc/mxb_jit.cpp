@@ -777,7 +777,8 @@ struct Kernel {
     bool pipe = false;
     bool need_blob = false;
     std::string hash, origin;
-    int smem_attr_dev = -1;
+    // per-device launch state, guarded by g_mu (one process may drive several GPUs from several threads)
+    uint64_t smem_attr_devs = 0;      // bit d: MaxDynamicSharedMemorySize set on device d
     bool occupancy_known = false;
 };
 
@@ -1111,17 +1112,23 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     if (rc) return rc;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (k->smem_bytes > 48 * 1024 && k->smem_attr_dev != dev) {
-        cudaError_t ce = cudaFuncSetAttribute((const void*)k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k->smem_bytes);
-        if (ce != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(ce); return MXB_ECUDA; }
-        k->smem_attr_dev = dev;
-    }
-    if (!k->occupancy_known) {
-        k->occupancy_known = true;
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k->fn, k->threads, k->smem_bytes) == cudaSuccess && nb > 0)
-            k->blocks_per_sm = nb;
-        else { cudaGetLastError(); k->blocks_per_sm = 1; }
+    int blocks_per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        const uint64_t dev_bit = (dev >= 0 && dev < 64) ? (1ULL << dev) : 0ULL;
+        if (k->smem_bytes > 48 * 1024 && !(k->smem_attr_devs & dev_bit)) {
+            cudaError_t ce = cudaFuncSetAttribute((const void*)k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k->smem_bytes);
+            if (ce != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(ce); return MXB_ECUDA; }
+            k->smem_attr_devs |= dev_bit;
+        }
+        if (!k->occupancy_known) {
+            k->occupancy_known = true;
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k->fn, k->threads, k->smem_bytes) == cudaSuccess && nb > 0)
+                k->blocks_per_sm = nb;
+            else { cudaGetLastError(); k->blocks_per_sm = 1; }
+        }
+        blocks_per_sm = k->blocks_per_sm;
     }
     // parameter block: n id0 seed status prog f[] i[] d[] s[]   (all 8-byte words)
     std::vector<uint64_t> pw;
@@ -1147,7 +1154,7 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     for (int o : k->smap) { uint64_t u; memcpy(&u, prog_host + o, 8); pw.push_back(u); }
     if (k->smap.empty()) pw.push_back(0);
     long long blocks = (n + k->threads - 1) / k->threads;
-    const long long cap = (long long)sm_count_of(dev) * k->blocks_per_sm;
+    const long long cap = (long long)sm_count_of(dev) * blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     void* args[] = {pw.data()};
@@ -1156,7 +1163,7 @@ int launch(const double* prog_dev, const double* prog_host, size_t words, int n_
     if (ce != cudaSuccess) { cudaGetLastError(); *err = std::string("cudaLaunchKernel(jit): ") + cudaGetErrorString(ce); return MXB_ECUDA; }
     char b[256];
     snprintf(b, sizeof(b), "jit %s (%s): %d regs, %d threads x %lld CTAs (%d/SM), %d B staged, %d scalars, input pipe %s",
-             k->hash.c_str(), k->origin.c_str(), k->regs, k->threads, blocks, k->blocks_per_sm, k->stage_bytes,
+             k->hash.c_str(), k->origin.c_str(), k->regs, k->threads, blocks, blocks_per_sm, k->stage_bytes,
              (int)k->smap.size(), k->pipe ? ((flags & 1) ? "on" : "off (unaligned planes)") : "off");
     g_info = b;
     return MXB_OK;

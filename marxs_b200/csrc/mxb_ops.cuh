@@ -340,15 +340,26 @@ MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, doubl
     ph.unit = true;
 }
 
-// filter.py:90-94  params: n, x[n], y[n]   (n == 0: constant y[0])
+// filter.py:90-94  params: n, x[n], y[n] [, fill_lo, fill_hi]   (n == 0: constant y[0])
+// flags (scipy.interpolate.interp1d modes): 1 bounds_error -> ValueError outside the table; 2 out-of-range
+// queries return fill_lo / fill_hi (fill_value=number or pair; NaN by default); 4 fill_value='extrapolate'
+// (the end segments continue); none of them: ends clamped like np.interp
 template <typename PP>
 MXB_DEV double filter_value(unsigned long long* st_sm, PP p, double energy, int flags) {
     const int n = (int)p[0];
     if (n == 0) return p[1];
     PP xp = p + 1;
     PP fp = p + 1 + n;
-    if ((flags & 1) && (energy < xp[0] || energy > xp[n - 1]))
-        count_status(st_sm, MXB_ST_FILTER_BOUNDS);
+    const bool below = energy < xp[0], above = energy > xp[n - 1];
+    if (below || above) {
+        if (flags & 1) count_status(st_sm, MXB_ST_FILTER_BOUNDS);
+        else if (flags & 2) return below ? p[1 + 2 * n] : p[2 + 2 * n];
+        else if ((flags & 4) && n >= 2) {
+            const int lo = below ? 0 : n - 2;
+            const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+            return slope * (energy - xp[lo]) + fp[lo];
+        }
+    }
     return interp_clamped(xp, fp, n, energy);
 }
 

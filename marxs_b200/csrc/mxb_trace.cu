@@ -780,11 +780,15 @@ int launch_interp(const double* prog_dev, int n_ops, int stage_words, bool born,
     const size_t stage_bytes = (size_t)stage_words * 8;
     const int grid = grid_for(n, kThreads, 1);
     if (stage_bytes <= (size_t)kMaxSmemStageBytes) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        // the attribute is per device (and the call is cheap next to a launch): set it whenever this
+        // thread's current device changes, so one process can drive several GPUs
+        static thread_local int attr_dev = -1;
+        int dev = -1;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (attr_dev != dev) {
             CUDA_TRY(cudaFuncSetAttribute(mxb_trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kMaxSmemStageBytes));
-            attr_set = true;
+            attr_dev = dev;
         }
         mxb_trace_kernel<true><<<grid, kThreads, stage_bytes, stream>>>(P);
     } else {

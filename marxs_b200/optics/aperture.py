@@ -58,13 +58,49 @@ class FlatAperture(BaseAperture, FlatOpticalElement):
         return run_fused([self], photons)
 
 
+class AreaMM2(float):
+    """An aperture area in mm**2.  The reference returns ``... * u.mm**2`` (aperture.py:100,152,199) and
+    sources convert it against a flux per cm**2 (basesources.py:174); astropy is not a dependency here, so
+    the unit travels as the type: ``PointSource(geomarea=aperture.area)`` divides by 100, a bare number
+    is taken as cm**2.  Scaling by plain numbers and sums of areas keep the unit."""
+    unit = 'mm2'
+
+    @property
+    def value(self):
+        return float(self)
+
+    def to(self, unit):
+        name = unit if isinstance(unit, str) else getattr(unit, 'to_string', lambda: str(unit))()
+        name = name.replace(' ', '').replace('**', '').replace('^', '')
+        if name == 'mm2':
+            return float(self)
+        if name == 'cm2':
+            return float(self) / 100.
+        raise ValueError('AreaMM2 converts to mm2 or cm2, not {0}'.format(unit))
+
+    def __mul__(self, other):
+        return AreaMM2(float(self) * other) if type(other) in (int, float) else float.__mul__(self, other)
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        return AreaMM2(float(self) / other) if type(other) in (int, float) else float.__truediv__(self, other)
+
+    def __add__(self, other):
+        return AreaMM2(float(self) + float(other)) if isinstance(other, AreaMM2) else float.__add__(self, other)
+
+    def __radd__(self, other):
+        if isinstance(other, AreaMM2) or (type(other) is int and other == 0):      # sum() starts at 0
+            return AreaMM2(float(self) + float(other))
+        return float.__radd__(self, other)
+
+
 class RectangleAperture(FlatAperture):
     """Rectangular opening (reference :85-100)."""
     default_geometry = RectangleHole
 
     @property
     def area(self):
-        return 4 * np.linalg.norm(self.geometry['v_y']) * np.linalg.norm(self.geometry['v_z'])
+        return AreaMM2(4 * np.linalg.norm(self.geometry['v_y']) * np.linalg.norm(self.geometry['v_z']))
 
 
 class CircleAperture(FlatAperture):
@@ -82,7 +118,7 @@ class CircleAperture(FlatAperture):
     @property
     def area(self):
         A_circ = np.pi * (np.linalg.norm(self.geometry['v_y']) ** 2 - self.geometry['r_inner'] ** 2)
-        return (self.geometry.phi[1] - self.geometry.phi[0]) / (2 * np.pi) * A_circ
+        return AreaMM2((self.geometry.phi[1] - self.geometry.phi[0]) / (2 * np.pi) * A_circ)
 
 
 class MultiAperture(BaseAperture, BaseContainer):
@@ -101,7 +137,7 @@ class MultiAperture(BaseAperture, BaseContainer):
 
     @property
     def area(self):
-        return sum(e.area for e in self.elements)
+        return AreaMM2(sum(float(e.area) for e in self.elements))
 
     def _can_lower(self):
         return (not self.preprocess_steps and not self.postprocess_steps

@@ -111,6 +111,34 @@ class OpticalElement(SimulationSequenceElement):
                     photons.remove_column(n)
         return photons
 
+    def _run_scalar_hook(self, photons, intersect):
+        """The scalar plug-in hook ``process_photon(dir, pos, energy, polarization)`` (reference
+        optics/base.py:98-142, loop :186-197).  It is user Python written against numpy scalars and
+        4-vectors, so it runs as in the reference: the intersect is a kernel, then the hook is called once
+        per HIT photon on host copies of that photon's values, and its return values
+        ``(dir, pos, energy, polarization, probability, *output_columns)`` are written back to the device
+        columns with the reference's rules (probability multiplies and is range-checked,
+        optics/base.py:12-51).  One D2H of the four input columns of the hit photons and one H2D per
+        returned column - not one transfer per photon."""
+        idx = torch.nonzero(torch.as_tensor(intersect, device=photons.device)).ravel()
+        n_hit = int(idx.numel())
+        names = _scalar_hook_names(self)
+        self.add_output_cols(photons)
+        host = {c: photons[c].data.as_subclass(torch.Tensor)[idx].cpu().numpy()
+                for c in ('dir', 'pos', 'energy', 'polarization')}
+        outs = None
+        for k in range(n_hit):
+            res = self.process_photon(host['dir'][k], host['pos'][k], host['energy'][k], host['polarization'][k])
+            if len(res) != len(names):
+                raise ValueError('process_photon returned {0} values, expected {1}: {2}'.format(
+                    len(res), len(names), names))
+            if outs is None:
+                outs = [np.empty((n_hit,) + np.shape(r), dtype=float) for r in res]
+            for o, r in zip(outs, res):
+                o[k] = r
+        for col, o in zip(names, outs or []):
+            _assign_col_value(photons, col, idx, o)
+
     def process_photons(self, photons, intersect, interpos, intercoos):
         """Reference semantics of optics/base.py:149-211 on device tensors."""
         if self._can_lower():
@@ -123,8 +151,7 @@ class OpticalElement(SimulationSequenceElement):
             for col in outcols:
                 _assign_col_value(photons, col, intersect, outcols[col])
         elif hasattr(self, 'process_photon'):
-            raise NotImplementedError('per-photon Python loops (process_photon) are not supported on the '
-                                      'device path: vectorise as specific_process_photons')
+            self._run_scalar_hook(photons, intersect)
         else:
             raise AttributeError('Optical element must have one of three: specific_process_photons, '
                                  'process_photon, or override process_photons.')
@@ -136,6 +163,11 @@ class OpticalElement(SimulationSequenceElement):
             photons[self.id_col][intersect] = self.id_num
         photons['pos'][intersect] = interpos[intersect]
         return photons
+
+
+def _scalar_hook_names(elem):
+    return ['dir', 'pos', 'energy', 'polarization', 'probability'] + [
+        (c['name'] if isinstance(c, dict) else c) for c in elem.output_columns]
 
 
 def photonlocalcoords(f, colnames=['pos', 'dir']):

@@ -16,14 +16,32 @@ __all__ = ['Tabulated1D', 'EnergyFilter', 'GlobalEnergyFilter']
 
 
 class Tabulated1D:
-    """Linear interpolation table p(E); ``bounds_error`` like scipy.interpolate.interp1d."""
+    """Linear interpolation table p(E) with the out-of-range modes of scipy.interpolate.interp1d:
+    ``bounds_error=True`` (scipy's default) raises ValueError, otherwise ``fill_value`` applies - a number
+    or a ``(below, above)`` pair (NaN by default, like scipy) or ``'extrapolate'``."""
 
-    def __init__(self, x, y, bounds_error=True):
+    def __init__(self, x, y, bounds_error=True, fill_value=np.nan):
         self.x = np.asarray(x, dtype=float)
         self.y = np.asarray(y, dtype=float)
         self.bounds_error = bounds_error
+        self.fill_value = fill_value
         if np.any(np.diff(self.x) <= 0):
             raise ValueError('x must be strictly increasing')
+
+
+def _fill_mode(f):
+    """(flags, extra params) of the out-of-range behaviour of a Tabulated1D / scipy interp1d object."""
+    if getattr(f, 'bounds_error', True):
+        return 1, []
+    fill = getattr(f, 'fill_value', np.nan)
+    if (isinstance(fill, str) and fill == 'extrapolate') or getattr(f, '_extrapolate', False):
+        return 4, []
+    fill = np.asarray(fill, dtype=float).ravel()      # scipy stores (below, above) or one broadcastable value
+    if fill.size == 1:
+        return 2, [float(fill[0]), float(fill[0])]
+    if fill.size == 2:
+        return 2, [float(fill[0]), float(fill[1])]
+    raise NotFusable('unsupported fill_value of the filter table')
 
 
 def lower_filter(f):
@@ -39,7 +57,11 @@ def lower_filter(f):
             raise NotFusable('filter table must be one-dimensional')
         if np.any(y < 0.) or np.any(y > 1.):
             raise ValueError('Probabilities returned by filterfunc must be in interval [0, 1].')
-        return np.concatenate([[len(x)], x, y]), (1 if getattr(f, 'bounds_error', True) else 0)
+        flags, extra = _fill_mode(f)
+        for v in extra:
+            if v < 0. or v > 1.:       # NaN passes, as in the reference's range check
+                raise ValueError('Probabilities returned by filterfunc must be in interval [0, 1].')
+        return np.concatenate([[len(x)], x, y, extra]), flags
     raise NotFusable('filterfunc is an arbitrary callable')
 
 

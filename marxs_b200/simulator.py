@@ -29,13 +29,26 @@ def _lowerable(elem):
     return callable(getattr(elem, '_lower', None)) and getattr(elem, '_can_lower', lambda: True)()
 
 
-def fingerprint(objs, extra=()):
-    """Digest of everything a lowering can depend on: the attribute trees of the elements (arrays
-    by content, numbers and strings by value, functions / classes / opaque objects by identity,
-    device tensors by address and shape) plus ``extra`` (column names, meta).  MARXS elements are
-    mutable between calls (geometry, selectors, ``generate_elements()``), so lowered programs are
-    cached under this digest instead of being trusted blindly: walking 350 elements costs a few
-    milliseconds, lowering them 50."""
+class Uncacheable(Exception):
+    """The element tree cannot be digested safely (nesting too deep): lower without the plan cache."""
+
+
+_FP_MAX_DEPTH = 32
+_FP_TENSOR_BY_CONTENT = 1 << 16     # elements; larger tensors are identified by (address, shape, version)
+
+
+def fingerprint(objs, extra=(), pins=None):
+    """Digest of everything a lowering can depend on: the attribute trees of the elements (arrays and
+    tensors by content, numbers and strings by value, functions / classes / opaque objects by identity)
+    plus ``extra`` (column names, meta).  MARXS elements are mutable between calls (geometry, selectors,
+    ``generate_elements()``), so lowered programs are cached under this digest instead of being trusted
+    blindly: walking 350 elements costs a few milliseconds, lowering them 50.
+
+    Objects that can only be identified by ``id()`` / address are appended to ``pins``; the cache entry
+    keeps them alive, so an id cannot be recycled for a different object while the entry exists.  Output
+    buffers (attributes in ``_FP_BUFFERS``, e.g. the fused detector ``image``) are identified by address
+    and shape only: their content is a result, not an input of the lowering.  A tree nested deeper than
+    ``_FP_MAX_DEPTH`` raises ``Uncacheable`` (fail closed) instead of falling back to identity."""
     import hashlib
     import types
     import torch
@@ -46,7 +59,25 @@ def fingerprint(objs, extra=()):
     scalars = (bool, int, float, str, bytes, type(None))
     opaque = (type, types.FunctionType, types.BuiltinFunctionType, types.MethodType, types.ModuleType)
 
-    def feed(v, depth):
+    def pin(v):
+        if pins is not None:
+            pins.append(v)
+
+    def feed_tensor(v, buffer):
+        if buffer:
+            add('B{0}{1}{2}{3}'.format(v.data_ptr(), tuple(v.shape), v.dtype, v.device).encode())
+            pin(v)
+        elif v.numel() <= _FP_TENSOR_BY_CONTENT:
+            add('T{0}{1}{2}'.format(tuple(v.shape), v.dtype, v.device).encode())
+            add(v.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes())
+        else:
+            # in-place torch ops bump _version, so a modified tensor misses; the pin keeps the address unique
+            add('V{0}{1}{2}{3}{4}'.format(v.data_ptr(), tuple(v.shape), v.dtype, v.device, v._version).encode())
+            pin(v)
+
+    def feed(v, depth, buffer=False):
+        if depth > _FP_MAX_DEPTH:
+            raise Uncacheable('element tree nested deeper than {0} levels'.format(_FP_MAX_DEPTH))
         t = type(v)
         if t in scalars:                                  # exact types first: the common leaves
             add(repr(v).encode())
@@ -72,7 +103,7 @@ def fingerprint(objs, extra=()):
         elif isinstance(v, np.generic):
             add(repr(v.item()).encode())
         elif isinstance(v, torch.Tensor):
-            add('T{0}{1}{2}'.format(v.data_ptr(), tuple(v.shape), v.dtype).encode())
+            feed_tensor(v, buffer)
         elif isinstance(v, (list, tuple)):
             add(b'[')
             for x in v:
@@ -86,10 +117,12 @@ def fingerprint(objs, extra=()):
             add(b'}')
         elif isinstance(v, opaque):
             add('F{0}{1}'.format(getattr(v, '__qualname__', ''), id(v)).encode())
+            pin(v)
         else:
             d = getattr(v, '__dict__', None)
-            if d is None or depth > 12:
+            if d is None:
                 add('O{0}{1}'.format(t.__qualname__, id(v)).encode())
+                pin(v)
             elif id(v) in seen:
                 add(b'@')
             else:
@@ -102,7 +135,7 @@ def fingerprint(objs, extra=()):
                     if k in _FP_SKIP or k in skip:
                         continue
                     add(k.encode())
-                    feed(x, depth + 1)
+                    feed(x, depth + 1, k in _FP_BUFFERS)
     for o in objs:
         feed(o, 0)
     feed(extra, 0)
@@ -112,6 +145,8 @@ def fingerprint(objs, extra=()):
 
 # attributes no lowering reads (labels, plotting hints)
 _FP_SKIP = frozenset(('display', 'name'))
+# attributes that hold device OUTPUT buffers the kernels accumulate into (identity, not content)
+_FP_BUFFERS = frozenset(('image',))
 
 _plan_cache = {}
 _PLAN_CACHE_MAX = 64
@@ -124,12 +159,19 @@ def _lower_run(elements, i, photons):
     import os
     use_cache = os.environ.get('MXB_PLAN_CACHE', '1') != '0'
     key = None
+    pins = []
     if use_cache:
-        key = fingerprint(elements[i:], (tuple(photons.colnames), photons.meta))
+        try:
+            key = fingerprint(elements[i:], (tuple(photons.colnames), photons.meta), pins)
+        except Uncacheable:
+            use_cache = False
+    if use_cache:
         hit = _plan_cache.get(key)
         if hit is not None:
             plan_cache_stats['hit'] += 1
-            return hit
+            # the key describes the TAIL elements[i:], so the entry holds the run LENGTH: the same tail
+            # reached at another start offset must not inherit an absolute end index
+            return i + hit[0], hit[1], hit[2]
         plan_cache_stats['miss'] += 1
     lw = Lowering(photons.colnames, meta=photons.meta)
     j = i
@@ -142,12 +184,12 @@ def _lower_run(elements, i, photons):
             lw.rollback(cp)
             break
         j += 1
-    out = (j, lw.finish() if j > i else None, lw.needs_pos)
+    prog = lw.finish() if j > i else None
     if use_cache:
         if len(_plan_cache) >= _PLAN_CACHE_MAX:
             _plan_cache.pop(next(iter(_plan_cache)))
-        _plan_cache[key] = out
-    return out
+        _plan_cache[key] = (j - i, prog, lw.needs_pos, pins)    # pins: identity-hashed objects stay alive
+    return j, prog, lw.needs_pos
 
 
 def run_fused(elements, photons, check=True):

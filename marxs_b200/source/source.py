@@ -34,6 +34,27 @@ def _val(x, unit=None):
     return float(x)
 
 
+def _area_cm2(x):
+    """Geometric area in cm**2 (the unit of ``flux`` is 1 / s / cm**2, reference basesources.py:151-174 where
+    ``(flux * geomarea * u.s).decompose()`` converts): ``aperture.area`` values carry mm**2
+    (``marxs_b200.optics.aperture.AreaMM2``, the reference returns ``u.mm**2`` quantities), astropy
+    quantities are converted, bare numbers are cm**2 like the reference default ``1 * u.cm**2``."""
+    from ..optics.aperture import AreaMM2
+    if isinstance(x, AreaMM2):
+        return float(x) / 100.
+    if hasattr(x, 'to') and hasattr(x, 'unit'):
+        import astropy.units as u
+        return float(x.to(u.cm ** 2).value)
+    return float(x)
+
+
+def _flux_per_s_cm2(x):
+    if hasattr(x, 'to') and hasattr(x, 'unit'):
+        import astropy.units as u
+        return float(x.to(1 / u.s / u.cm ** 2).value)
+    return float(x)
+
+
 def _strip(x, unit):
     """Array (numpy or torch) from an array or an astropy-like Quantity array (converted to ``unit`` first)."""
     if hasattr(x, 'to') and hasattr(x, 'unit'):
@@ -47,10 +68,10 @@ def poisson_process(rate):
     basesources.py:15-62 ``poisson_process``), generated ON THE DEVICE: exponential waiting times (torch's
     Philox stream) and their running sum, cut at the exposure time.  Returns the function
     ``flux(exposuretime, geomarea)`` a source takes as its ``flux``."""
-    rate = _val(rate)
+    rate = _flux_per_s_cm2(rate)
 
     def poisson_rate(exposuretime, geomarea, device='cuda'):
-        full = rate * _val(geomarea)
+        full = rate * _area_cm2(geomarea)
         t_exp = _val(exposuretime, 's')
         # 10 % more numbers than expected (+ 5 sigma), more if that was not enough
         n = int(t_exp * full * 1.1 + 5. * np.sqrt(t_exp * full) + 16)
@@ -114,7 +135,7 @@ class Source(SimulationSequenceElement):
     def _rate(self):
         if callable(self.flux):
             return float('inf')      # dt = 0: the time column comes from the callable (GENERATE flag bit 2)
-        return _val(self.flux) * _val(self.geomarea)
+        return _flux_per_s_cm2(self.flux) * _area_cm2(self.geomarea)
 
     def n_photons(self, exposuretime):
         if callable(self.flux):
@@ -436,17 +457,22 @@ _born_cache = {}
 def _run_born(elements, photons, check=True, given=()):
     """Lower (cached under the fingerprint of the element trees, like simulator._lower_run) and launch.
     ``given``: columns the host filled before the launch (results of callable source specifications)."""
-    from ..simulator import fingerprint
-    key = fingerprint(elements, ('born', photons.meta, tuple(given)))
-    prog = _born_cache.get(key)
+    from ..simulator import fingerprint, Uncacheable
+    pins = []
+    try:
+        key = fingerprint(elements, ('born', photons.meta, tuple(given)), pins)
+    except Uncacheable:
+        key = None
+    prog = _born_cache.get(key, (None,))[0] if key is not None else None
     if prog is None:
         lw = Lowering(list(given), meta=photons.meta)
         for e in elements:
             e._lower(lw)
         prog = lw.finish()
-        if len(_born_cache) >= 32:
-            _born_cache.pop(next(iter(_born_cache)))
-        _born_cache[key] = prog
+        if key is not None:
+            if len(_born_cache) >= 32:
+                _born_cache.pop(next(iter(_born_cache)))
+            _born_cache[key] = (prog, pins)      # pins: identity-hashed objects stay alive with the entry
     draws = _rng.take_injected(len(prog.slot_kinds))
     prog.run(photons, draws=draws, seed=_rng.next_launch_seed(), id0=getattr(photons, 'id0', 0), check=check)
     return prog

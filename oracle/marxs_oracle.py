@@ -714,8 +714,10 @@ def interp1d_np(x, xp, fp):
 
 
 class Tabulated1D:
-    """A filter curve: linear interpolation on (x, y); ``bounds_error`` as
-    scipy.interpolate.interp1d (raise outside the range) or clamp (np.interp)."""
+    """A filter curve with the semantics of scipy.interpolate.interp1d(kind='linear') as the reference's
+    callers use it (missions/arcus/arcus.py:257,288-305): ``bounds_error=True`` (scipy's default) raises
+    outside the table; otherwise ``fill_value`` - a number or a (below, above) pair, NaN by default - or
+    'extrapolate' (the end segments continue).  Pinned against scipy itself in tests/test_oracle_golden.py."""
 
     def __init__(self, x, y, bounds_error=True, fill_value=np.nan):
         self.x = np.asarray(x, dtype=float)
@@ -725,13 +727,20 @@ class Tabulated1D:
 
     def __call__(self, en):
         en = np.asarray(en, dtype=float)
-        outside = (en < self.x[0]) | (en > self.x[-1])
-        if self.bounds_error and np.any(outside):
+        below, above = en < self.x[0], en > self.x[-1]
+        if self.bounds_error and np.any(below | above):
             raise ValueError('A value in x_new is outside the interpolation range.')
         out = interp1d_np(en, self.x, self.y)
-        if not self.bounds_error and not np.isnan(self.fill_value):
-            out = np.where(outside, self.fill_value, out)
-        return out
+        if self.bounds_error:
+            return out
+        if isinstance(self.fill_value, str) and self.fill_value == 'extrapolate':
+            for mask, j in ((below, 0), (above, len(self.x) - 2)):
+                slope = (self.y[j + 1] - self.y[j]) / (self.x[j + 1] - self.x[j])
+                out = np.where(mask, slope * (en - self.x[j]) + self.y[j], out)
+            return out
+        fill = np.asarray(self.fill_value, dtype=float).ravel()
+        lo, hi = (fill[0], fill[0]) if fill.size == 1 else (fill[0], fill[1])
+        return np.where(below, lo, np.where(above, hi, out))
 
 
 def _eval_filter(f, en):

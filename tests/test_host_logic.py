@@ -428,3 +428,145 @@ def test_chip2tdet_matches_reference_known_answers():
     assert np.allclose(chip2tdet(chip, TDET['ACIS'], 7), chip + [3917, 1702])
     # I0 (id 0): theta = 90 deg: (x, y) -> (y, -x) about the chip origin
     assert np.allclose(chip2tdet(np.array([[1., 1.]]), TDET['ACIS'], 0), [[0.5 + 3061.5, -0.5 + 5131.5]])
+
+
+# ---- round-2 regressions ---------------------------------------------
+def test_plan_cache_stores_run_length_not_end_index():
+    """The cache key describes the tail elements[i:]; the same tail reached at another start offset used
+    to return the first call's ABSOLUTE end index (elements skipped or applied twice, or an endless loop)."""
+    p = mb.generate_test_photons(4, device='cpu')
+    a = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    b = optics.EnergyFilter(filterfunc=0.5, zoom=[1, 20, 20], position=[-1, 0, 0])
+    c = optics.FlatDetector(pixsize=0.2, zoom=[1, 20, 20], position=[-2, 0, 0])
+
+    class Opaque:          # a user element that cannot be lowered
+        def __call__(self, photons):
+            return photons
+    simulator._plan_cache.clear()
+    j0, prog0, _ = simulator._lower_run([a, b, c], 0, p)
+    assert j0 == 3 and prog0 is not None
+    hits = simulator.plan_cache_stats['hit']
+    j1, prog1, _ = simulator._lower_run([Opaque(), a, b, c], 1, p)
+    assert simulator.plan_cache_stats['hit'] == hits + 1 and prog1 is prog0
+    assert j1 == 4                                   # was 3: run_fused would have run `c` twice
+    j2, _, _ = simulator._lower_run([Opaque(), Opaque(), a, b, c], 2, p)
+    assert j2 == 5
+    # a run that stops at a non-lowerable element: length 2 at any offset
+    simulator._plan_cache.clear()
+    tail = [a, b, Opaque(), c]
+    assert simulator._lower_run(tail, 0, p)[0] == 2
+    assert simulator._lower_run([Opaque()] + tail, 1, p)[0] == 3
+
+
+def test_fingerprint_tensor_content_pins_and_depth():
+    det = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    det.table = torch.arange(6, dtype=torch.float64)
+    f0 = simulator.fingerprint([det])
+    det.table[2] = 7.                                # in-place change of a small tensor: content is hashed
+    f1 = simulator.fingerprint([det])
+    assert f1 != f0
+    big = torch.zeros(simulator._FP_TENSOR_BY_CONTENT + 1, dtype=torch.float64)
+    det.table = big
+    pins = []
+    f2 = simulator.fingerprint([det], pins=pins)
+    assert any(x is big for x in pins)               # identity-hashed: kept alive by the cache entry
+    big[5] = 1.                                      # torch bumps _version
+    assert simulator.fingerprint([det]) != f2
+    # output buffers (the fused detector image) are identified by address, not content
+    det.table = None
+    det.image = torch.zeros((1, 8, 8), dtype=torch.float64)
+    f3 = simulator.fingerprint([det])
+    det.image.zero_()
+    det.image += 1.
+    assert simulator.fingerprint([det]) == f3
+    # functions are pinned as well
+    flt = optics.EnergyFilter(filterfunc=lambda e: e * 0 + 0.5, zoom=[1, 20, 20])
+    pins = []
+    simulator.fingerprint([flt], pins=pins)
+    assert any(x is flt.filterfunc for x in pins)
+    # too deep: fail closed instead of hashing by id()
+    class Node:
+        pass
+    root = cur = Node()
+    for _ in range(simulator._FP_MAX_DEPTH + 2):
+        cur.child = Node()
+        cur = cur.child
+    with pytest.raises(simulator.Uncacheable):
+        simulator.fingerprint([root])
+    p = mb.generate_test_photons(4, device='cpu')
+    det2 = optics.FlatDetector(pixsize=0.1, zoom=[1, 20, 20])
+    det2.deep = root
+    n_cached = len(simulator._plan_cache)
+    assert simulator._lower_run([det2], 0, p)[0] == 1 and len(simulator._plan_cache) == n_cached   # lowered, not cached
+
+
+def test_source_rate_converts_area_units():
+    """flux is per cm**2; aperture.area is mm**2 (reference aperture.py:100, basesources.py:174)."""
+    from marxs_b200 import source
+    from marxs_b200.optics.aperture import AreaMM2
+    aper = optics.RectangleAperture(zoom=[1, 10, 10])
+    assert isinstance(aper.area, AreaMM2) and float(aper.area) == 400. and aper.area.to('cm2') == 4.
+    s = source.PointSource(coords=(0., 0.), flux=100., geomarea=aper.area)
+    # reference: len(np.arange(0, T, 1 / (flux * geomarea * u.s).decompose())) with 400 mm2 = 4 cm2
+    assert s.n_photons(10.) == len(np.arange(0, 10., 1. / (100. * 4.))) == 4000
+    assert source.PointSource(coords=(0., 0.), flux=100., geomarea=4.).n_photons(10.) == 4000      # bare number: cm2
+    assert source.PointSource(coords=(0., 0.), flux=100.).n_photons(10.) == 1000                    # default 1 cm2
+    circ = optics.CircleAperture(zoom=[1, 5, 5], r_inner=3.)
+    assert np.isclose(float(circ.area), np.pi * (25. - 9.)) and isinstance(circ.area, AreaMM2)
+    multi = optics.MultiAperture(elements=[aper, circ])
+    assert isinstance(multi.area, AreaMM2) and np.isclose(float(multi.area), 400. + np.pi * 16.)
+    assert isinstance(2 * aper.area, AreaMM2) and isinstance(aper.area + circ.area, AreaMM2)
+    assert isinstance(sum([aper.area, circ.area]), AreaMM2)
+    # Quantity-like objects (astropy or the test stand-in) are converted, not stripped
+    class Q:
+        def __init__(self, v, unit):
+            self.value, self.unit = v, unit
+        def to(self, unit):
+            assert self.unit == 'mm2'
+            return Q(self.value / 100., 'cm2')
+    import sys
+    import types
+    fake = types.ModuleType('astropy.units')
+    class U:
+        def __init__(self, name): self.name = name
+        def __pow__(self, k): return U('{0}{1}'.format(self.name, k))
+        def __rtruediv__(self, other): return U('1/' + self.name)
+        def __truediv__(self, other): return U(self.name + '/' + other.name)
+    fake.cm, fake.s = U('cm'), U('s')
+    pkg = types.ModuleType('astropy')
+    pkg.units = fake
+    saved = {k: sys.modules.get(k) for k in ('astropy', 'astropy.units')}
+    sys.modules['astropy'], sys.modules['astropy.units'] = pkg, fake
+    try:
+        s = source.PointSource(coords=(0., 0.), flux=100., geomarea=Q(300., 'mm2'))
+        assert s.n_photons(10.) == 3000
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_filter_fill_modes_follow_scipy():
+    """interp1d(bounds_error=False) returns fill_value (NaN by default) or extrapolates outside the table;
+    the lowering used to treat every such object as clamped."""
+    from scipy.interpolate import interp1d
+    from marxs_b200.optics.filter import lower_filter
+    x, y = np.array([1., 2., 4.]), np.array([0.2, 0.6, 0.4])
+    q = np.array([0.5, 1., 1.5, 3., 4., 5.])
+    cases = [dict(bounds_error=False), dict(bounds_error=False, fill_value=0.1),
+             dict(bounds_error=False, fill_value=(0.1, 0.3)), dict(bounds_error=False, fill_value='extrapolate')]
+    for kw in cases:
+        want = interp1d(x, y, **kw)(q)
+        assert np.allclose(mo.Tabulated1D(x, y, **kw)(q), want, rtol=1e-15, atol=1e-16, equal_nan=True), kw
+    params, flags = lower_filter(interp1d(x, y, bounds_error=False))
+    assert flags == 2 and np.isnan(params[-2:]).all()
+    params, flags = lower_filter(interp1d(x, y, bounds_error=False, fill_value=(0.1, 0.3)))
+    assert flags == 2 and params[-2:].tolist() == [0.1, 0.3]
+    assert lower_filter(interp1d(x, y, fill_value='extrapolate'))[1] == 4
+    assert lower_filter(interp1d(x, y))[1] == 1 and lower_filter(optics.Tabulated1D(x, y))[1] == 1
+    with pytest.raises(ValueError):
+        lower_filter(optics.Tabulated1D(x, y, bounds_error=False, fill_value=1.5))
+    with pytest.raises(ValueError):
+        mo.Tabulated1D(x, y)(q)
