@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 9
+#define MXB_ABI_VERSION 10
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -227,6 +227,29 @@ long long   mxb_jit_compile(const double* prog_host, size_t prog_words, const Mx
 int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
                    const MxbColumns* host_out, int64_t n, int64_t chunk,
                    int64_t photon_id0, uint64_t seed, unsigned long long* status_host);
+
+/* mxb_trace_host with a LEAN result set.  Planes absent from host_out are not brought back (a caller that
+ * only needs order / facet / CCD_ID / pixel coordinates / probability leaves the core vectors and the other
+ * diagnostics out: the kernel is then specialised without those stores and the D2H traffic shrinks to what
+ * is asked for - SURVEY 8(d) "lean mode").  opt->i32_out[k] != NULL: id column k (MxbColumns.i64 slot k) is
+ * narrowed to int32 on the device and lands in that host plane (n int32), instead of or besides the int64
+ * plane host_out->i64[k]; ids are small integers, -1 = no hit.  opt == NULL: mxb_trace_host. */
+typedef struct MxbHostOptions {
+    int32_t* i32_out[MXB_MAX_I64_COLS];
+} MxbHostOptions;
+int mxb_trace_host_opts(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
+                        const MxbColumns* host_out, int64_t n, int64_t chunk,
+                        int64_t photon_id0, uint64_t seed, unsigned long long* status_host,
+                        const MxbHostOptions* opt);
+
+/* The device random stream, exported for verification (tests, bench.py --verify): the draws a launch with
+ * (seed, photon_id0) makes for `slot`, produced by the same device routines the trace kernels call.
+ * kind 0: uniform [0,1) -> out0;  1: standard normal -> out0;  2: normal PAIR of ONE Philox call (the two
+ * deviates RadialMirrorScatter takes when both widths are non-zero; keyed by its first slot) -> out0, out1.
+ * Counter layout: Philox4x32-10, counter = (id lo, id hi, slot, 0), key = (seed lo, seed hi); a uniform is
+ * ((r0 << 32 | r1) >> 11) * 2^-53.  Device pointers; asynchronous on `stream`. */
+int mxb_debug_draws(uint64_t seed, int64_t photon_id0, int64_t n, int slot, int kind, double* out0, double* out1,
+                    void* stream);
 
 /* Geometry.intersect for one plane (math/geometry.py:211-261; circular != 0 adds :376-380).
  * geom: 14 host doubles (c, e_x, e_y, e_z, |v_y|, |v_z|).  dir/pos: 3 device planes each.

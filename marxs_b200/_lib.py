@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 9
+MXB_ABI_VERSION = 10
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -23,6 +23,10 @@ class MxbColumns(ctypes.Structure):
     _fields_ = [('f64', ctypes.c_void_p * MXB_MAX_F64_COLS),
                 ('i64', ctypes.c_void_p * MXB_MAX_I64_COLS),
                 ('draws', ctypes.c_void_p * MXB_MAX_SLOTS)]
+
+
+class MxbHostOptions(ctypes.Structure):
+    _fields_ = [('i32_out', ctypes.c_void_p * MXB_MAX_I64_COLS)]
 
 
 class MxbError(RuntimeError):
@@ -67,6 +71,11 @@ def load(strict=None):
     lib.mxb_trace_from.argtypes = [vp, sz, vp, vp, ctypes.POINTER(MxbColumns), i64, i64, u64, vp, vp]
     lib.mxb_trace_host.restype = ci
     lib.mxb_trace_host.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), ctypes.POINTER(MxbColumns), i64, i64, i64, u64, vp]
+    lib.mxb_trace_host_opts.restype = ci
+    lib.mxb_trace_host_opts.argtypes = [vp, sz, ctypes.POINTER(MxbColumns), ctypes.POINTER(MxbColumns), i64, i64, i64, u64, vp,
+                                        ctypes.POINTER(MxbHostOptions)]
+    lib.mxb_debug_draws.restype = ci
+    lib.mxb_debug_draws.argtypes = [u64, i64, i64, ci, ci, vp, vp, vp]
     lib.mxb_plane_intersect.restype = ci
     lib.mxb_plane_intersect.argtypes = [vp, ci, vp, vp, vp, vp, vp, i64, vp]
     lib.mxb_parallel_transport.restype = ci
@@ -110,5 +119,5 @@ def check(lib, rc, what):
 
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
-                    'mxb_trace_from', 'mxb_trace_host', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
+                    'mxb_trace_from', 'mxb_trace_host', 'mxb_trace_host_opts', 'mxb_debug_draws', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
                     'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events']

@@ -638,6 +638,32 @@ hist2d_kernel(const double* x, const double* y, const double* w, const long long
     hot_flush(hot, threadIdx.x, blockDim.x);
 }
 
+// the device random stream, exported: exactly the routines the trace kernels call (device_draw /
+// device_draw_normal_pair of mxb_device.cuh, same build flags), so a test or bench.py --verify can feed the
+// draws a timed launch used to the CPU oracle.  kind 0 uniform, 1 normal, 2 normal pair (RSCATTER with both
+// widths: ONE Philox call yields both deviates)
+__global__ void __launch_bounds__(256)
+debug_draws_kernel(unsigned long long seed, long long id0, long long n, int slot, int kind, double* out0, double* out1) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long gid = (unsigned long long)(id0 + i);
+        if (kind == 2) {
+            double z0, z1;
+            device_draw_normal_pair(seed, gid, slot, z0, z1);
+            out0[i] = z0;
+            if (out1) out1[i] = z1;
+        } else {
+            out0[i] = device_draw(seed, gid, slot, kind);
+        }
+    }
+}
+
+// id columns on the wire as int32 (lean host output: ids are small; -1 stays -1)
+__global__ void __launch_bounds__(256)
+narrow_i64_kernel(const long long* src, int* dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (int)src[i];
+}
+
 // ---------------------------------------------------------------------------
 // event compaction (multi-GPU epilogue): rows with sel >= sel_min (and weight > 0) of up to 64
 // 8-byte planes are packed densely, order preserved.  Three passes: per-block counts, one-block scan,
@@ -942,6 +968,15 @@ int mxb_compact_events(const void* const* src_planes, void* const* dst_planes, i
     return MXB_OK;
 }
 
+int mxb_debug_draws(uint64_t seed, int64_t photon_id0, int64_t n, int slot, int kind, double* out0, double* out1,
+                    void* stream) {
+    if (!out0 || kind < 0 || kind > 2 || slot < 0 || slot >= MXB_MAX_SLOTS) return fail(MXB_EINVAL, "mxb_debug_draws: bad argument");
+    if (n <= 0) return n == 0 ? MXB_OK : fail(MXB_EINVAL, "negative n");
+    debug_draws_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(seed, photon_id0, n, slot, kind, out0, out1);
+    CUDA_TRY(cudaGetLastError());
+    return MXB_OK;
+}
+
 int mxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -1027,6 +1062,12 @@ int mxb_hist2d(const double* x, const double* y, const double* w, const long lon
 int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
                    const MxbColumns* host_out, int64_t n, int64_t chunk, int64_t photon_id0,
                    uint64_t seed, unsigned long long* status_host) {
+    return mxb_trace_host_opts(prog_host, prog_words, host_in, host_out, n, chunk, photon_id0, seed, status_host, nullptr);
+}
+
+int mxb_trace_host_opts(const double* prog_host, size_t prog_words, const MxbColumns* host_in,
+                        const MxbColumns* host_out, int64_t n, int64_t chunk, int64_t photon_id0,
+                        uint64_t seed, unsigned long long* status_host, const MxbHostOptions* opt) {
     int n_ops = 0, stage_words = 0;
     int rc = validate_program(prog_host, prog_words, &n_ops, &stage_words);
     if (rc) return rc;
@@ -1043,9 +1084,14 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
     int nf = 0, ni = 0, nd = 0;
     int fidx[MXB_MAX_F64_COLS], iidx[MXB_MAX_I64_COLS], didx[MXB_MAX_SLOTS];
     for (int k = 0; k < MXB_MAX_F64_COLS; ++k) if (host_in->f64[k] || host_out->f64[k]) fidx[nf++] = k;
-    for (int k = 0; k < MXB_MAX_I64_COLS; ++k) if (host_out->i64[k]) iidx[ni++] = k;
+    int n32 = 0;        // id columns that travel as int32 (opt->i32_out): one more half-size plane each
+    for (int k = 0; k < MXB_MAX_I64_COLS; ++k) {
+        const bool narrow = opt && opt->i32_out[k];
+        if (host_out->i64[k] || narrow) iidx[ni++] = k;
+        if (narrow) ++n32;
+    }
     for (int k = 0; k < MXB_MAX_SLOTS; ++k) if (host_in->draws[k]) didx[nd++] = k;
-    const size_t planes = (size_t)nf + ni + nd;
+    const size_t planes = (size_t)nf + ni + nd + (size_t)(n32 + 1) / 2;
 
     // device staging (program copy, status block, NBUF chunk buffers, streams, events) is cached per
     // host thread and device and only grows: repeated calls do no cudaMalloc / cudaFree
@@ -1125,6 +1171,16 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
             rc = launch_trace(dprog, prog_host, prog_words, n_ops, stage_words, nullptr, &dc, m, photon_id0 + off,
                               seed, dstatus, s_k);
             if (rc) { result = rc; goto cleanup; }
+            int* narrow_base = reinterpret_cast<int*>(base + p * (size_t)chunk * 8);   // after the 8-byte planes
+            {
+                int j = 0;
+                for (int k = 0; k < ni; ++k) {
+                    if (!(opt && opt->i32_out[iidx[k]])) continue;
+                    narrow_i64_kernel<<<grid_for(m, 256, 8), 256, 0, s_k>>>(dc.i64[iidx[k]], narrow_base + (size_t)j * chunk, m);
+                    ++j;
+                }
+                HTRY(cudaGetLastError());
+            }
             HTRY(cudaEventRecord(S.ev_k[b], s_k));
             HTRY(cudaStreamWaitEvent(s_out, S.ev_k[b], 0));
             for (int k = 0; k < nf; ++k) {
@@ -1134,9 +1190,19 @@ int mxb_trace_host(const double* prog_host, size_t prog_words, const MxbColumns*
                 HTRY(cudaMemcpyAsync(host_out->f64[fidx[k]] + off, dc.f64[fidx[k]], (size_t)m * 8,
                                      cudaMemcpyDeviceToHost, s_out));
             }
-            for (int k = 0; k < ni; ++k)
-                HTRY(cudaMemcpyAsync(host_out->i64[iidx[k]] + off, dc.i64[iidx[k]], (size_t)m * 8,
-                                     cudaMemcpyDeviceToHost, s_out));
+            {
+                int j = 0;
+                for (int k = 0; k < ni; ++k) {
+                    if (opt && opt->i32_out[iidx[k]]) {
+                        HTRY(cudaMemcpyAsync(opt->i32_out[iidx[k]] + off, narrow_base + (size_t)j * chunk, (size_t)m * 4,
+                                             cudaMemcpyDeviceToHost, s_out));
+                        ++j;
+                    }
+                    if (host_out->i64[iidx[k]])
+                        HTRY(cudaMemcpyAsync(host_out->i64[iidx[k]] + off, dc.i64[iidx[k]], (size_t)m * 8,
+                                             cudaMemcpyDeviceToHost, s_out));
+                }
+            }
             HTRY(cudaEventRecord(S.ev_out[b], s_out));
         }
         HTRY(cudaStreamSynchronize(s_out));

@@ -70,28 +70,62 @@ def allreduce_images(tensors):
     return tensors
 
 
-def gather_events(columns, dst=0):
-    """All ranks send their compacted event columns (dict name -> 1-D tensor, same names,
-    ragged lengths) to ``dst``; returns the concatenated dict there, None elsewhere."""
+def gather_counts(n_local, device):
+    """All ranks' event counts as a python list (one small all-gather, one host read)."""
+    world = dist.get_world_size()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[dist.get_rank()] = int(n_local)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return [int(c) for c in counts.tolist()]
+
+
+def gather_events(columns, dst=0, counts=None, out=None):
+    """Gather-v of compacted event lists on rank ``dst``.
+
+    ``columns``: dict name -> 1-D tensor (same names and dtypes on every rank, ragged lengths).  One small
+    collective exchanges the counts, then ONE grouped point-to-point exchange (``batch_isend_irecv`` =
+    ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd on NCCL) moves every plane of every rank straight
+    into its final place in the destination columns: rank r's rows land at offset sum(counts[:r]) of each
+    column, so nothing is padded to the longest list and nothing is re-packed.  Returns the dict of
+    concatenated columns on ``dst`` (rank order = global photon-id order for contiguous shards), None on
+    the other ranks.  ``counts``: the per-rank lengths if the caller already knows them; ``out``: dict of
+    preallocated destination tensors of at least sum(counts) rows (dst only) to reuse memory."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return columns
     world, rank = dist.get_world_size(), dist.get_rank()
     names = sorted(columns.keys())
-    n_local = torch.tensor([len(columns[names[0]])], dtype=torch.int64, device=columns[names[0]].device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local)
-    counts = [int(c.item()) for c in counts]
-    nmax = max(counts)
-    out = {} if rank == dst else None
+    first = columns[names[0]]
+    n_local = int(first.shape[0])
     for name in names:
-        t = columns[name]
-        pad = torch.zeros(nmax, dtype=t.dtype, device=t.device)
-        pad[:len(t)] = t
-        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
-        dist.gather(pad, bufs, dst=dst)
-        if rank == dst:
-            out[name] = torch.cat([b[:c] for b, c in zip(bufs, counts)])
-    return out
+        if columns[name].dim() != 1 or columns[name].shape[0] != n_local:
+            raise ValueError('event columns must be 1-D and of equal length on a rank')
+    if counts is None:
+        counts = gather_counts(n_local, first.device)
+    offsets = [0]
+    for c in counts:
+        offsets.append(offsets[-1] + c)
+    total = offsets[-1]
+    ops = []
+    result = None
+    if rank == dst:
+        result = {}
+        for name in names:
+            t = columns[name]
+            buf = out[name] if out is not None and name in out else torch.empty(total, dtype=t.dtype, device=t.device)
+            if buf.shape[0] < total or buf.dtype != t.dtype:
+                raise ValueError('destination buffer of column {0} is too small or of the wrong dtype'.format(name))
+            buf[offsets[rank]:offsets[rank + 1]].copy_(t)
+            result[name] = buf[:total]
+            for r in range(world):
+                if r != dst and counts[r] > 0:
+                    ops.append(dist.P2POp(dist.irecv, buf[offsets[r]:offsets[r + 1]], r))
+    elif n_local > 0:
+        for name in names:
+            ops.append(dist.P2POp(dist.isend, columns[name].contiguous(), dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return result
 
 
 def max_over_ranks(value, device):

@@ -60,7 +60,8 @@ class HostPhotonTable:
         return a.T if a.ndim == 2 else a
 
     def new_column(self, name, dtype=np.float64, vector=False):
-        tdt = torch.float64 if np.dtype(dtype).kind == 'f' else torch.int64
+        dt = np.dtype(dtype)
+        tdt = torch.float64 if dt.kind == 'f' else (torch.int32 if dt.itemsize == 4 else torch.int64)
         self._keep[name] = _pinned((4, self.n) if vector else (self.n,), tdt)
         return self._keep[name][1]
 
@@ -89,6 +90,31 @@ def lower(elements, colnames, meta):
     return lw.finish()
 
 
+def _lean_struct(prog, table, lean):
+    """Output pointers for a LEAN result set: only the columns named in ``lean`` come back; id columns
+    travel as int32 (MxbHostOptions.i32_out) and are stored as int32 in ``table``."""
+    cols = _lib.MxbColumns()
+    opts = _lib.MxbHostOptions()
+    unknown = [c for c in lean if c not in prog.out_f64 and c not in prog.out_i64 and c not in ('probability', 'energy')]
+    if unknown:
+        raise KeyError('lean columns {0} are not produced by this program'.format(unknown))
+    if 'probability' in lean:
+        if 'probability' not in table:
+            table.new_column('probability', np.float64)
+        cols.f64[10] = table.planes('probability').ctypes.data
+    for k, name in enumerate(prog.out_f64):
+        if name in lean:
+            if name not in table:
+                table.new_column(name, np.float64)
+            cols.f64[FIRST_OUT + k] = table.planes(name).ctypes.data
+    for k, name in enumerate(prog.out_i64):
+        if name in lean:
+            if name not in table or table.planes(name).dtype != np.int32:
+                table.new_column(name, np.int32)
+            opts.i32_out[k] = table.planes(name).ctypes.data
+    return cols, opts
+
+
 def _struct(prog, table, which, draws=None):
     cols = _lib.MxbColumns()
     n = len(table)
@@ -115,11 +141,17 @@ def _struct(prog, table, which, draws=None):
     return cols
 
 
-def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, program=None):
+def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, program=None, lean=None):
     """Trace a HOST photon table through ``instrument`` (an element or list of elements).
 
     In place by default (reference semantics); with ``out`` (another HostPhotonTable of
-    the same length) the inputs stay untouched.  Returns (table_or_out, Program)."""
+    the same length) the inputs stay untouched.  Returns (table_or_out, Program).
+
+    ``lean``: names of the only columns to bring back (SURVEY 8d lean mode, e.g. ``['order', 'facet',
+    'CCD_ID', 'chipx', 'chipy', 'probability']``); needs ``out``.  The kernel is specialised without the
+    stores of the other diagnostics, pos / dir / polarization stay on the device, and id columns come
+    back as int32 (``out[name].astype(np.int64)`` widens them; -1 = no hit).  The energy column is not
+    modified by any element: read it from the input table."""
     lib = _lib.load()
     elements = instrument if isinstance(instrument, (list, tuple)) else [instrument]
     prog = program if program is not None else lower(elements, table.colnames, table.meta)
@@ -127,6 +159,10 @@ def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, 
         raise ValueError('fused device images (element.image) are not available on the host-buffer path: '
                          'the image lives on the device; unset it or use the device API')
     dst = table if out is None else out
+    if lean is not None:
+        if out is None:
+            raise ValueError('lean output needs a separate `out` table (the input stays as it is)')
+        return _trace_host_lean(lib, prog, table, out, draws, chunk, check, list(lean))
     if out is not None:
         for name in VECTORS:
             if name not in out:
@@ -158,6 +194,42 @@ def trace_host(instrument, table, out=None, draws=None, chunk=None, check=True, 
         if status[_lib.MXB_ST_INTENSITY]:
             raise ValueError('Intensity cannot be > 1')
     return dst, prog
+
+
+def _trace_host_lean(lib, prog, table, out, draws, chunk, check, lean):
+    keep = None
+    if draws is not None:
+        keep = [np.ascontiguousarray(d, dtype=np.float64) if d is not None else None
+                for d in (draws.table if hasattr(draws, 'table') else draws)]
+    cin = _struct(prog, table, 'in', keep)
+    cout, opts = _lean_struct(prog, out, lean)
+    status = np.zeros(_lib.MXB_STATUS_WORDS, dtype=np.uint64)
+    rc = lib.mxb_trace_host_opts(prog.blob.ctypes.data, prog.blob.size, ctypes.byref(cin), ctypes.byref(cout),
+                                 len(table), int(chunk if chunk else os.environ.get('MXB_HOST_CHUNK', 0)), int(table.id0),
+                                 rng.next_launch_seed(), status.ctypes.data, ctypes.byref(opts))
+    _lib.check(lib, rc, 'mxb_trace_host_opts')
+    out.meta.update(prog.meta_updates)
+    prog.last_status = status
+    if check:
+        _raise_status(status)
+    return out, prog
+
+
+def _raise_status(status):
+    if status[_lib.MXB_ST_PROB_RANGE]:
+        raise ValueError('Found probability outside of the 0..1 arange.')
+    if status[_lib.MXB_ST_FILTER_BOUNDS]:
+        raise ValueError('A value in x_new is outside the interpolation range.')
+    if status[_lib.MXB_ST_INTENSITY]:
+        raise ValueError('Intensity cannot be > 1')
+
+
+def lean_bytes(prog, n, lean):
+    """(h2d, d2h) bytes per call of the lean mode, counted from the planes copied."""
+    d2h = 0
+    for name in lean:
+        d2h += 4 * n if name in prog.out_i64 else 8 * n
+    return 11 * 8 * n, d2h
 
 
 def h2d_d2h_bytes(prog, n, in_place=True):

@@ -1,26 +1,49 @@
 """Tier-R oracle loader: import the UNMODIFIED reference under the stand-ins.
 
-TEST INFRASTRUCTURE.  Only ``oracle/gen_golden.py`` and the oracle
-cross-check tests use this, and only in the build container:
-``/root/reference`` does not exist on the GPU box, so nothing in ``-m gpu``
-tests, ``smoke()`` or ``bench.py`` may call it (``available()`` is False there).
+TEST INFRASTRUCTURE.  Two places hold the reference: ``/root/reference`` (the source tree, build
+container only: ``oracle/gen_golden.py`` and the oracle cross-check tests read it) and
+``baseline/_ref`` (the offline ``pip install --target`` of the same tree made by
+``baseline/install_ref.py``; git-ignored, it travels to the GPU box with the snapshot).  The GPU box
+has no ``/root/reference``: there only ``bench.py``'s CPU legs (``--impl reference`` and
+``cpu_baseline``) import the installed copy, as the checker / baseline, never on the product path.
 """
 import importlib
 import importlib.metadata
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get('MARXS_REFERENCE_ROOT', '/root/reference')
-_STANDIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'standin')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')
+_STANDIN = os.path.join(_HERE, 'standin')
+
+
+def _pick_root():
+    env = os.environ.get('MARXS_REFERENCE_ROOT')
+    for c in ([env] if env else []) + ['/root/reference', INSTALLED_ROOT]:
+        if os.path.isdir(os.path.join(c, 'marxs')):
+            return c
+    return env or '/root/reference'
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'marxs'))
 
 
-def load_reference():
+def installed_available():
+    """The pip-installed copy under baseline/_ref (the one that exists on the GPU box)."""
+    return os.path.isdir(os.path.join(INSTALLED_ROOT, 'marxs'))
+
+
+def load_reference(root=None):
     """Return the imported reference package ``marxs`` (with sub-packages
-    math, optics, simulator, missions.chandra importable)."""
+    math, optics, simulator, missions.chandra importable).  ``root``: directory that holds the
+    ``marxs`` package (default: the source tree if present, else the installed copy)."""
+    global REFERENCE_ROOT
+    if root is not None:
+        REFERENCE_ROOT = root
     if not available():
         raise RuntimeError('reference tree not present at ' + REFERENCE_ROOT)
     if 'marxs' in sys.modules and getattr(sys.modules['marxs'], '_tier_r', False):

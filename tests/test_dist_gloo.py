@@ -41,10 +41,25 @@ WORKER = textwrap.dedent('''
     assert np.array_equal(cnt.numpy(), ref) and np.allclose(img.numpy(), 0.5 * ref)
     ev = mdist.gather_events({{'id': ids[ids % 7 == 0], 'w': (ids[ids % 7 == 0]).double() * 2}})
     if rank == 0:
-        assert np.array_equal(np.sort(ev['id'].numpy()), np.arange(0, 1001, 7))
+        # rows land in rank order = global photon-id order, no padding, no sort needed
+        assert np.array_equal(ev['id'].numpy(), np.arange(0, 1001, 7))
         assert np.allclose(ev['w'].numpy(), ev['id'].numpy() * 2.)
     else:
         assert ev is None
+    # ragged to the extreme: rank 1 has no events at all; destination buffers preallocated and reused
+    mine = ids[:5] if rank == 0 else ids[:0]
+    out = {{'id': torch.full((64,), -7, dtype=torch.int64)}} if rank == 0 else None
+    ev = mdist.gather_events({{'id': mine}}, out=out)
+    if rank == 0:
+        assert ev['id'].tolist() == [0, 1, 2, 3, 4] and ev['id'].data_ptr() == out['id'].data_ptr()
+    # gather on another rank, counts known beforehand
+    cnt2 = [3, 4]
+    ev = mdist.gather_events({{'x': torch.arange(cnt2[rank], dtype=torch.float64) + 10 * rank}}, dst=1, counts=cnt2)
+    if rank == 1:
+        assert ev['x'].tolist() == [0., 1., 2., 10., 11., 12., 13.]
+    else:
+        assert ev is None
+    assert mdist.gather_counts(3 + rank, torch.device('cpu')) == [3, 4]
     t = mdist.max_over_ranks(1.0 + rank, torch.device('cpu'))
     assert t == 2.0
     dist.barrier()
