@@ -60,6 +60,27 @@ def synth_c2_numpy(n, seed):
     return dict(pos=pos, dir=d, energy=rng.uniform(0.5, 8., n), polarization=pol, probability=np.ones(n))
 
 
+def synth_c2_device_chunked(n, seed, device, chunk=25_000_000):
+    """synth_c2_device for shards too large for its temporaries: filled chunk by chunk (chunk k is
+    synth_c2_device(m_k, seed + k))."""
+    import torch
+    import marxs_b200 as mb
+    if n <= chunk:
+        return synth_c2_device(n, seed, device)
+    b = mb.PhotonBatch(device=device)
+    store = {c: b.new_column(c, torch.float64, vector=True, n=n) for c in ('pos', 'dir', 'polarization')}
+    for c in ('energy', 'probability'):
+        store[c] = b.new_column(c, torch.float64)
+    for k, o in enumerate(range(0, n, chunk)):
+        m = min(chunk, n - o)
+        part = synth_c2_device(m, seed + k, device)
+        for c in store:
+            store[c][..., o:o + m] = part.storage(c)
+        del part
+    b.meta['ROLL_PNT'] = (0., 'roll')
+    return b
+
+
 def synth_c2_device(n, seed, device):
     import torch
     import marxs_b200 as mb
@@ -515,6 +536,161 @@ def run_engine(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------
+# BASELINE.json config 5: ONE Chandra HETG observation of --c5-photons photons, strong scaling over the GPUs.
+# Each rank holds its shard of the photon list resident in HBM (contiguous global photon ids), traces it batch
+# by batch into a reused result table with the detector image fused into the kernel, and appends the detected
+# events of every batch to its event store on the device (mxb_compact_append, no host round trip).  Epilogue,
+# inside the timed region: NCCL all-reduce of the image and a gather-v of the event lists on rank 0.
+# ---------------------------------------------------------------------------
+C5_EVENT_COLS = ['energy', 'order', 'CCD_ID', 'chipx', 'chipy', 'probability']
+
+
+def run_c5(args):
+    import ctypes
+    import torch
+    from marxs_b200 import _lib, dist as mdist, events as mevents
+    from marxs_b200.program import Lowering
+
+    rank, world, local = mdist.init_from_env('nccl' if args.gpus > 1 else None)
+    if world != args.gpus:
+        raise SystemExit('launch with torchrun --nproc-per-node {0} (WORLD_SIZE={1})'.format(args.gpus, world))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    lib = _lib.load()
+    n_total = int(args.c5_photons)
+    lo, hi = mdist.shard_range(n_total, rank, world)
+    n = hi - lo
+    B = min(int(args.c5_batch), n)
+    K, W = args.steps, args.warmup
+    inst = c2_instrument()
+    image = torch.zeros((6, 1024, 1024), dtype=torch.float64, device=device)
+    inst.elements[2].image = image
+    base = synth_c2_device_chunked(n, 20261017 + 1000 * rank, device)
+    base.id0 = lo
+    lw = Lowering(base.colnames, meta=base.meta)
+    inst._lower(lw)
+    prog = lw.finish()
+    blob = prog.device_blob(device)
+    # result table of ONE batch, reused by every batch (the events are what is kept)
+    out = synth_c2_device(B, 1, device)
+    cols, _ = prog.columns_struct(out)
+    status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    planes = []
+    for name in ('pos', 'dir', 'polarization'):
+        st = base.storage(name)
+        planes += [st.data_ptr() + k * n * 8 for k in range(3)]
+    planes += [base.storage('energy').data_ptr(), base.storage('probability').data_ptr()]
+    # energy is an INPUT column: it is not written to the result table in place ... out of place it is (flag 2)
+    dtypes = [out.storage(c).dtype for c in C5_EVENT_COLS]
+    cap = int(0.97 * n) + 1024                    # 94 % of the photons reach a CCD (zero order included)
+    store = mevents.EventStore(C5_EVENT_COLS, dtypes, cap, device)
+
+    def trace_shard(k):
+        for o in range(0, n, B):
+            m = min(B, n - o)
+            src = (ctypes.c_void_p * 11)(*[p + 8 * o for p in planes])
+            rc = lib.mxb_trace_from(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, src, ctypes.byref(cols),
+                                    m, lo + o, 777 + k, status.data_ptr(), stream)
+            if rc:
+                raise RuntimeError(lib.mxb_last_error().decode())
+            store.append(out, sel='CCD_ID', sel_min=0, weight='probability', n=m)
+
+    gathered = {}
+
+    def observation(k, ev=None):
+        store.reset()
+        image.zero_()
+        if ev:
+            ev[0].record()
+        trace_shard(k)
+        if ev:
+            ev[1].record()
+        mdist.allreduce_images([image])
+        if ev:
+            ev[2].record()
+        n_ev, dropped = store.count()
+        counts = mdist.gather_counts(n_ev, device) if world > 1 else [n_ev]
+        evcols = {c: store.cols[c][:n_ev] for c in C5_EVENT_COLS}
+        res = mdist.gather_events(evcols, dst=0, counts=counts, out=gathered.get('buf')) if world > 1 else evcols
+        if ev:
+            ev[3].record()
+        if rank == 0 and world > 1 and 'buf' not in gathered:
+            gathered['buf'] = {c: torch.empty(int(sum(counts) * 1.01) + 1024, dtype=t.dtype, device=device) for c, t in res.items()}
+        return counts, dropped, res
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(W):
+        observation(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(K):
+        counts, dropped, res = observation(W + k, evs[k])
+    ev1.record()
+    barrier()
+    total_ms = mdist.max_over_ranks(ev0.elapsed_time(ev1), device)
+    parts = [mdist.max_over_ranks(float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])), device) for j in range(3)]
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_path = lib.mxb_jit_info().decode()
+    n_events = int(sum(counts))
+    img_sum = float(image.sum())
+    on_rank0 = int(res[C5_EVENT_COLS[0]].shape[0]) if (rank == 0 and res is not None) else None
+    checks = None
+    if rank == 0:
+        e = res
+        checks = dict(events=n_events, events_over_photons=n_events / n_total, dropped=int(dropped), image_sum=img_sum,
+                      image_sum_vs_event_probability=float(e['probability'].sum()) / img_sum if img_sum else None,
+                      ccd_ids=sorted(int(v) for v in torch.unique(e['CCD_ID'][:: max(1, on_rank0 // 1000000)]).tolist()),
+                      chipx_range=[float(e['chipx'].min()), float(e['chipx'].max())])
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    ms_obs = total_ms / K
+    achieved = ALGO_BYTES_PER_PHOTON * n_total / (ms_obs * 1e-3) / 1e9
+    trace_gbs = ALGO_BYTES_PER_PHOTON * n / (parts[0] * 1e-3) / 1e9
+    ev_bytes = 8 * len(C5_EVENT_COLS)
+    line = dict(metric=METRIC, value=n_total * K / (total_ms * 1e-3), unit='photons/s', n_gpus=world, steps=K, warmup=W,
+                ms_per_step=ms_obs, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload='C5: one Chandra HETG observation (HRMA + HETG 336 facets + ACIS-S) of {0:.3g} photons sharded by '
+                                     'global photon id over {1} GPU(s); a step = the whole observation incl. image all-reduce and '
+                                     'event gather on rank 0'.format(n_total, world),
+                            photons_total=n_total, photons_per_gpu=n, batch=B, event_columns=C5_EVENT_COLS,
+                            rng='device Philox4x32-10 keyed by the global photon id',
+                            l2='every batch streams {0:.1f} GB (>> 126 MB L2)'.format(B * 336 / 1e9),
+                            build=lib.mxb_build_info().decode(), parallelism='photon-range sharding x{0}'.format(world)),
+                roofline=dict(bound='hbm', unit='GB/s', peak=peak * world, peak_source=peak_src + ' x {0} GPUs'.format(world),
+                              achieved=achieved, frac=achieved / (peak * world),
+                              frac_of_nominal_8tbs=achieved / (8000. * world),
+                              algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
+                              trace_only=dict(ms=parts[0], achieved_per_gpu=trace_gbs, frac=trace_gbs / peak,
+                                              note='trace + event compaction of one shard (max over ranks), before the epilogue'),
+                              traffic=None,
+                              note='achieved = 408 B x ALL photons / whole observation time (trace, compaction, all-reduce, gather)'),
+                phases_ms=dict(trace_and_compaction=parts[0], image_allreduce=parts[1], event_gather=parts[2]),
+                collective_ms=parts[1] + parts[2],
+                collective='ncclAllReduce (fp64 image, 50.3 MB) + counts all-reduce + grouped ncclSend/ncclRecv gather-v of '
+                           '{0} event columns ({1} B/event) onto rank 0'.format(len(C5_EVENT_COLS), ev_bytes),
+                events=n_events, gathered_on_rank0=on_rank0, gathered_bytes=(on_rank0 or 0) * ev_bytes,
+                clocks=clocks, gpu_launches=K * ((n + B - 1) // B) * 4, kernel_path=kernel_path, checks=checks,
+                e2e=None)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -529,6 +705,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--verify', type=int, default=100000,
                     help='photons of the timed batch checked against the CPU oracle with the exported Philox draws (0: off)')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c5'], help='c2: the headline (default); c5: the sharded observation')
+    ap.add_argument('--c5-photons', type=float, default=1e9, help='photons of the whole observation (config c5)')
+    ap.add_argument('--c5-batch', type=float, default=2.5e7, help='photons per launch within a shard (config c5)')
     ap.add_argument('--no-image', action='store_true', help='experiment: do not fuse the detector image')
     ap.add_argument('--isolate', action='store_true', help='experiment: synchronise after every step')
     args = ap.parse_args()
@@ -536,6 +715,8 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 'c5':
+        run_c5(args)
     else:
         run_engine(args)
 

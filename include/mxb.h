@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 10
+#define MXB_ABI_VERSION 11
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -288,6 +288,16 @@ size_t mxb_compact_workspace(int64_t n);
 int mxb_compact_events(const void* const* src_planes, void* const* dst_planes, int n_planes,
                        const long long* sel, long long sel_min, const double* weight, int64_t n,
                        long long* n_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+
+/* mxb_compact_events in APPEND mode, for observations traced batch by batch: the rows kept go to
+ * dst_planes[p][cursor_dev[0] + k] and cursor_dev[0] (device, int64) advances by their number, all on the
+ * device - no host round trip between batches.  dst planes hold `capacity` rows; rows beyond it are dropped
+ * and counted in cursor_dev[1] (the caller checks it once at the end).  dst planes may be PEER memory (another
+ * GPU's event store mapped over NVLink): the scatter kernel then is the gather.  Asynchronous on `stream`. */
+int mxb_compact_append(const void* const* src_planes, void* const* dst_planes, int n_planes,
+                       const long long* sel, long long sel_min, const double* weight, int64_t n,
+                       long long* cursor_dev, int64_t capacity, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 10
+MXB_ABI_VERSION = 11
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -94,6 +94,8 @@ def load(strict=None):
     lib.mxb_compact_workspace.argtypes = [i64]
     lib.mxb_compact_events.restype = ci
     lib.mxb_compact_events.argtypes = [vp, vp, ci, vp, ctypes.c_longlong, vp, i64, vp, vp, sz, vp]
+    lib.mxb_compact_append.restype = ci
+    lib.mxb_compact_append.argtypes = [vp, vp, ci, vp, ctypes.c_longlong, vp, i64, vp, i64, vp, sz, vp]
     lib.mxb_jit_compile.restype = ctypes.c_longlong
     lib.mxb_jit_compile.argtypes = [vp, sz, ctypes.POINTER(MxbColumns)]
     if lib.mxb_version() != MXB_ABI_VERSION:
@@ -120,4 +122,4 @@ def check(lib, rc, what):
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
                     'mxb_trace_from', 'mxb_trace_host', 'mxb_trace_host_opts', 'mxb_debug_draws', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
-                    'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events']
+                    'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events', 'mxb_compact_append']

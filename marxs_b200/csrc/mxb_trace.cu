@@ -689,13 +689,18 @@ compact_count_kernel(const long long* sel, long long sel_min, const double* w, l
     const int c = __syncthreads_count(compact_keep(sel, sel_min, w, i, n) ? 1 : 0);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
+// cursor != nullptr (append mode): the exclusive offsets start at cursor[0], which then advances by the
+// number of rows kept; rows that would land at or beyond `capacity` are dropped by the scatter kernel and
+// counted in cursor[1]
 __global__ void __launch_bounds__(1024)
-compact_scan_kernel(long long* block_counts, long long n_blocks, long long* n_out) {
+compact_scan_kernel(long long* block_counts, long long n_blocks, long long* n_out, long long* cursor = nullptr,
+                    long long capacity = 0) {
     // exclusive scan in place, one CTA: chunks of 1024 with a running carry
     __shared__ long long warp_sum[32];
     __shared__ long long carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = cursor ? cursor[0] : 0;
     __syncthreads();
+    const long long start = carry;
     for (long long base = 0; base < n_blocks; base += 1024) {
         const long long k = base + threadIdx.x;
         const long long v = k < n_blocks ? block_counts[k] : 0;
@@ -723,11 +728,19 @@ compact_scan_kernel(long long* block_counts, long long n_blocks, long long* n_ou
         if (threadIdx.x == 1023) carry = before + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *n_out = carry;
+    if (threadIdx.x == 0) {
+        if (n_out) *n_out = carry - start;
+        if (cursor) {
+            const long long end = carry > capacity ? capacity : carry;
+            if (carry > capacity) cursor[1] += carry - (start > capacity ? start : capacity);
+            cursor[0] = end;
+        }
+    }
 }
 __global__ void __launch_bounds__(kCompactThreads)
 compact_scatter_kernel(const __grid_constant__ CompactPlanes P, int n_planes, const long long* sel, long long sel_min,
-                       const double* w, long long n, const long long* block_offsets) {
+                       const double* w, long long n, const long long* block_offsets,
+                       long long capacity = 0x7fffffffffffffffLL) {
     __shared__ int warp_cnt[kCompactThreads / 32];
     const long long i = (long long)blockIdx.x * kCompactThreads + threadIdx.x;
     const bool keep = compact_keep(sel, sel_min, w, i, n);
@@ -747,6 +760,7 @@ compact_scatter_kernel(const __grid_constant__ CompactPlanes P, int n_planes, co
     __syncthreads();
     if (!keep) return;
     const long long o = block_offsets[blockIdx.x] + (warp ? warp_cnt[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u));
+    if (o >= capacity) return;
     for (int p = 0; p < n_planes; ++p) P.dst[p][o] = P.src[p][i];
 }
 
@@ -964,6 +978,31 @@ int mxb_compact_events(const void* const* src_planes, void* const* dst_planes, i
     compact_count_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(sel, sel_min, weight, n, counts);
     compact_scan_kernel<<<1, 1024, 0, s>>>(counts, blocks, n_out_dev);
     compact_scatter_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(P, n_planes, sel, sel_min, weight, n, counts);
+    CUDA_TRY(cudaGetLastError());
+    return MXB_OK;
+}
+
+int mxb_compact_append(const void* const* src_planes, void* const* dst_planes, int n_planes, const long long* sel,
+                       long long sel_min, const double* weight, int64_t n, long long* cursor_dev, int64_t capacity,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!src_planes || !dst_planes || !cursor_dev || !workspace) return fail(MXB_EINVAL, "mxb_compact_append: null pointer");
+    if (n_planes < 1 || n_planes > kCompactMaxPlanes) return fail(MXB_EINVAL, "mxb_compact_append: 1..64 planes");
+    if (n < 0 || capacity < 0) return fail(MXB_EINVAL, "negative n or capacity");
+    if (workspace_bytes < mxb_compact_workspace(n)) return fail(MXB_EINVAL, "mxb_compact_append: workspace too small");
+    if (n == 0) return MXB_OK;
+    CompactPlanes P;
+    memset(&P, 0, sizeof(P));
+    for (int p = 0; p < n_planes; ++p) {
+        if (!src_planes[p] || !dst_planes[p]) return fail(MXB_EINVAL, "mxb_compact_append: null plane");
+        P.src[p] = static_cast<const unsigned long long*>(src_planes[p]);
+        P.dst[p] = static_cast<unsigned long long*>(dst_planes[p]);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long blocks = (n + kCompactThreads - 1) / kCompactThreads;
+    long long* counts = static_cast<long long*>(workspace);
+    compact_count_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(sel, sel_min, weight, n, counts);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(counts, blocks, nullptr, cursor_dev, capacity);
+    compact_scatter_kernel<<<(unsigned)blocks, kCompactThreads, 0, s>>>(P, n_planes, sel, sel_min, weight, n, counts, capacity);
     CUDA_TRY(cudaGetLastError());
     return MXB_OK;
 }

@@ -60,7 +60,7 @@ def test_global_energy_filter(mode):
     run_pair(optics.GlobalEnergyFilter(filterfunc=optics.Tabulated1D(x, y)), mo.GlobalEnergyFilter(mo.Tabulated1D(x, y)),
              table, exact_float=(mode == 'strict'))
     for kw in (dict(bounds_error=False, fill_value=(0.1, 0.2)), dict(bounds_error=False, fill_value='extrapolate')):
-        xs, ys = x[1:-1], y[1:-1] * 0.5 + 0.2
+        xs, ys = x[1:-1], np.array([0.4, 0.5, 0.55, 0.6])      # extrapolated ends stay inside [0, 1] for 0.3..8 keV
         run_pair(optics.GlobalEnergyFilter(filterfunc=optics.Tabulated1D(xs, ys, **kw)),
                  mo.GlobalEnergyFilter(mo.Tabulated1D(xs, ys, **kw)), table, rtol=1e-13)
     # out of range with bounds_error -> the ValueError scipy raises in the reference
@@ -150,12 +150,20 @@ def test_lean_host_output_matches_full(mode):
     out, prog = mhost.trace_host(prod, src, out=lean, draws=draws, chunk=8192, lean=LEAN)
     got = lean.to_numpy()
     assert set(got.keys()) == set(LEAN)
-    for c in LEAN:
-        if c in ('facet', 'CCD_ID'):
-            assert got[c].dtype == np.int32
-            assert np.array_equal(got[c].astype(np.int64), want[c]), c
-        else:
-            assert np.array_equal(got[c], want[c], equal_nan=True), c
+    def same(got, want):
+        # the lean kernel is ANOTHER specialisation (no stores of the other columns): in the fast build its FMA
+        # contraction may differ in the last bit; ids, orders and pixel indices are exact, the strict build all of it
+        for c in LEAN:
+            if c in ('facet', 'CCD_ID'):
+                assert got[c].dtype == np.int32
+                assert np.array_equal(got[c].astype(np.int64), want[c]), c
+            elif c == 'order' or mode == 'strict':
+                assert np.array_equal(got[c], want[c], equal_nan=True), c
+            else:
+                np.testing.assert_allclose(got[c], want[c], rtol=1e-13, atol=0, equal_nan=True, err_msg=c)
+                ok = np.isfinite(want[c])
+                assert np.array_equal(np.round(got[c][ok]), np.round(want[c][ok])), c
+    same(got, want)
     h2d, d2h = mhost.lean_bytes(prog, n, LEAN)
     assert h2d == 88 * n and d2h == (4 * 8 + 2 * 4) * n
     assert np.array_equal(src['pos'], table['pos'])
@@ -164,9 +172,7 @@ def test_lean_host_output_matches_full(mode):
     mhost.trace_host(prod, src, out=full, chunk=20000)
     mb.set_seed(9)
     mhost.trace_host(prod, src, out=lean, chunk=7000, lean=LEAN)
-    want, got = full.to_numpy(), lean.to_numpy()
-    for c in LEAN:
-        assert np.array_equal(got[c].astype(want[c].dtype), want[c], equal_nan=True), c
+    same(lean.to_numpy(), full.to_numpy())
     with pytest.raises(KeyError):
         mhost.trace_host(prod, src, out=lean, lean=['no_such_column'])
     with pytest.raises(ValueError):
@@ -209,9 +215,15 @@ def test_exported_draws_match_numpy_philox(mode):
     u1 = ((r[:, 0] << np.uint64(32) | r[:, 1]) >> np.uint64(11)).astype(float) / 2. ** 53
     u2 = ((r[:, 2] << np.uint64(32) | r[:, 3]) >> np.uint64(11)).astype(float) / 2. ** 53
     rad = np.sqrt(-2. * np.log(1. - u1))
-    tol = 1e-13 if mode == 'strict' else 3e-6
-    np.testing.assert_allclose(z.cpu().numpy(), rad * np.cos(2 * np.pi * u2), atol=tol * 5, rtol=tol)
-    np.testing.assert_allclose(z1.cpu().numpy(), rad * np.sin(2 * np.pi * u2), atol=tol * 5, rtol=tol)
+    # the fast build takes the angle in [-pi, pi): 2 pi (u2 - 1/2), i.e. both members change sign
+    tol, sgn = (1e-13, 1.) if mode == 'strict' else (3e-6, -1.)
+    np.testing.assert_allclose(z.cpu().numpy(), sgn * rad * np.cos(2 * np.pi * u2), atol=tol * 5, rtol=tol)
+    np.testing.assert_allclose(z1.cpu().numpy(), sgn * rad * np.sin(2 * np.pi * u2), atol=tol * 5, rtol=tol)
+    # a single normal (kind 1) is the first member of the same block
+    zs = torch.empty(n, dtype=torch.float64, device='cuda')
+    assert lib.mxb_debug_draws(seed, id0, n, 2, 1, zs.data_ptr(), None, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(zs, z)
 
 
 def test_philox_drawn_launch_matches_oracle(mode):
@@ -308,3 +320,96 @@ def test_box_muller_ks_at_1e8():
     c = float((z0 * z1).mean())
     c2 = float(((z0 * z0 - 1) * (z1 * z1 - 1)).mean())
     assert abs(c) < 5e-4 and abs(c2) < 1.5e-3, (c, c2)
+
+
+def test_event_store_append():
+    """mxb_compact_append: batches appended with a device-side cursor == boolean indexing of the concatenation,
+    order preserved; overflow is counted, never written past the capacity."""
+    mb = _mb()
+    from marxs_b200 import events, _lib
+    rng = np.random.default_rng(SEED + 107)
+    names = ['energy', 'CCD_ID', 'probability']
+    sizes = (5, 1023, 1024, 1025, 70001)
+    tabs = []
+    for n in sizes:
+        ccd = rng.integers(-1, 6, n)
+        prob = rng.uniform(-0.2, 1., n)
+        prob[rng.random(n) < 0.05] = np.nan
+        tabs.append({'energy': rng.random(n), 'probability': prob, 'CCD_ID': ccd})
+    want = {c: np.concatenate([t[c][(t['CCD_ID'] >= 0) & (t['probability'] > 0)] for t in tabs]) for c in names}
+    total = len(want['energy'])
+    store = events.EventStore(names, [torch.float64, torch.int64, torch.float64], total + 10, 'cuda')
+    for rep in range(2):                                   # reset() and reuse
+        store.reset()
+        for t in tabs:
+            b = mb.PhotonBatch(dict(t, pos=np.zeros((len(t['energy']), 4))), device='cuda')
+            store.append(b)
+        assert store.count() == (total, 0)
+        got = store.columns()
+        for c in names:
+            assert np.array_equal(got[c].cpu().numpy(), want[c]), c
+    # a batch larger than what is used of it (n=), and overflow
+    small = events.EventStore(names, [torch.float64, torch.int64, torch.float64], 100, 'cuda')
+    guard = small.cols['energy']
+    big = mb.PhotonBatch(dict(tabs[-1], pos=np.zeros((sizes[-1], 4))), device='cuda')
+    small.append(big, n=150)
+    keep150 = ((tabs[-1]['CCD_ID'][:150] >= 0) & (tabs[-1]['probability'][:150] > 0))
+    assert small.count() == (int(keep150.sum()), 0)
+    small.append(big)
+    m, dropped = small.count()
+    keep_all = int(((tabs[-1]['CCD_ID'] >= 0) & (tabs[-1]['probability'] > 0)).sum())
+    assert m == 100 and dropped == int(keep150.sum()) + keep_all - 100
+    with pytest.raises(_lib.MxbError):
+        small.columns()
+    assert guard.shape[0] == 100
+    first = np.concatenate([tabs[-1]['energy'][:150][keep150],
+                            tabs[-1]['energy'][(tabs[-1]['CCD_ID'] >= 0) & (tabs[-1]['probability'] > 0)]])[:100]
+    assert np.array_equal(small.cols['energy'].cpu().numpy(), first)
+
+
+def test_scalar_process_photon_hook(mode):
+    """The scalar plug-in hook (reference optics/base.py:98-142, loop :186-197): kernel intersect, then the
+    user's per-photon Python on the hits; outputs written back with the reference's column rules."""
+    from marxs_b200 import optics
+    mb = _mb()
+    rng = np.random.default_rng(SEED + 108)
+    n = 3000
+    pos4d = rand_pos4d(rng, zoom=(1., 6., 6.))
+    table = make_photons(rng, n, spread=0.05, lateral=9.)
+
+    class Kicker(optics.FlatOpticalElement):
+        output_columns = ['kick', 'esq']
+        loc_coos_name = ['ky', 'kz']
+
+        def process_photon(self, dir, pos, energy, polarization):
+            assert dir.shape == (4,) and pos.shape == (4,) and np.ndim(energy) == 0
+            kick = 1e-3 * energy
+            new = dir + np.array([0., kick, -kick, 0.])
+            return new, pos, energy * 0.5, polarization[[0, 2, 1, 3]], 0.25, kick, energy ** 2
+
+    elem = Kicker(pos4d=pos4d, id_col='kicker', id_num=7)
+    got = elem(mb.PhotonBatch(table, device='cuda')).to_numpy()
+    hit, interpos, loc = mo.plane_intersect(mo.PlaneConsts(pos4d), table['dir'], table['pos'], False)
+    assert 0.2 < hit.mean() < 0.95
+    kick = 1e-3 * table['energy']
+    want_dir = table['dir'].copy()
+    want_dir[hit, 1] += kick[hit]
+    want_dir[hit, 2] -= kick[hit]
+    np.testing.assert_array_equal(got['dir'], want_dir)
+    np.testing.assert_array_equal(got['energy'], np.where(hit, table['energy'] * 0.5, table['energy']))
+    np.testing.assert_array_equal(got['probability'], np.where(hit, table['probability'] * 0.25, table['probability']))
+    np.testing.assert_array_equal(got['polarization'][hit], table['polarization'][hit][:, [0, 2, 1, 3]])
+    np.testing.assert_array_equal(got['polarization'][~hit], table['polarization'][~hit])
+    np.testing.assert_array_equal(got['kick'], np.where(hit, kick, np.nan))
+    np.testing.assert_array_equal(got['esq'], np.where(hit, table['energy'] ** 2, np.nan))
+    np.testing.assert_array_equal(got['kicker'], np.where(hit, 7, -1))
+    np.testing.assert_allclose(got['pos'][hit], interpos[hit], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(got['pos'][~hit], table['pos'][~hit])
+    np.testing.assert_allclose(got['ky'][hit], loc[hit, 0], rtol=1e-12, atol=1e-12)
+    assert np.isnan(got['ky'][~hit]).all()
+
+    class Bad(Kicker):
+        def process_photon(self, dir, pos, energy, polarization):
+            return dir, pos, energy, polarization, 1.5, 0., 0.
+    with pytest.raises(ValueError):
+        Bad(pos4d=pos4d)(mb.PhotonBatch(table, device='cuda'))
