@@ -158,6 +158,24 @@ class Cylinder(Geometry):
     def phi_lim(self):
         return self.coos_limits[0]
 
+    def get_local_euklid_bases(self, interpos_local):
+        """Local base (e_phi, e_z, e_n) at the positions ``interpos_local`` = (phi, z) (reference :602-626):
+        the tangent and the normal are the images of the unit-circle vectors under pos4d, normalised;
+        e_z is the (un-normalised) global-frame axis vector as the reference returns it.  Host arrays."""
+        loc = np.asarray(interpos_local.detach().cpu() if isinstance(interpos_local, torch.Tensor) else interpos_local,
+                         dtype=float)
+        phi = loc[:, 0]
+        zeros = np.zeros_like(phi)
+        e_phi = np.array([-np.sin(phi), np.cos(phi), zeros, zeros]).T
+        e_n = np.array([np.cos(phi), np.sin(phi), zeros, zeros]).T
+        e_z = np.tile(self['e_z'], (loc.shape[0], 1))
+        e_phi = np.einsum('ij,nj->ni', self.pos4d, e_phi)
+        e_n = np.einsum('ij,nj->ni', self.pos4d, e_n)
+
+        def unit(v):
+            return v / np.linalg.norm(v, axis=-1)[:, None]
+        return unit(e_phi), e_z, unit(e_n)
+
     def intersect(self, dir, pos):
         """-> (intersect bool (N,), interpos (N, 4), interpos_local (N, 2) = (phi, z)), NaN on miss.
         Runs the CYLINDER op of the trace kernel on a scratch table."""

@@ -626,6 +626,22 @@ def case_cylinder(marxs, rng):
     save('cylinder', **arrays)
 
 
+def case_euklid_bases(marxs, rng):
+    """Geometry.get_local_euklid_bases of FinitePlane (geometry.py:263-281) and Cylinder (:602-626)."""
+    from marxs.math.geometry import Cylinder, FinitePlane
+    from transforms3d.euler import euler2mat
+    from transforms3d.affines import compose
+    arrays = {}
+    for tag, cls, zoom in (('plane', FinitePlane, [1., 7., 3.]), ('cyl', Cylinder, [40., 25., 6.])):
+        pos4d = compose(rng.uniform(-3, 3, 3), euler2mat(*rng.uniform(-0.5, 0.5, 3)), zoom)
+        g = cls({'pos4d': pos4d})
+        loc = np.column_stack([rng.uniform(-3, 3, 50), rng.uniform(-1, 1, 50)])
+        e1, e2, n = g.get_local_euklid_bases(loc)
+        arrays[tag + '_pos4d'], arrays[tag + '_loc'] = pos4d, loc
+        arrays[tag + '_e1'], arrays[tag + '_e2'], arrays[tag + '_n'] = np.asarray(e1), np.asarray(e2), np.asarray(n)
+    save('euklid_bases', **arrays)
+
+
 class SeqFeeder:
     """Replace np.random.uniform / rand for code that draws outside any optical element (sources):
     the k-th call returns low + (high - low) * table[k]."""
@@ -916,7 +932,7 @@ def main():
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
                               case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing,
-                              case_lens_reflectivity, case_grating_callable_d, case_scatter_callable]):
+                              case_lens_reflectivity, case_grating_callable_d, case_scatter_callable, case_euklid_bases]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

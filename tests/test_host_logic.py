@@ -570,3 +570,28 @@ def test_filter_fill_modes_follow_scipy():
         lower_filter(optics.Tabulated1D(x, y, bounds_error=False, fill_value=1.5))
     with pytest.raises(ValueError):
         mo.Tabulated1D(x, y)(q)
+
+
+def test_get_local_euklid_bases_golden():
+    """Geometry.get_local_euklid_bases (reference math/geometry.py:263-281 plane, :602-626 cylinder) against a
+    run of the unmodified reference (tests/golden/euklid_bases.npz, oracle/gen_golden.py case_euklid_bases),
+    plus the reference's own known answer (math/tests/test_geometry.py:240-252)."""
+    import os
+    from marxs_b200 import geometry
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'euklid_bases.npz')))
+    for tag, cls in (('plane', geometry.FinitePlane), ('cyl', geometry.Cylinder)):
+        geo = cls({'pos4d': g[tag + '_pos4d']})
+        e1, e2, n = geo.get_local_euklid_bases(g[tag + '_loc'])
+        for got, name in ((e1, 'e1'), (e2, 'e2'), (n, 'n')):
+            assert np.asarray(got).shape == (50, 4)
+            np.testing.assert_allclose(np.asarray(got), g[tag + '_' + name], rtol=1e-14, atol=1e-15, err_msg=tag + name)
+    # a plane's base is its own axes, whatever the position
+    geo = geometry.FinitePlane({'position': [5., 1., 2.], 'zoom': [1., 3., 7.]})
+    x, y, z = geo.get_local_euklid_bases(np.random.rand(5, 2))
+    assert np.all(x == np.array([0., 1., 0., 0.])) and np.all(y == np.array([0., 0., 1., 0.]))
+    assert np.all(z == np.array([1., 0., 0., 0.]))
+    # cylinder: tangent, axis and normal are mutually perpendicular for an un-sheared, isotropic-radius tube
+    geo = geometry.Cylinder({'zoom': [10., 10., 4.], 'position': [1., 2., 3.]})
+    e_phi, e_z, e_n = geo.get_local_euklid_bases(np.column_stack([np.linspace(-3, 3, 7), np.zeros(7)]))
+    assert np.allclose(np.einsum('ij,ij->i', e_phi, e_n), 0.) and np.allclose(np.einsum('ij,ij->i', e_phi, e_z), 0.)
+    assert np.allclose(np.linalg.norm(e_n, axis=1), 1.)

@@ -93,11 +93,26 @@ SCALE = {'pos': 1e4, 'x': 1e4, 'y': 1e4, 'detx': 1e4, 'dety': 1e4, 'tdetx': 1e4,
          'chipx': 1e3, 'chipy': 1e3, 'detpix_x': 1e3, 'detpix_y': 1e3}
 
 
-def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=()):
-    """got_batch: PhotonBatch, want: oracle PhotonTable."""
+CORE_TIGHT = ('pos', 'dir', 'probability')       # BASELINE.json north_star: 1e-12 relative, whatever the chain
+ERROR_LOG = []                                   # (test id, column, max normalised error): written to gpurun_out/ at exit
+
+
+def _norm_err(g, w, scale):
+    ok = np.isfinite(w) & np.isfinite(g)
+    if not ok.any():
+        return 0.
+    return float(np.max(np.abs(g[ok] - w[ok]) / np.maximum(np.abs(w[ok]), scale)))
+
+
+def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=(), pol_bound=None):
+    """got_batch: PhotonBatch, want: oracle PhotonTable.  ``rtol`` applies to the diagnostic columns; pos, dir and
+    probability are ALWAYS held to 1e-12 (relative; absolute 1e-12 x the column's scale).  ``pol_bound``: per-photon
+    absolute bound for the polarization column where a chain makes it ill-conditioned (parallel transport after
+    a tiny redirection amplifies rounding by 1/|d1 x d2|, see _pol_bound)."""
     got = got_batch.to_numpy()
     assert set(want.colnames) - set(skip) <= set(got.keys()), (want.colnames, list(got.keys()))
     assert set(got.keys()) <= set(want.colnames), 'extra columns: {0}'.format(set(got) - set(want.colnames))
+    test_id = os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0]
     for c in want.colnames:
         if c in skip:
             continue
@@ -108,6 +123,7 @@ def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=()):
                                           np.nan_to_num(w.astype(float), nan=-99), err_msg=c)
             continue
         np.testing.assert_array_equal(np.isnan(g), np.isnan(w), err_msg='NaN pattern of ' + c)
+        ERROR_LOG.append((test_id, c, _norm_err(g, w, SCALE.get(c, 1.))))
         if c in PIXEL_COLS:
             ok = np.isfinite(w)
             np.testing.assert_array_equal(np.round(g[ok]), np.round(w[ok]), err_msg='pixel index ' + c)
@@ -122,8 +138,26 @@ def compare(got_batch, want, exact_float=False, rtol=1e-12, skip=()):
             tol = rtol * np.abs(w[ok]) + 2e-15 / np.maximum(w[ok], 1e-7)   # ~10 ulp of the cosine
             assert np.all(np.abs(g[ok] - w[ok]) <= tol), 'blaze: max excess {0}'.format(
                 (np.abs(g[ok] - w[ok]) - tol).max())
+        elif c == 'polarization' and pol_bound is not None:
+            ok = np.isfinite(w).all(axis=1)
+            err = np.abs(g[ok] - w[ok]).max(axis=1)
+            assert np.all(err <= pol_bound[ok]), 'polarization: max excess over the conditioning bound {0}'.format(
+                (err - pol_bound[ok]).max())
         else:
-            np.testing.assert_allclose(g, w, rtol=rtol, atol=rtol * SCALE.get(c, 1.), equal_nan=True, err_msg=c)
+            r = min(rtol, 1e-12) if c in CORE_TIGHT else rtol
+            np.testing.assert_allclose(g, w, rtol=r, atol=r * SCALE.get(c, 1.), equal_nan=True, err_msg=c)
+
+
+def _pol_bound(angles, base=1e-12, k=64):
+    """Bound of the polarization error after parallel transports by the small redirection angles ``angles``
+    (list of (N,) arrays, NaN = no redirection): each transport normalises s = d1 x d2, so rounding of the cross
+    product (eps relative to |d1||d2| = 1) becomes a k * eps / |d1 x d2| component.  The reference's own result
+    carries the same uncertainty (math/polarization.py:122-170; identity below |s| = 1e-8)."""
+    b = np.full(len(angles[0]), base)
+    for a in angles:
+        a = np.abs(np.nan_to_num(a, nan=np.inf))
+        b = b + k * 2.2e-16 / np.maximum(a, 1e-8)
+    return b
 
 
 def run_pair(prod, orac, table, draws=None, **cmp):
@@ -751,8 +785,17 @@ def test_chandra_c2_golden(mode):
         ref = g['out_' + c]
         if c in INDEX_COLS:
             np.testing.assert_array_equal(np.nan_to_num(out[c].astype(float), nan=-99), np.nan_to_num(ref.astype(float), nan=-99), err_msg=c)
+        elif c == 'polarization':
+            # two Rodrigues rotations by ~1e-5 / ~1e-6 rad, then ONE transport from the old to the new direction
+            bound = _pol_bound([np.hypot(g['out_inplanescatter'], g['out_perpplanescatter'])])
+            ok = np.isfinite(ref).all(axis=1)
+            assert np.all(np.abs(out[c][ok] - ref[ok]).max(axis=1) <= bound[ok])
         else:
-            np.testing.assert_allclose(out[c], ref, rtol=1e-11, atol=1e-9, equal_nan=True, err_msg=c)
+            # the reference's own BLAS summation order gives its golden values ~2e-13 relative
+            r = 1e-12 if c in CORE_TIGHT else 1e-11
+            np.testing.assert_allclose(out[c], ref, rtol=r, atol=r * SCALE.get(c, 1.), equal_nan=True, err_msg=c)
+        if c not in INDEX_COLS:
+            ERROR_LOG.append((os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0], c, _norm_err(out[c], ref, SCALE.get(c, 1.))))
         if c in PIXEL_COLS:
             ok = np.isfinite(ref)
             np.testing.assert_array_equal(np.round(out[c][ok]), np.round(ref[ok]), err_msg=c)
@@ -765,7 +808,8 @@ def test_chandra_c2_vs_oracle(mode):
     prod, orac = chandra_pair()
     table = chandra_photons(rng, n)
     draws = [rng.standard_normal(n), rng.standard_normal(n), rng.random(n)]
-    got, want = run_pair(prod, orac, table, draws, rtol=1e-11)
+    got, want = run_pair(prod, orac, table, draws, rtol=1e-11,
+                         pol_bound=_pol_bound([np.hypot(draws[0] * 3.6e-6, draws[1] * 1.2e-6)]))    # HRMA scatter widths (hrma_py.py)
     assert 0.8 < (want['facet'] >= 0).mean() < 0.9
     assert (want['CCD_ID'] >= 0).mean() > 0.5
 

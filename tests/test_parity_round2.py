@@ -8,7 +8,7 @@ import torch
 
 from oracle import marxs_oracle as mo
 from test_parity_gpu import (mode, _jit_default_forced, make_photons, rand_pos4d, run_pair, compare,  # noqa: F401
-                             chandra_pair, chandra_photons, SEED, _mb)
+                             chandra_pair, chandra_photons, SEED, _mb, _pol_bound)
 
 pytestmark = pytest.mark.gpu
 
@@ -160,7 +160,9 @@ def test_lean_host_output_matches_full(mode):
             elif c == 'order' or mode == 'strict':
                 assert np.array_equal(got[c], want[c], equal_nan=True), c
             else:
-                np.testing.assert_allclose(got[c], want[c], rtol=1e-13, atol=0, equal_nan=True, err_msg=c)
+                # chip coordinates inherit 1e-12 of a 1e4 mm position: 1e-8 mm / 0.024 mm per pixel
+                np.testing.assert_allclose(got[c], want[c], rtol=1e-12, atol=1e-6 if c.startswith('chip') else 0,
+                                           equal_nan=True, err_msg=c)
                 ok = np.isfinite(want[c])
                 assert np.array_equal(np.round(got[c][ok]), np.round(want[c][ok])), c
     same(got, want)
@@ -250,7 +252,7 @@ def test_philox_drawn_launch_matches_oracle(mode):
     draws = [d.cpu().numpy() for d in draws]
     mo.assign_slots(orac)
     want = orac(table.copy(), mo.Draws(draws))
-    compare(got, want, rtol=1e-11)
+    compare(got, want, rtol=1e-11, pol_bound=_pol_bound([np.hypot(draws[0] * 3.6e-6, draws[1] * 1.2e-6)]))
     assert (want['CCD_ID'] >= 0).mean() > 0.5
 
 

@@ -1,6 +1,6 @@
 """Summarise gpurun_out ncu artefacts into profiles/ (tracked).
 
-    python tools/summarize_profile.py <tag> <launches.csv> <report.ncu-rep> [photons_per_launch]
+    python tools/summarize_profile.py <tag> <launches.csv> <report.ncu-rep> [photons_per_launch] [kernel_hash]
 
 Writes profiles/<tag>_launches.csv (kernel share table), profiles/<tag>_trace_kernel.md (key ncu
 metrics, opcode mix, hottest source lines) and updates profiles/traffic.json (dram bytes/photon,
@@ -130,7 +130,8 @@ def main():
                                                                     l[2][:90].replace('|', '\\|')))
     with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
         json.dump({'tag': tag, 'dram_bytes_per_photon': (rd + wr) / nph, 'read': rd / nph, 'write': wr / nph,
-                   'kernel_ms_under_ncu': dur * 1e3}, f)
+                   'kernel_ms_under_ncu': dur * 1e3, 'kernel_hash': sys.argv[5] if len(sys.argv) > 5 else '?',
+                   'capture': 'profiles/{0}_trace_kernel.md'.format(tag)}, f)
     print('wrote profiles/{0}_*'.format(tag))
 
 
