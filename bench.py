@@ -543,6 +543,108 @@ def run_engine(args):
 # events of every batch to its event store on the device (mxb_compact_append, no host round trip).  Epilogue,
 # inside the timed region: NCCL all-reduce of the image and a gather-v of the event lists on rank 0.
 # ---------------------------------------------------------------------------
+def run_other(args):
+    """--config c3 | c4: the other full-size BASELINE.json configurations in the same JSON schema (one GPU).
+    C3: lens + scatter -> 561 CATL1L2Stack facets on a Rowland torus (135 x 25 x 28 efficiency table) -> 16 CCDs, 1e8
+    resident photons traced out of place.  C4: multilayer polarimeter, 1e8 photons BORN on the device (nothing read)."""
+    import ctypes
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_configs as bc
+    from marxs_b200 import _lib, simulator, source
+    from marxs_b200.program import Lowering
+    if args.gpus != 1 or int(os.environ.get('WORLD_SIZE', '1')) != 1:
+        raise SystemExit('--config c3/c4 run on one GPU')
+    torch.cuda.set_device(0)
+    device = torch.device('cuda', 0)
+    lib = _lib.load()
+    K, W = args.steps, args.warmup
+    n = int(args.photons if args.photons != N_PER_GPU else 1e8)
+    if args.config == 'c3':
+        elements, base, n_facets = bc.c3_setup(n)
+        inst = simulator.Sequence(elements=elements)
+        lw = Lowering(base.colnames, meta=base.meta)
+        inst._lower(lw)
+        prog = lw.finish()
+        out = base.copy()
+        cols, _ = prog.columns_struct(out)
+        src = prog.source_planes(base, n)
+        blob = prog.device_blob(device)
+        status = torch.zeros(_lib.MXB_STATUS_WORDS, dtype=torch.int64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        diag = len(prog.out_f64) + len(prog.out_i64)
+        algo = 240 + 8 * diag
+        workload = 'C3: CAT-grating spectrograph, lens + scatter -> {0} CATL1L2Stack facets (Rowland torus, 135x25x28 efficiency table) -> 16 CCDs, {1:.0e} photons per step'.format(n_facets, n)
+
+        def step(k):
+            rc = lib.mxb_trace_from(blob.data_ptr(), prog.blob.size, prog.blob.ctypes.data, src, ctypes.byref(cols), n, 0,
+                                    99 + k, status.data_ptr(), stream)
+            if rc:
+                raise RuntimeError(lib.mxb_last_error().decode())
+
+        def checks():
+            return dict(on_facet=float((out['facet'] >= 0).double().mean()), on_ccd=float((out['CCD_ID'] >= 0).double().mean()),
+                        mean_order=float(torch.nanmean(out['order'])))
+    else:
+        import numpy as _np
+        from marxs_b200 import optics
+        g = dict(_np.load(os.path.join(ROOT, 'tests', 'golden', 'mlmirror.npz')))
+        refl = {'X(mm)': g['ml_x_mm'], 'Peak lambda': g['ml_peak_lambda'], 'Peak': g['ml_peak'], 'FWHM(nm)': g['ml_fwhm']}
+        polt = {'Photon energy': g['ml_pol_energy_ev'], 'Polarization': g['ml_pol']}
+        a = 2 ** -0.5
+        rot1 = _np.array([[a, 0, -a], [0, 1, 0], [a, 0, a]])
+        rot2 = _np.array([[0, 0, 1.], [a, a, 0], [-a, a, 0]])
+        elements = [optics.MultiLayerMirror(reflFile=refl, testedPolarization=polt, orientation=rot1, zoom=[1, 24.5, 12.]),
+                    optics.FlatBrewsterMirror(orientation=rot2, position=[0., 0., 30.], zoom=[1, 10., 30.]),
+                    optics.FlatDetector(pixsize=0.05, position=[0., 50., 30.],
+                                        orientation=_np.array([[0, -1., 0], [1., 0, 0], [0, 0, 1.]]), zoom=[1, 20., 20.])]
+        srcobj = source.LabPointSourceCone(position=[200., 0, 0], direction=[-1., 0, 0], half_opening=0.02, flux=float(n), energy=0.31)
+        holder = [None]
+        workload = 'C4: multilayer-mirror polarimeter, {0:.0e} photons per step BORN on the device (LabPointSourceCone -> MultiLayerMirror -> FlatBrewsterMirror -> FlatDetector)'.format(n)
+
+        def step(k):
+            holder[0] = source.observe(srcobj, None, elements, 1., device=device, check=False, out=holder[0])
+        step(0)
+        out = holder[0]
+        algo = 120 + 8 * (len(out.colnames) - 5)       # born: the record is only written
+
+        def checks():
+            o = holder[0]
+            return dict(on_detector=float(torch.isfinite(o['det_x']).double().mean()),
+                        mean_probability_detected=float(o['probability'][torch.isfinite(o['det_x'])].mean()))
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    ev0.record()
+    for k in range(K):
+        ka[k].record()
+        step(W + k)
+        kb[k].record()
+    ev1.record()
+    torch.cuda.synchronize(device)
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([x.elapsed_time(y) for x, y in zip(ka, kb)]))
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = algo * n / (kern_ms * 1e-3) / 1e9
+    line = dict(metric=METRIC, value=n * K / (total_ms * 1e-3), unit='photons/s', n_gpus=1, steps=K, warmup=W,
+                ms_per_step=total_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload=workload, photons_per_gpu_per_step=n, rng='device Philox4x32-10',
+                            l2='every step streams far more than the 126 MB L2', build=lib.mxb_build_info().decode()),
+                roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                              frac_of_nominal_8tbs=achieved / 8000., traffic=None, peak_source=peak_src, kernel_ms=kern_ms,
+                              algorithmic_bytes_per_photon=algo, kernel='mxb_jit_kernel (program-specialised, NVRTC sm_100a)'),
+                clocks=clocks, e2e=None, gpu_launches=K, kernel_path=lib.mxb_jit_info().decode(), checks=checks())
+    print(json.dumps(line), flush=True)
+
+
 C5_EVENT_COLS = ['energy', 'order', 'CCD_ID', 'chipx', 'chipy', 'probability']
 
 
@@ -705,7 +807,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--verify', type=int, default=100000,
                     help='photons of the timed batch checked against the CPU oracle with the exported Philox draws (0: off)')
-    ap.add_argument('--config', default='c2', choices=['c2', 'c5'], help='c2: the headline (default); c5: the sharded observation')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c3', 'c4', 'c5'],
+                    help='c2: the headline (default); c3 / c4: the other full-size configurations (one GPU); c5: the sharded observation')
     ap.add_argument('--c5-photons', type=float, default=1e9, help='photons of the whole observation (config c5)')
     ap.add_argument('--c5-batch', type=float, default=2.5e7, help='photons per launch within a shard (config c5)')
     ap.add_argument('--no-image', action='store_true', help='experiment: do not fuse the detector image')
@@ -717,6 +820,10 @@ def main():
         run_reference(args)
     elif args.config == 'c5':
         run_c5(args)
+    elif args.config in ('c3', 'c4'):
+        if args.steps == 200:
+            args.steps = 10
+        run_other(args)
     else:
         run_engine(args)
 
