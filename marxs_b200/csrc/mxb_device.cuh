@@ -104,6 +104,14 @@ MXB_DEV V3 normalize(const V3& a) {
 
 // sin and cos; the fast build uses the Taylor series for the tiny scatter angles (|x| < 2^-7:
 // truncation error x^10/10! < 1e-28), libm otherwise
+#ifdef MXB_FAST
+// libm sincos for the (rare) large scatter angle: one out-of-line copy instead of ~110 inlined instructions per site
+__device__ __noinline__ double2 sincos_large(double x) {
+    double s, c;
+    m_sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+#endif
 MXB_DEV void sincos_small(double x, double* s, double* c) {
 #ifdef MXB_FAST
     if (fabs(x) < 0.0078125) {
@@ -114,8 +122,12 @@ MXB_DEV void sincos_small(double x, double* s, double* c) {
                                  4.1666666666666664e-02), -0.5), 1.0);
         return;
     }
-#endif
+    const double2 sc = sincos_large(x);
+    *s = sc.x;
+    *c = sc.y;
+#else
     m_sincos(x, s, c);
+#endif
 }
 
 MXB_DEV double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }  // NaN propagates like np.clip
@@ -256,6 +268,22 @@ MXB_DEV double u01_from_bits(uint32_t hi, uint32_t lo) {
     return (double)(b >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
 }
 
+// Box-Muller in fp64 (libm log / sincos).  In the fast build this is the EXTREME TAIL only (1 - u < 2^-20, one draw
+// in a million), so it is one out-of-line routine: inlined at every draw site it was ~270 instructions of code per
+// site that practically never run (instruction-cache pressure of large fused programs).  The strict build uses it
+// for every normal and keeps it inline.
+#ifdef MXB_FAST
+__device__ __noinline__
+#else
+MXB_DEV
+#endif
+double2 box_muller_f64(double v, double u2) {     // by value: no address of a caller's variable escapes
+    const double rad = sqrt(-2.0 * m_log(v));
+    double s, c;
+    m_sincos(kTwoPi * u2, &s, &c);
+    return make_double2(rad * c, rad * s);
+}
+
 // kind 0: uniform [0,1); kind 1: standard normal (Box-Muller; the fast build evaluates it with the fp32
 // SFU intrinsics like device_draw_normal_pair below, the extreme tail and the strict build in fp64)
 MXB_DEV double device_draw(uint64_t seed, uint64_t photon_id, int slot, int kind) {
@@ -272,9 +300,7 @@ MXB_DEV double device_draw(uint64_t seed, uint64_t photon_id, int slot, int kind
         return (double)(rad * __cosf(6.2831853f * ((float)u2 - 0.5f)));
     }
 #endif
-    double s, c;
-    m_sincos(kTwoPi * u2, &s, &c);
-    return sqrt(-2.0 * m_log(v)) * c;
+    return box_muller_f64(v, u2).x;
 }
 
 // two independent standard normals from ONE Philox call (both Box-Muller branches).
@@ -298,11 +324,9 @@ MXB_DEV void device_draw_normal_pair(uint64_t seed, uint64_t photon_id, int slot
         return;
     }
 #endif
-    const double rad = sqrt(-2.0 * m_log(v));
-    double s, c;
-    m_sincos(kTwoPi * u2, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+    const double2 z = box_muller_f64(v, u2);
+    z0 = z.x;
+    z1 = z.y;
 }
 
 }  // namespace mxb

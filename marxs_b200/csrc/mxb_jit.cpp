@@ -714,10 +714,19 @@ struct Gen {
         }
         out("        photon_loaded(ph);");
         out("#if JIT_PREFETCH && !%d", born ? 1 : 0);
+#if 1
+        out("#if JIT_PREFETCH == 2");
+        out("        // next group's inputs -> L2 while this one is traced: the 32 photons of a warp are 256 B = two 128-byte");
+        out("        // lines of each of the 11 planes; lane l < 22 fetches line (l & 1) of plane (l >> 1): ONE instruction");
+        out("        if (base + stride < n_ph && lane < 2 * MXB_IN_PLANES)");
+        out("            asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.in[lane >> 1] + base + stride + ((lane & 1) << 4)));");
+        out("#else");
+#endif
         out("        if (i + stride < n_ph) {   // next group's inputs -> L2 while this one is traced");
         out("#pragma unroll");
         out("            for (int k = 0; k < MXB_IN_PLANES; ++k) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(P.in[k] + i + stride));");
         out("        }");
+        out("#endif");
         out("#endif");
         out("        ph.ip = V3{kNaN, kNaN, kNaN};");
         out("        ph.l0 = ph.l1 = kNaN;");

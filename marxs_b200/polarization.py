@@ -1,6 +1,8 @@
 """Polarization vectors and parallel transport on the device (reference math/polarization.py)."""
 import ctypes
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -53,24 +55,47 @@ def polarization_vectors(dir_array, angles):
 
 
 def paralleltransport_matrix(dir1, dir2, jones=None, replace_nans=True):
-    """(n, 3, 3) parallel-transport ray matrices (reference math/polarization.py:90-149) for the identity
-    Jones matrix: column k is the transported unit vector e_k, three launches of the transport kernel.
-    ``replace_nans=True`` (identity where dir1 is parallel to dir2) is the only mode; other Jones matrices are
-    not implemented (no element of the reference's hot path uses them)."""
-    if jones is not None and not torch.equal(torch.as_tensor(jones, dtype=torch.float64), torch.eye(2, dtype=torch.float64)):
-        raise NotImplementedError('paralleltransport_matrix: only the identity Jones matrix')
-    if not replace_nans:
-        raise NotImplementedError('paralleltransport_matrix: replace_nans=False')
-    n = dir1.shape[0]
+    """(n, 3, 3) parallel-transport ray matrices (reference math/polarization.py:90-149).
 
-    def h(v):      # (n, 3) or (n, 4) -> (n, 4) with w = 0
-        if v.shape[1] == 4:
-            return v
-        return torch.cat([v, torch.zeros((n, 1), dtype=v.dtype, device=v.device)], dim=1)
-    d1, d2 = h(dir1), h(dir2)
-    cols = []
-    for k in range(3):
-        e = torch.zeros((n, 4), dtype=torch.float64, device=d1.device)
-        e[:, k] = 1.
-        cols.append(parallel_transport(d1, d2, e)[:, :3])
-    return torch.stack(cols, dim=2)
+    Identity Jones matrix (the default, and what every element of the hot path uses): column k is the transported
+    unit vector e_k - three launches of the transport kernel, consistent with ``parallel_transport`` bit for bit.
+    Any other 2 x 2 ``jones`` matrix (local s, p system of the element): P = O_out . diag(jones, 1) . O_in^-1 with
+    O_in rows (s, p_in, dir1) and O_out columns (s, p_out, dir2), s = dir1 x dir2 normalised, evaluated with tensor
+    operations on the device of the inputs.  Rays with dir1 parallel to dir2 (|dir1 x dir2| <= 1e-8, np.isclose)
+    get the identity, or NaN with ``replace_nans=False``."""
+    n = dir1.shape[0]
+    identity = jones is None or torch.equal(torch.as_tensor(jones, dtype=torch.float64).cpu(), torch.eye(2, dtype=torch.float64))
+    if not isinstance(dir1, torch.Tensor):
+        dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+        dir1 = torch.as_tensor(np.asarray(dir1, dtype=float), device=dev)
+        dir2 = torch.as_tensor(np.asarray(dir2, dtype=float), device=dev)
+    d1 = dir1.as_subclass(torch.Tensor)[:, :3].to(torch.float64)
+    d2 = dir2.as_subclass(torch.Tensor)[:, :3].to(torch.float64)
+    d1 = d1 / d1.norm(dim=1, keepdim=True)
+    d2 = d2 / d2.norm(dim=1, keepdim=True)
+    s = torch.linalg.cross(d1, d2)
+    s_norm = s.norm(dim=1)
+    same = s_norm.abs() <= 1e-8                      # np.isclose(s_norm, 0)
+    if identity and d1.device.type == 'cuda':
+        def h(v):
+            return torch.cat([v, torch.zeros((n, 1), dtype=v.dtype, device=v.device)], dim=1)
+        cols = []
+        for k in range(3):
+            e = torch.zeros((n, 4), dtype=torch.float64, device=d1.device)
+            e[:, k] = 1.
+            cols.append(parallel_transport(h(d1), h(d2), e)[:, :3])
+        pmat = torch.stack(cols, dim=2)
+    else:
+        j3 = torch.eye(3, dtype=torch.float64, device=d1.device)
+        if jones is not None:
+            j3[:2, :2] = torch.as_tensor(np.asarray(jones, dtype=float) if not isinstance(jones, torch.Tensor) else jones,
+                                         dtype=torch.float64, device=d1.device)
+        su = s / torch.where(same, torch.ones_like(s_norm), s_norm)[:, None]
+        p_in = torch.linalg.cross(d1, su)
+        p_out = torch.linalg.cross(d2, su)
+        o_in = torch.stack([su, p_in, d1], dim=1)          # rows
+        o_out = torch.stack([su, p_out, d2], dim=2)        # columns
+        pmat = o_out @ (j3 @ o_in)
+    fill = torch.eye(3, dtype=torch.float64, device=d1.device) * (1. if replace_nans else float('nan'))
+    pmat = torch.where(same[:, None, None], fill[None], pmat)
+    return pmat

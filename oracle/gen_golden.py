@@ -642,6 +642,19 @@ def case_euklid_bases(marxs, rng):
     save('euklid_bases', **arrays)
 
 
+def case_pt_matrix(marxs, rng):
+    """paralleltransport_matrix (math/polarization.py:90-149) with the identity and a general Jones matrix."""
+    from marxs.math.polarization import paralleltransport_matrix
+    n = 40
+    d1 = rng.normal(size=(n, 3))
+    d2 = d1 + rng.normal(scale=0.3, size=(n, 3))
+    d2[:5] = d1[:5] * rng.uniform(0.5, 2., 5)[:, None]          # parallel: the undefined case
+    jones = np.array([[0.8, 0.1], [-0.2, 0.5]])
+    save('pt_matrix', d1=d1, d2=d2, jones=jones,
+         ident=paralleltransport_matrix(d1, d2), ident_nan=paralleltransport_matrix(d1, d2, replace_nans=False),
+         gen=paralleltransport_matrix(d1, d2, jones=jones), gen_nan=paralleltransport_matrix(d1, d2, jones=jones, replace_nans=False))
+
+
 class SeqFeeder:
     """Replace np.random.uniform / rand for code that draws outside any optical element (sources):
     the k-th call returns low + (high - low) * table[k]."""
@@ -932,7 +945,7 @@ def main():
                               case_order_selectors, case_lens_scatter, case_detectors,
                               case_mlmirror, case_apertures_baffle, case_chandra,
                               case_parallel_overlap, case_cat_stack, case_cylinder, case_sources, case_rowland, case_tolerancing,
-                              case_lens_reflectivity, case_grating_callable_d, case_scatter_callable, case_euklid_bases]):
+                              case_lens_reflectivity, case_grating_callable_d, case_scatter_callable, case_euklid_bases, case_pt_matrix]):
         rng = np.random.Generator(np.random.PCG64(SEED + i))
         if only and case.__name__ not in only:
             continue

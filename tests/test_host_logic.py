@@ -595,3 +595,19 @@ def test_get_local_euklid_bases_golden():
     e_phi, e_z, e_n = geo.get_local_euklid_bases(np.column_stack([np.linspace(-3, 3, 7), np.zeros(7)]))
     assert np.allclose(np.einsum('ij,ij->i', e_phi, e_n), 0.) and np.allclose(np.einsum('ij,ij->i', e_phi, e_z), 0.)
     assert np.allclose(np.linalg.norm(e_n, axis=1), 1.)
+
+
+def test_paralleltransport_matrix_golden():
+    """paralleltransport_matrix incl. a general Jones matrix and replace_nans=False against the unmodified
+    reference (tests/golden/pt_matrix.npz; reference math/polarization.py:90-149, tests test_polarization.py:40-72)."""
+    import os
+    import torch
+    from marxs_b200 import polarization
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'pt_matrix.npz')))
+    d1, d2 = torch.as_tensor(g['d1']), torch.as_tensor(g['d2'])
+    for key, kw in (('ident', {}), ('ident_nan', {'replace_nans': False}), ('gen', {'jones': g['jones']}),
+                    ('gen_nan', {'jones': g['jones'], 'replace_nans': False})):
+        got = polarization.paralleltransport_matrix(d1, d2, **kw).numpy()
+        assert got.shape == (40, 3, 3)
+        np.testing.assert_allclose(got, g[key], rtol=1e-12, atol=1e-13, equal_nan=True, err_msg=key)
+    assert np.isnan(g['ident_nan'][:5]).all() and np.array_equal(g['ident'][:5], np.tile(np.eye(3), (5, 1, 1)))

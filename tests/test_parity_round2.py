@@ -416,3 +416,16 @@ def test_scalar_process_photon_hook(mode):
             return dir, pos, energy, polarization, 1.5, 0., 0.
     with pytest.raises(ValueError):
         Bad(pos4d=pos4d)(mb.PhotonBatch(table, device='cuda'))
+
+
+def test_paralleltransport_matrix_jones_gpu():
+    """General Jones matrix / replace_nans=False on device tensors against the reference golden; the identity case
+    (transport kernel) agrees with the golden as well."""
+    from test_parity_gpu import load
+    from marxs_b200 import polarization
+    g = load('pt_matrix')
+    d1, d2 = torch.as_tensor(g['d1'], device='cuda'), torch.as_tensor(g['d2'], device='cuda')
+    for key, kw in (('ident', {}), ('ident_nan', {'replace_nans': False}), ('gen', {'jones': g['jones']}),
+                    ('gen_nan', {'jones': g['jones'], 'replace_nans': False})):
+        got = polarization.paralleltransport_matrix(d1, d2, **kw).cpu().numpy()
+        np.testing.assert_allclose(got, g[key], rtol=1e-12, atol=1e-13, equal_nan=True, err_msg=key)
