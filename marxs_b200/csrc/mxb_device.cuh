@@ -201,10 +201,14 @@ MXB_DEV_BIG V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3
 }
 
 // math/rotations.py:50-87 axangle2mat applied TRANSPOSED (scatter.py:60,68)
+// ANY_ANGLE: the angle is a full-circle quantity (2 pi u): libm sincos inline; otherwise it is a scatter angle,
+// tiny in practice (Taylor series in the fast build, libm out of line for the rare large one)
+template <bool ANY_ANGLE = false>
 MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
     const V3 a = normalize(axis);  // axes / np.linalg.norm(axes): true division in strict build
     double s, c;
-    sincos_small(angle, &s, &c);
+    if (ANY_ANGLE) m_sincos(angle, &s, &c);
+    else sincos_small(angle, &s, &c);
     const double C = 1 - c;
     const double x = a.x, y = a.y, z = a.z;
     const double xs = x * s, ys = y * s, zs = z * s;

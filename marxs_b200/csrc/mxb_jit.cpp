@@ -612,7 +612,7 @@ struct Gen {
         out("using namespace mxb;");
         out("#ifndef JIT_THREADS\n#define JIT_THREADS 640\n#endif");
         out("#ifndef JIT_MINBLOCKS\n#define JIT_MINBLOCKS 1\n#endif");
-        out("#ifndef JIT_PREFETCH\n#define JIT_PREFETCH 1\n#endif");
+        out("#ifndef JIT_PREFETCH\n#define JIT_PREFETCH 2\n#endif");
         // photon index type: launches are sliced below 2^31 photons (mxbjit::launch), so plane addresses are one
         // IMAD.WIDE.U32 off the pointer in the constant bank instead of 64-bit shift/add chains
         out("#ifndef JIT_IDX32\n#define JIT_IDX32 %d\n#endif", idx64 ? 0 : 1);
@@ -916,7 +916,7 @@ int compile(const std::string& source, bool fast_build, const std::string& hash,
     opts.push_back("-DJIT_THREADS=" + std::to_string(threads));
     opts.push_back("--ptxas-options=-v");
     opts.push_back("-DJIT_MINBLOCKS=" + std::to_string(env_int("MXB_JIT_MINBLOCKS", 1)));
-    opts.push_back("-DJIT_PREFETCH=" + std::to_string(env_int("MXB_JIT_PREFETCH", 1)));
+    opts.push_back("-DJIT_PREFETCH=" + std::to_string(env_int("MXB_JIT_PREFETCH", 2)));
     if (const char* extra = getenv("MXB_JIT_DEFINES")) {      // experiments: space separated -D options
         std::string e(extra);
         size_t pos = 0;
@@ -961,7 +961,7 @@ std::string options_tag(bool fast_build) {
     char b[160];
     snprintf(b, sizeof(b), "%s t%d b%d r%d p%d f%d g%d", fast_build ? "fast" : "strict", env_int("MXB_JIT_THREADS", 0),
              env_int("MXB_JIT_MINBLOCKS", 1), env_int("MXB_JIT_MAXREG", 0), env_int("MXB_JIT_PIPE", 0),
-             env_int("MXB_JIT_PREFETCH", 1), env_int("MXB_JIT_GROW", 1));
+             env_int("MXB_JIT_PREFETCH", 2), env_int("MXB_JIT_GROW", 1));
     std::string tag(b);
     if (const char* extra = getenv("MXB_JIT_DEFINES")) tag += std::string(" ") + extra;
     return tag;

@@ -334,7 +334,7 @@ MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, doubl
     }
     V3 out = axangle_rotate_T(perp, ang, pdir);
     const double ang2 = u * 2 * 3.141592653589793;
-    out = axangle_rotate_T(pdir, ang2, out);
+    out = axangle_rotate_T<true>(pdir, ang2, out);
     ph.pol = parallel_transport(kTrackUnit ? pdir : ph.dir, out, ph.pol, kTrackUnit, true);
     ph.dir = out;
     ph.unit = true;
