@@ -368,6 +368,34 @@ def verify_against_oracle(prog, base, out, m, seed, id0, device):
     return res
 
 
+def element_api_block(inst, base, out, device, reps=10):
+    """ms per 1e7-photon step of (a) instrument(photons) on a resident table (reference semantics: in place; the
+    program is found in the plan cache under a digest of the element tree), (b) simulator.trace_from(instrument,
+    source, out) (out of place, same digest), (c) a CompiledInstrument (no digest): wall clock around a synchronised
+    call, i.e. kernel + all host work."""
+    import torch
+    from marxs_b200 import simulator
+
+    def timed(f):
+        f()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        torch.cuda.synchronize(device)
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    run = simulator.compile_instrument(inst, base)
+    res = dict(
+        copy_ms=timed(lambda: base.copy()),
+        copy_and_call_ms=timed(lambda: inst(base.copy())),
+        trace_from_ms=timed(lambda: simulator.trace_from(inst, base, out=out, check=False)),
+        compiled_trace_from_ms=timed(lambda: run.trace_from(base, out, check=False)),
+        note='wall clock per step of 1e7 resident photons incl. host work: instrument(photons.copy()) (and the copy alone) / simulator.trace_from / '
+             'CompiledInstrument.trace_from; `value` is the C-ABI call these end in')
+    return res
+
+
 def run_engine(args):
     import ctypes
     import torch
@@ -460,6 +488,12 @@ def run_engine(args):
     if rank == 0 and args.verify > 0:
         verify = verify_against_oracle(prog, base, out0, min(args.verify, n), 1234 + W + K - 1, rank * n, device)
 
+    # ---- the same step through the Python element API (what a user of the reference types), outside the timed region:
+    # `value` above calls the C ABI directly; this is the host-side price of the drop-in classes per call
+    element_api = None
+    if rank == 0 and not args.no_api:
+        element_api = element_api_block(inst, base, out0, device)
+
     # ---- end to end through the host-buffer C ABI (rank-local pinned tables) ----
     e2e = None
     if not args.no_e2e:
@@ -524,7 +558,7 @@ def run_engine(args):
                               kernel_ms=kern_ms, algorithmic_bytes_per_photon=ALGO_BYTES_PER_PHOTON,
                               note='one launch traces all photons of the step; limited by dependent fp64 issue latency at '
                                    '5 warps/SMSP (see DESIGN.md section 4), not by HBM'),
-                clocks=clocks, e2e=e2e, gpu_launches=K, kernel_path=kernel_path, collective_ms=collective_ms,
+                clocks=clocks, e2e=e2e, element_api=element_api, gpu_launches=K, kernel_path=kernel_path, collective_ms=collective_ms,
                 collective=('ncclAllReduce fp64 sum of the 6x1024x1024 detector image ({0:.1f} MB), once after the {1} steps, '
                             'warmed at size before the timed region'.format(image.numel() * 8 / 1e6, K) if world > 1
                             else 'none (1 GPU)'),
@@ -805,6 +839,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-api', action='store_true', help='skip the element-API timing block')
     ap.add_argument('--verify', type=int, default=100000,
                     help='photons of the timed batch checked against the CPU oracle with the exported Philox draws (0: off)')
     ap.add_argument('--config', default='c2', choices=['c2', 'c3', 'c4', 'c5'],

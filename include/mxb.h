@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MXB_ABI_VERSION 11
+#define MXB_ABI_VERSION 12
 
 /* ---- error codes ------------------------------------------------------ */
 #define MXB_OK            0
@@ -130,7 +130,7 @@ typedef struct MxbColumns {
 #define MXB_OP_GFILTER     17  /* filter.py:48-53 GlobalEnergyFilter (all photons); params as FILTER                                 */
 #define MXB_OP_LOADHIT     18  /* process_photons(photons, intersect, interpos, intercoos) with an EXTERNAL intersect:
                                   c0 hit (0/1 as f64) c1..c3 interpos c4,c5 intercoos columns; pg: geom[14]                        */
-#define MXB_OP_QFACTOR     19  /* mitsnl/catgrating.py:147-161 QualityFactor: params factor ; probability *= factor ** order**2
+#define MXB_OP_QFACTOR     19  /* mitsnl/catgrating.py:147-161 QualityFactor: params factor, log(factor) hi, lo ; probability *= factor ** order**2
                                   with the order drawn by the preceding GRATING op of the same stack                             */
 #define MXB_OP_L2ABS       20  /* mitsnl/catgrating.py:222-259 L2Abs: params openfraction, bardepth*innerfree, totalarea         */
 #define MXB_OP_CYLINDER    21  /* math/geometry.py:470-564 Cylinder.intersect: pg: inv(pos4d)[16] pos4d[16] (row major)
@@ -250,6 +250,22 @@ int mxb_trace_host_opts(const double* prog_host, size_t prog_words, const MxbCol
  * ((r0 << 32 | r1) >> 11) * 2^-53.  Device pointers; asynchronous on `stream`. */
 int mxb_debug_draws(uint64_t seed, int64_t photon_id0, int64_t n, int slot, int kind, double* out0, double* out1,
                     void* stream);
+
+/* The device math routines of this build (the fast build replaces libm's acos / asin / pow by its own: see
+ * csrc/mxb_device.cuh), exported for verification against numpy.  kind 0: arccos(x)  1: arcsin(x)
+ * 2: x ** y as QualityFactor uses it (mitsnl/catgrating.py:147-161, y = order^2; x is ONE number for the call and
+ *    log_hi + log_lo its natural logarithm as a double-double, the parameters the host lowers)  3: x / y
+ * 4 / 5: sin(x) / cos(x) of the scatter rotations (math/rotations.py:50-87)  6 / 7: sin / cos of x turns, the
+ * uniform azimuth x * 2 * pi of RandomGaussianScatter (optics/scatter.py:135-137).  Device pointers. */
+int mxb_debug_math(int kind, const double* x, const double* y, double* out, int64_t n, double log_hi, double log_lo, void* stream);
+
+/* sigma_clipped_stats of a device column (reference marxs/analysis/analysis.py:9-25 -> astropy.stats.sigma_clipped_stats
+ * with its defaults: median centre, std width, non-finite values masked, at most `maxiters` clipping rounds at
+ * `sigma` standard deviations): out4 (device) = mean, median, std, number of surviving values (NaN, NaN, NaN, 0 when
+ * nothing survives).  Streaming passes over x only (exact radix-select median, no sort, no copy); the whole iteration
+ * is enqueued on `stream` without a host round trip.  workspace: mxb_sigma_clip_workspace() device bytes. */
+size_t mxb_sigma_clip_workspace(void);
+int mxb_sigma_clip_stats(const double* x, int64_t n, double sigma, int maxiters, double* out4, void* workspace, void* stream);
 
 /* Geometry.intersect for one plane (math/geometry.py:211-261; circular != 0 adds :376-380).
  * geom: 14 host doubles (c, e_x, e_y, e_z, |v_y|, |v_z|).  dir/pos: 3 device planes each.

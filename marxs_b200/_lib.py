@@ -8,7 +8,7 @@ build (``libmxb.so``: FMA contraction, reciprocal normalisation).
 import ctypes
 import os
 
-MXB_ABI_VERSION = 11
+MXB_ABI_VERSION = 12
 MXB_MAX_F64_COLS = 56
 MXB_MAX_I64_COLS = 8
 MXB_MAX_SLOTS = 16
@@ -76,6 +76,12 @@ def load(strict=None):
                                         ctypes.POINTER(MxbHostOptions)]
     lib.mxb_debug_draws.restype = ci
     lib.mxb_debug_draws.argtypes = [u64, i64, i64, ci, ci, vp, vp, vp]
+    lib.mxb_sigma_clip_workspace.restype = ctypes.c_size_t
+    lib.mxb_sigma_clip_workspace.argtypes = []
+    lib.mxb_sigma_clip_stats.restype = ci
+    lib.mxb_sigma_clip_stats.argtypes = [vp, i64, ctypes.c_double, ci, vp, vp, vp]
+    lib.mxb_debug_math.restype = ci
+    lib.mxb_debug_math.argtypes = [ci, vp, vp, vp, i64, ctypes.c_double, ctypes.c_double, vp]
     lib.mxb_plane_intersect.restype = ci
     lib.mxb_plane_intersect.argtypes = [vp, ci, vp, vp, vp, vp, vp, i64, vp]
     lib.mxb_parallel_transport.restype = ci
@@ -121,5 +127,5 @@ def check(lib, rc, what):
 
 
 EXPORTED_SYMBOLS = ['mxb_version', 'mxb_build_info', 'mxb_last_error', 'mxb_device_count', 'mxb_host_release', 'mxb_trace',
-                    'mxb_trace_from', 'mxb_trace_host', 'mxb_trace_host_opts', 'mxb_debug_draws', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
+                    'mxb_trace_from', 'mxb_trace_host', 'mxb_trace_host_opts', 'mxb_debug_draws', 'mxb_debug_math', 'mxb_sigma_clip_workspace', 'mxb_sigma_clip_stats', 'mxb_plane_intersect', 'mxb_parallel_transport', 'mxb_polarization_vectors', 'mxb_hist2d',
                     'mxb_set_jit', 'mxb_get_jit', 'mxb_jit_info', 'mxb_jit_source', 'mxb_jit_compile', 'mxb_compact_workspace', 'mxb_compact_events', 'mxb_compact_append']

@@ -1,7 +1,8 @@
 """Analysis helpers that drive the trace path (reference marxs/analysis/analysis.py:9-111,
 analysis/gratings.py:26-132) - SURVEY 8(f) rank 4: the heaviest CALLERS of the hot path.
 
-Everything stays on the device: the reductions are torch reductions over photon columns, and every
+Everything stays on the device: sigma clipping is a kernel (csrc/mxb_stats.cu), the other reductions are torch
+reductions over photon columns, and every
 trial detector of ``find_best_detector_position`` is one out-of-place launch of the trace kernel on
 the resident photon list (``simulator.trace_from`` into a reused work table; the kernel specialised
 for "one flat detector" is compiled once because detector positions are parameters, not structure).
@@ -31,25 +32,26 @@ def _column(photons, colname):
 
 def sigma_clipped_stats(data, sigma=3.0, maxiters=5):
     """(mean, median, std) after iterative clipping at ``sigma`` standard deviations around the median
-    (astropy.stats.sigma_clipped_stats defaults: cenfunc='median', stdfunc='std', NaN ignored)."""
-    x = torch.as_tensor(data).flatten().to(torch.float64)
-    x = x[torch.isfinite(x)]
-    for _ in range(maxiters):
-        if x.numel() == 0:
-            break
-        med = torch.median(x) if x.numel() % 2 else 0.5 * (torch.kthvalue(x, x.numel() // 2).values
-                                                           + torch.kthvalue(x, x.numel() // 2 + 1).values)
-        std = torch.std(x, unbiased=False)
-        keep = (x >= med - sigma * std) & (x <= med + sigma * std)
-        if bool(keep.all()):
-            break
-        x = x[keep]
-    if x.numel() == 0:
-        nan = float('nan')
-        return nan, nan, nan
-    n = x.numel()
-    med = torch.median(x) if n % 2 else 0.5 * (torch.kthvalue(x, n // 2).values + torch.kthvalue(x, n // 2 + 1).values)
-    return float(x.mean()), float(med), float(torch.std(x, unbiased=False))
+    (astropy.stats.sigma_clipped_stats defaults: cenfunc='median', stdfunc='std', non-finite values masked).
+
+    One call of ``mxb_sigma_clip_stats`` (csrc/mxb_stats.cu): every clipping round is a few streaming passes over the
+    resident column (count / sum, squared deviations, an exact radix-select median) - no sort, no compaction, no host
+    round trip between the rounds.  Host data is copied to the device first; there is no CPU path."""
+    from . import _lib
+    x = torch.as_tensor(data)
+    if x.device.type != 'cuda':
+        x = x.to('cuda')
+    x = x.flatten().to(torch.float64).contiguous()
+    lib = _lib.load()
+    work = torch.empty(int(lib.mxb_sigma_clip_workspace()), dtype=torch.uint8, device=x.device)
+    out = torch.empty(4, dtype=torch.float64, device=x.device)
+    iters = 100 if maxiters is None else int(maxiters)       # astropy: None = until nothing is clipped
+    with torch.cuda.device(x.device):
+        rc = lib.mxb_sigma_clip_stats(x.data_ptr(), x.numel(), float(sigma), iters, out.data_ptr(), work.data_ptr(),
+                                      torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(lib, rc, 'mxb_sigma_clip_stats')
+    mean, med, std, _ = out.tolist()
+    return mean, med, std
 
 
 def sigma_clipped_std(photons, colname='det_x', **kwargs):

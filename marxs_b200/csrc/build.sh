@@ -27,8 +27,8 @@ if old != new:
     open('mxb_embed.inc', 'w').write(new)
 PY
 COMMON="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -Xptxas -v"
-$NVCC $COMMON -DMXB_FAST -o ../libmxb.so mxb_trace.cu mxb_jit.cpp -ldl 2> build_fast.log || { cat build_fast.log; exit 1; }
-$NVCC $COMMON -fmad=false -o ../libmxb_strict.so mxb_trace.cu mxb_jit.cpp -ldl 2> build_strict.log || { cat build_strict.log; exit 1; }
+$NVCC $COMMON -DMXB_FAST -o ../libmxb.so mxb_trace.cu mxb_stats.cu mxb_jit.cpp -ldl 2> build_fast.log || { cat build_fast.log; exit 1; }
+$NVCC $COMMON -fmad=false -o ../libmxb_strict.so mxb_trace.cu mxb_stats.cu mxb_jit.cpp -ldl 2> build_strict.log || { cat build_strict.log; exit 1; }
 # (compile times would make the tracked logs change with every build)
 sed -i '/Compile time/d' build_fast.log build_strict.log
 grep -E "registers|spill|error|warning" build_fast.log build_strict.log | grep -v "^$" | head -40

@@ -12,6 +12,11 @@
 #endif
 
 #define MXB_DEV __device__ __forceinline__
+#ifdef MXB_NO_EXPECT
+#define MXB_UNLIKELY(x) (x)
+#else
+#define MXB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
 // -DMXB_SHARE_CODE turns parallel transport / Rodrigues rotation into real functions (one copy, called)
 // for very large programs; measured slower on C3 (r01: 5.9 -> 6.9 ms), so it is off by default.
 #ifdef MXB_SHARE_CODE
@@ -30,8 +35,12 @@ namespace mxb {
 #else
 #define MXB_LIBM __device__ __forceinline__     // measured: calls in the hot loop cost more than the code they save
 #endif
+#if defined(MXB_FAST) && !defined(MXB_LIBM_ASIN)
+#define MXB_OWN_ASIN 1   // m_acos / m_asin are defined below (after fast_rsqrt)
+#else
 MXB_LIBM double m_acos(double x) { return acos(x); }
 MXB_LIBM double m_asin(double x) { return asin(x); }
+#endif
 MXB_LIBM double m_sin(double x) { return sin(x); }
 MXB_LIBM double m_log(double x) { return log(x); }
 MXB_LIBM double m_exp(double x) { return exp(x); }
@@ -74,6 +83,55 @@ MXB_DEV double fast_rsqrt(double x) {   // only used in the fast build
     e = fma(-hx * r, r, 0.5);
     return fma(r, e, r);
 }
+// sqrt of a finite z >= 0 from the Newton rsqrt (0 -> 0; negative or NaN -> NaN), faithful: the IEEE sqrt sequence of
+// the compiler carries a slow path for denormals / infinities at every site
+MXB_DEV double sqrt_nn(double z) {
+    const double r = fast_rsqrt(z);
+    double s = z * r;
+    s = fma(fma(-s, s, z), 0.5 * r, s);
+    return (z == 0.0) ? 0.0 : s;
+}
+MXB_DEV double m_sqrt(double x) {     // strict build: IEEE (bit parity with np.sqrt)
+#if defined(MXB_FAST) && !defined(MXB_IEEE_SQRT)
+    return sqrt_nn(x);
+#else
+    return sqrt(x);
+#endif
+}
+#ifdef MXB_OWN_ASIN
+// asin / acos of the fast build.  libm's versions are 65 instructions per site, a third of them MOVs that build
+// polynomial coefficients; here the coefficients sit in the constant bank and the large-argument branch uses the
+// Newton rsqrt above.  asin(s) = s + s z P(z), z = s^2 <= 1/4, P = degree-11 interpolant of (asin(s) - s) / s^3 at
+// the Chebyshev nodes of [0, 1/4] (fitted at 60 digits with mpmath, tools/fit_asin.py; <= 1.5 ulp);
+// |x| > 1/2: asin(|x|) = pi/2 - 2 asin(sqrt((1 - |x|) / 2)) (fdlibm's reduction).  Errors <= 2.5 ulp.
+__constant__ double kAsinP[12] = {0.1666666666666665, 0.07500000000020764, 0.044642857103423646, 0.03038194736709848,
+                                  0.02237204763174451, 0.017355259955786323, 0.013929652902326633, 0.011875494382636922,
+                                  0.0078029494773533175, 0.01603551434914882, -0.010749050339697808, 0.028169218060881414};
+MXB_DEV double asin_poly(double s, double z) {
+    double p = kAsinP[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) p = fma(p, z, kAsinP[k]);
+    return fma(s * z, p, s);
+}
+MXB_DEV double m_acos(double x) {
+    const double ax = fabs(x);
+    if (ax > 0.5) {
+        const double z = (1.0 - ax) * 0.5;          // exact; negative for |x| > 1 -> NaN like np.arccos
+        const double r = 2.0 * asin_poly(sqrt_nn(z), z);
+        return (x < 0.0) ? (3.141592653589793116 - r) + 1.2246467991473532e-16 : r;
+    }
+    return 1.5707963267948966 - (asin_poly(x, x * x) - 6.123233995736766e-17);   // NaN propagates
+}
+MXB_DEV double m_asin(double x) {
+    const double ax = fabs(x);
+    if (ax > 0.5) {
+        const double z = (1.0 - ax) * 0.5;
+        const double r = 1.5707963267948966 - (2.0 * asin_poly(sqrt_nn(z), z) - 6.123233995736766e-17);
+        return (x < 0.0) ? -r : r;
+    }
+    return asin_poly(x, x * x);
+}
+#endif
 MXB_DEV double div(double a, double b) {
 #ifdef MXB_FAST
     const double r = fast_rcp(b);
@@ -112,14 +170,26 @@ __device__ __noinline__ double2 sincos_large(double x) {
     return make_double2(s, c);
 }
 #endif
+#ifdef MXB_FAST
+// polynomial coefficients live in the constant bank (DFMA reads c[3][..] directly): a double literal costs two
+// MOV instructions at every use, which is 15 % of the instruction stream of a large fused program
+__constant__ double kSinT[4] = {2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03,
+                                -1.6666666666666666e-01};
+__constant__ double kCosT[3] = {2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02};
+#endif
 MXB_DEV void sincos_small(double x, double* s, double* c) {
 #ifdef MXB_FAST
     if (fabs(x) < 0.0078125) {
         const double x2 = x * x;
+#ifndef MXB_NO_CONST_TABLES
+        *s = x * fma(x2, fma(x2, fma(x2, fma(x2, kSinT[0], kSinT[1]), kSinT[2]), kSinT[3]), 1.0);
+        *c = fma(x2, fma(x2, fma(x2, fma(x2, kCosT[0], kCosT[1]), kCosT[2]), -0.5), 1.0);
+#else
         *s = x * fma(x2, fma(x2, fma(x2, fma(x2, 2.7557319223985893e-06, -1.9841269841269841e-04),
                                      8.3333333333333332e-03), -1.6666666666666666e-01), 1.0);
         *c = fma(x2, fma(x2, fma(x2, fma(x2, 2.4801587301587302e-05, -1.3888888888888889e-03),
                                  4.1666666666666664e-02), -0.5), 1.0);
+#endif
         return;
     }
     const double2 sc = sincos_large(x);
@@ -160,6 +230,25 @@ MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V
     return hit;
 }
 
+// Division-free form of the same test for SEARCHES that only need to know whether a facet is hit (the steep-ray
+// footprint scan): with pc = c - pos, k = (pc.ex) / (dir.ex) and l = (k dir - pc).e = ((pc.ex)(dir.e) - (pc.e)(dir.ex)) / (dir.ex)
+// the conditions k >= 0, |l0| <= Ly, |l1| <= Lz become sign and magnitude tests on products.  The bounds are inflated
+// by 1e-12 so that rounding can never reject a facet the exact test accepts; callers confirm a hit with
+// plane_intersect (which also yields ip / l0 / l1) and go on searching when it disagrees.
+template <typename P>
+MXB_DEV bool plane_maybe_hit(P g, const V3& pos, const V3& dir) {
+    const double2 g01 = g.ld2(0), g23 = g.ld2(1), g45 = g.ld2(2), g67 = g.ld2(3), g89 = g.ld2(4),
+                  gab = g.ld2(5), gcd = g.ld2(6);
+    const double px = g01.x - pos.x, py = g01.y - pos.y, pz = g23.x - pos.z;
+    const double kn = px * g23.y + py * g45.x + pz * g45.y;
+    const double kd = dir.x * g23.y + dir.y * g45.x + dir.z * g45.y;
+    const double a0 = px * g67.x + py * g67.y + pz * g89.x, b0 = dir.x * g67.x + dir.y * g67.y + dir.z * g89.x;
+    const double a1 = px * g89.y + py * gab.x + pz * gab.y, b1 = dir.x * g89.y + dir.y * gab.x + dir.z * gab.y;
+    const double lim = fabs(kd) * 1.000000000001;
+    const bool fwd = (kn * kd >= 0.0) || (kn == 0.0);       // k >= 0 (k = -0 passes, like the IEEE comparison)
+    return (kd != 0.0) & fwd & (fabs(kn * b0 - a0 * kd) <= gcd.x * lim) & (fabs(kn * b1 - a1 * kd) <= gcd.y * lim);
+}
+
 // Unit-length tracking (fast build only).  The reference re-normalises directions in every
 // routine; a vector this kernel has just produced by normalisation, rotation or the grating
 // equation already has |v| = 1 to rounding, and normalising it again changes it by <= 1 ulp.  The
@@ -178,10 +267,8 @@ MXB_DEV V3 normalize_unless(bool unit, const V3& a) {
 // ---------------------------------------------------------------------------
 // math/polarization.py:90-170 parallel_transport (identity when |d1 x d2| <= 1e-8)
 // ---------------------------------------------------------------------------
-MXB_DEV_BIG V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol, bool old_unit = false,
-                                  bool new_unit = false) {
-    const V3 d1 = normalize_unless(old_unit, dir_old);
-    const V3 d2 = normalize_unless(new_unit, dir_new);
+// the reference's construction: pol in the frame {s, d1 x s, d1} re-expressed in {s, d2 x s, d2}, s = d1 x d2 / |d1 x d2|
+MXB_DEV V3 parallel_transport_frame(const V3& d1, const V3& d2, const V3& pol) {
     V3 s = cross(d1, d2);
 #ifdef MXB_FAST
     const double ns2 = dot(s, s);
@@ -199,16 +286,95 @@ MXB_DEV_BIG V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3
     return V3{s.x * a + p_out.x * b + d2.x * c, s.y * a + p_out.y * b + d2.y * c,
               s.z * a + p_out.z * b + d2.z * c};
 }
+#ifdef MXB_FAST
+// rays turned by more than ~170 degrees (cold): one out-of-line copy, arguments by value
+__device__ __noinline__ double3 parallel_transport_reversed(double3 a, double3 b, double3 p) {
+    const V3 r = parallel_transport_frame(V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z}, V3{p.x, p.y, p.z});
+    return make_double3(r.x, r.y, r.z);
+}
+#endif
+MXB_DEV_BIG V3 parallel_transport(const V3& dir_old, const V3& dir_new, const V3& pol, bool old_unit = false,
+                                  bool new_unit = false) {
+    const V3 d1 = normalize_unless(old_unit, dir_old);
+    const V3 d2 = normalize_unless(new_unit, dir_new);
+#if defined(MXB_FAST) && !defined(MXB_PT_FRAME)
+    // Fast build: the frame map is the rotation about s = d1 x d2 that takes d1 to d2.  With the UNNORMALISED
+    // a = d1 x d2 (|a| = sin t) and c = d1 . d2 Rodrigues' formula is
+    //     R p = c p + a x p + a (a . p) / (1 + c),
+    // the same map without normalising the (possibly tiny) cross product and without building the two frames:
+    // 34 instead of 50 fp64 instructions, and better conditioned than the frame form for small deflections
+    // (error ~ eps instead of eps / |a|).  Near a reversal (1 + c -> 0) it is the worse form: those rays take the
+    // frame construction.
+    const V3 a = cross(d1, d2);
+    const double ns2 = dot(a, a);
+    if (!(ns2 > 1e-16)) { if (ns2 == ns2) return pol; }   // |d1 x d2| <= 1e-8 -> identity; NaN falls through
+    const double c = dot(d1, d2);
+    if (c < -0.98) {
+        const double3 r = parallel_transport_reversed(make_double3(d1.x, d1.y, d1.z), make_double3(d2.x, d2.y, d2.z),
+                                                      make_double3(pol.x, pol.y, pol.z));
+        return V3{r.x, r.y, r.z};
+    }
+    const V3 axp = cross(a, pol);
+    const double k = dot(a, pol) * fast_rcp(1.0 + c);
+    return V3{fma(a.x, k, fma(pol.x, c, axp.x)), fma(a.y, k, fma(pol.y, c, axp.y)), fma(a.z, k, fma(pol.z, c, axp.z))};
+#else
+    return parallel_transport_frame(d1, d2, pol);
+#endif
+}
 
-// math/rotations.py:50-87 axangle2mat applied TRANSPOSED (scatter.py:60,68)
-// ANY_ANGLE: the angle is a full-circle quantity (2 pi u): libm sincos inline; otherwise it is a scatter angle,
-// tiny in practice (Taylor series in the fast build, libm out of line for the rare large one)
-template <bool ANY_ANGLE = false>
-MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
+// sin / cos of u turns, i.e. of the angle u * 2 * pi the reference forms for a uniform azimuth (scatter.py:135-137)
+#if defined(MXB_FAST) && !defined(MXB_LIBM_SINCOS)
+// (sin x - x) / x^3 and (cos x - 1 + x^2 / 2) / x^4 in z = x^2 on |x| <= pi / 4 (tools/fit_sincos.py: 1.2 / 1.7 ulp)
+__constant__ double kSinQ[6] = {-0.16666666666666666, 0.0083333333333307, -0.00019841269836387345, 2.755731591191116e-06,
+                                -2.5051092507061385e-08, 1.59153232122714e-10};
+__constant__ double kCosQ[6] = {0.041666666666666664, -0.0013888888888887241, 2.4801587298533456e-05, -2.755731715246704e-07,
+                                2.087612165887116e-09, -1.1380876948169717e-11};
+#endif
+MXB_DEV void sincos_turn(double u, double* s, double* c) {
+#if defined(MXB_FAST) && !defined(MXB_LIBM_SINCOS)
+    // quarter-turn reduction is EXACT in turns (no Cody-Waite / Payne-Hanek as for an angle in radians): 30 instead of
+    // libm's ~110 instructions per site
+    const double q = rint(4.0 * u);
+    const double r = fma(-0.25, q, u);              // |r| <= 1/8, exact
+    const double x = r * kTwoPi;
+    const double z = x * x;
+    double ps = kSinQ[5], pc = kCosQ[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        ps = fma(ps, z, kSinQ[k]);
+        pc = fma(pc, z, kCosQ[k]);
+    }
+    const double sn = fma(x * z, ps, x);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int k = (int)q;
+    const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+#else
+    m_sincos(u * 2 * 3.141592653589793, s, c);
+#endif
+}
+
+// math/rotations.py:50-87 axangle2mat applied TRANSPOSED (scatter.py:60,68), from sin / cos of the angle.
+// PERP: axis . v == 0 by construction (axis = v x something); AXIS_UNIT: |axis| == 1 already (fast build only)
+template <bool PERP = false, bool AXIS_UNIT = false>
+MXB_DEV_BIG V3 rotate_T_sc(const V3& axis, double s, double c, const V3& v) {
+#if defined(MXB_FAST) && !defined(MXB_ROT_MATRIX)
+    // Fast build: R^T v = c v - s (a x v) + (1 - c)(a . v) a with the axis normalisation folded into the
+    // coefficients: no 3x3 matrix (27-45 instead of 52 fp64 instructions)
+    {
+        const double inv = (kTrackUnit && AXIS_UNIT) ? 1.0 : fast_rsqrt(dot(axis, axis));
+        const V3 axv = cross(axis, v);
+        const double sk = -(s * inv);
+        V3 out{fma(axv.x, sk, v.x * c), fma(axv.y, sk, v.y * c), fma(axv.z, sk, v.z * c)};
+        if (!PERP) {
+            const double k = ((1.0 - c) * inv) * (inv * dot(axis, v));
+            out = V3{fma(axis.x, k, out.x), fma(axis.y, k, out.y), fma(axis.z, k, out.z)};
+        }
+        return out;
+    }
+#endif
     const V3 a = normalize(axis);  // axes / np.linalg.norm(axes): true division in strict build
-    double s, c;
-    if (ANY_ANGLE) m_sincos(angle, &s, &c);
-    else sincos_small(angle, &s, &c);
     const double C = 1 - c;
     const double x = a.x, y = a.y, z = a.z;
     const double xs = x * s, ys = y * s, zs = z * s;
@@ -219,6 +385,14 @@ MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
     const double r20 = zxC - ys, r21 = yzC + xs, r22 = z * zC + c;
     return V3{r00 * v.x + r10 * v.y + r20 * v.z, r01 * v.x + r11 * v.y + r21 * v.z,
               r02 * v.x + r12 * v.y + r22 * v.z};
+}
+// the angle is a scatter angle, tiny in practice (Taylor series in the fast build, libm out of line for the rare
+// large one)
+template <bool PERP = false, bool AXIS_UNIT = false>
+MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
+    double s, c;
+    sincos_small(angle, &s, &c);
+    return rotate_T_sc<PERP, AXIS_UNIT>(axis, s, c, v);
 }
 
 // np.interp arithmetic, clamped ends (oracle interp1d_np)
@@ -232,7 +406,7 @@ MXB_DEV double interp_clamped(P xp, P fp, int n, double x) {
         if (xp[mid] <= x) lo = mid; else hi = mid;
     }
     if (lo > n - 2) lo = n - 2;
-    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    const double slope = div(fp[lo + 1] - fp[lo], xp[lo + 1] - xp[lo]);
     return slope * (x - xp[lo]) + fp[lo];
 }
 
@@ -253,8 +427,30 @@ MXB_DEV int bracket(P xk, int n, double x) {
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = (photon id lo, hi, slot, 0)
 // ---------------------------------------------------------------------------
+#ifdef MXB_SHARE_PHILOX
+__device__ __noinline__ uint4 philox_shared(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+    uint32_t c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+#endif
 MXB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                            uint32_t k1, uint32_t out[4]) {
+#ifdef MXB_SHARE_PHILOX
+    if (c3 == 0u) {       // (always: the counter's last word is unused)
+        const uint4 r = philox_shared(c0, c1, c2, k0, k1);
+        out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+        return;
+    }
+#endif
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;

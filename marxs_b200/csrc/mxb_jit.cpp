@@ -298,13 +298,22 @@ struct Gen {
             break;
         case MXB_OP_RSCATTER: {
             const std::string p = PR(o, 5);
+            // whether a width is zero is part of the structure (a zero width skips its rotation and its draw):
+            // known at compile time for a single element, tested per photon for per-facet parameter rows
+            int nz_in = -1, nz_perp = -1;
+            if (!(in_array && o.pf >= 0) && range_ok(pr_off(o), 5)) {
+                nz_in = W[pr_off(o) + 3] != 0.0 ? 1 : 0;
+                nz_perp = W[pr_off(o) + 4] != 0.0 ? 1 : 0;
+                keyi(nz_in);
+                keyi(nz_perp);
+            }
             out("            {");
             out("            double a = 0, b = 0;");
             out("            if (ph.hit) {");
             out("                double z0, z1;");
-            out("                rscatter_draws(%s[3], %s[4], %s, %s, i, P.seed, gid, %d, %d, z0, z1);", p.c_str(), p.c_str(),
-                D(o.s0).c_str(), D(o.s1).c_str(), o.s0, o.s1);
-            out("                op_rscatter(ph, %s, z0, z1, a, b);", p.c_str());
+            out("                rscatter_draws<%d, %d>(%s[3], %s[4], %s, %s, i, P.seed, gid, %d, %d, z0, z1);", nz_in, nz_perp, p.c_str(),
+                p.c_str(), D(o.s0).c_str(), D(o.s1).c_str(), o.s0, o.s1);
+            out("                op_rscatter<%d, %d>(ph, %s, z0, z1, a, b);", nz_in, nz_perp, p.c_str());
             out("            }");
             put(o.c[0], "a");
             put(o.c[1], "b");
@@ -467,7 +476,7 @@ struct Gen {
             break;
         }
         case MXB_OP_QFACTOR:
-            out("            if (ph.hit) op_qfactor(st_sm, ph, %s);", PR(o, 1).c_str());
+            out("            if (ph.hit) op_qfactor(st_sm, ph, %s);", PR(o, 3).c_str());
             break;
         case MXB_OP_L2ABS:
             out("            if (ph.hit) op_l2abs(st_sm, ph, %s, %s);", PR(o, 3).c_str(), geom.c_str());

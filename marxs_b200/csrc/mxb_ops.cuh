@@ -166,7 +166,14 @@ MXB_DEV void st_global(long long* p, long long v) {
 // (every call site passes a constant, so the lanes that arrive here together count the same word: one
 //  shared-memory atomic per converged group instead of one per lane - steep-ray photons of a strongly
 //  dispersing array would otherwise serialise on one address)
-MXB_DEV void count_status(unsigned long long* st_sm, int which) {
+// (out of line: it is called from ~20 cold sites of a fused program, and inlined there it sits between the hot blocks;
+//  measured on C2: 0.891 -> 0.879 ms)
+#ifndef MXB_INLINE_STATUS
+__device__ __noinline__
+#else
+MXB_DEV
+#endif
+void count_status(unsigned long long* st_sm, int which) {
     const unsigned m = __activemask();
     if ((int)(threadIdx.x & 31u) == __ffs(m) - 1) atomicAdd(&st_sm[which], (unsigned long long)__popc(m));
 }
@@ -274,8 +281,8 @@ MXB_DEV void op_lens_refl(unsigned long long* st_sm, Photon& ph, PP p, const dou
     const double xq = fmin(fmax(ph.energy, xk[0]), xk[nx - 1]);
     const double yq = fmin(fmax(angle / 4, yk[0]), yk[ny - 1]);
     const int i = bracket(xk, nx, xq), j = bracket(yk, ny, yq);
-    const double tx = (xq - xk[i]) / (xk[i + 1] - xk[i]);
-    const double ty = (yq - yk[j]) / (yk[j + 1] - yk[j]);
+    const double tx = div(xq - xk[i], xk[i + 1] - xk[i]);
+    const double ty = div(yq - yk[j], yk[j + 1] - yk[j]);
     const double a00 = z[i * ny + j], a10 = z[(i + 1) * ny + j], a01 = z[i * ny + j + 1], a11 = z[(i + 1) * ny + j + 1];
     const double f0 = a00 + tx * (a10 - a00);
     const double f1 = a01 + tx * (a11 - a01);
@@ -284,18 +291,19 @@ MXB_DEV void op_lens_refl(unsigned long long* st_sm, Photon& ph, PP p, const dou
 }
 
 // scatter.py:49-77  params: center[3] sig_in sig_perp ; z0, z1 standard normal draws
-template <typename PP>
+// NZ_IN / NZ_PERP: whether the width is non-zero, when the caller knows at compile time (1 / 0; -1: test p[3] / p[4])
+template <int NZ_IN = -1, int NZ_PERP = -1, typename PP>
 MXB_DEV void op_rscatter(Photon& ph, PP p, double z0, double z1, double& a, double& b) {
     const V3 radial{ph.pos.x - p[0], ph.pos.y - p[1], ph.pos.z - p[2]};
     const V3 perp = cross(ph.dir, radial);
     V3 out = ph.dir;
     a = 0.0;
     b = 0.0;
-    if (p[3] != 0.0) {
+    if (NZ_IN < 0 ? (p[3] != 0.0) : (NZ_IN != 0)) {
         a = p[3] * z0;
-        out = axangle_rotate_T(perp, a, ph.dir);
+        out = axangle_rotate_T<true>(perp, a, ph.dir);     // perp = dir x radial
     }
-    if (p[4] != 0.0) {
+    if (NZ_PERP < 0 ? (p[4] != 0.0) : (NZ_PERP != 0)) {
         b = p[4] * z1;
         out = axangle_rotate_T(radial, b, out);
     }
@@ -304,16 +312,19 @@ MXB_DEV void op_rscatter(Photon& ph, PP p, double z0, double z1, double& a, doub
 }
 // the two normals of op_rscatter: drawn only for non-zero widths; one Philox call when both come
 // from the device stream
+template <int NZ_IN = -1, int NZ_PERP = -1>
 MXB_DEV void rscatter_draws(double sig_in, double sig_perp, const double* inj0, const double* inj1, long long i,
                             unsigned long long seed, unsigned long long gid, int s0, int s1, double& z0,
                             double& z1) {
     z0 = 0.0;
     z1 = 0.0;
-    if ((sig_in != 0.0) && (sig_perp != 0.0) && !inj0 && !inj1) {
+    const bool nz_in = NZ_IN < 0 ? (sig_in != 0.0) : (NZ_IN != 0);
+    const bool nz_perp = NZ_PERP < 0 ? (sig_perp != 0.0) : (NZ_PERP != 0);
+    if (nz_in && nz_perp && !inj0 && !inj1) {
         device_draw_normal_pair(seed, gid, s0, z0, z1);
     } else {
-        if (sig_in != 0.0) z0 = draw_value(inj0, i, seed, gid, s0, 1);
-        if (sig_perp != 0.0) z1 = draw_value(inj1, i, seed, gid, s1, 1);
+        if (nz_in) z0 = draw_value(inj0, i, seed, gid, s0, 1);
+        if (nz_perp) z1 = draw_value(inj1, i, seed, gid, s1, 1);
     }
 }
 
@@ -332,9 +343,10 @@ MXB_DEV void op_gscatter(Photon& ph, PP p, int flags, double zn, double u, doubl
     } else {
         ang = p[0] * zn;
     }
-    V3 out = axangle_rotate_T(perp, ang, pdir);
-    const double ang2 = u * 2 * 3.141592653589793;
-    out = axangle_rotate_T<true>(pdir, ang2, out);
+    V3 out = axangle_rotate_T<true>(perp, ang, pdir);   // perp = pdir x guess
+    double s2, c2;
+    sincos_turn(u, &s2, &c2);                           // ang2 = u * 2 * pi
+    out = rotate_T_sc<false, true>(pdir, s2, c2, out);  // pdir was normalised above
     ph.pol = parallel_transport(kTrackUnit ? pdir : ph.dir, out, ph.pol, kTrackUnit, true);
     ph.dir = out;
     ph.unit = true;
@@ -356,7 +368,7 @@ MXB_DEV double filter_value(unsigned long long* st_sm, PP p, double energy, int 
         else if (flags & 2) return below ? p[1 + 2 * n] : p[2 + 2 * n];
         else if ((flags & 4) && n >= 2) {
             const int lo = below ? 0 : n - 2;
-            const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+            const double slope = div(fp[lo + 1] - fp[lo], xp[lo + 1] - xp[lo]);
             return slope * (energy - xp[lo]) + fp[lo];
         }
     }
@@ -409,12 +421,12 @@ MXB_DEV double select_order(PP sel, const double* gprog, double u, double energy
         PP wk = sel + 5;
         PP tk = sel + 5 + nw;
         PP ord = sel + 5 + nw + nt;
-        double xq = kHcKevNm / energy;
+        double xq = div(kHcKevNm, energy);
         xq = fmin(fmax(xq, wk[0]), wk[nw - 1]);
         double yq = fmin(fmax(blaze, tk[0]), tk[nt - 1]);
         const int i = bracket(wk, nw, xq), j = bracket(tk, nt, yq);
-        const double tx = (xq - wk[i]) / (wk[i + 1] - wk[i]);
-        const double ty = (yq - tk[j]) / (tk[j + 1] - tk[j]);
+        const double tx = div(xq - wk[i], wk[i + 1] - wk[i]);
+        const double ty = div(yq - tk[j], tk[j + 1] - tk[j]);
         const double* t00 = tab + ((long long)i * nt + j) * no;
         const double* t10 = t00 + (long long)nt * no;
         const double* t01 = t00 + no;
@@ -507,7 +519,7 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
     // flags bit 4: the grating constant varies over the facet (grating.py:209-220, callable d): the caller
     // passes the value d(intercoos) of this photon
     const double p_d = p_dd + div(sign * order * wave, (flags & 16) ? d_photon : p[6]);
-    const double p_n = sqrt(1. - p_d * p_d - p_l * p_l);
+    const double p_n = m_sqrt(1. - p_d * p_d - p_l * p_l);     // NaN for an evanescent order, like np.sqrt
     const double pdn = dot(pn, n);
     double direction = (pdn > 0.0) ? 1.0 : ((pdn < 0.0) ? -1.0 : pdn);  // np.sign
     if (flags & 2) direction = direction * -1;
@@ -531,9 +543,31 @@ MXB_DEV void op_grating(unsigned long long* st_sm, Photon& ph, PP p, GP geom, in
 }
 
 // mitsnl/catgrating.py:147-161  params: factor
+#ifdef MXB_FAST
+__device__ __noinline__ double pow_cold(double x, double y) { return m_pow(x, y); }
+#endif
+// factor ** y with log(factor) = lhi + llo supplied by the host as a double-double (the factor is one number per
+// element: missions/mitsnl/catgrating.py lowers it with 40-digit arithmetic).  Fast build: exp(y lhi) corrected by the
+// rounding of the product and by y llo, i.e. libm's exp (1 ulp) instead of libm's pow (~200 instructions with an
+// extended-precision log inside); <= 3 ulp for any exponent.  A NaN lhi (factor <= 0 or not finite) takes libm's pow.
+MXB_DEV double pow_loghost(double x, double lhi, double llo, double y) {
+#ifdef MXB_FAST
+    if (lhi == lhi) {
+        if (lhi == 0.0 && llo == 0.0) return 1.0;        // 1 ** y
+        const double p = y * lhi;
+        const double e = fma(y, lhi, -p) + y * llo;
+        const double r = m_exp(p);
+        return fma(r, e, r);
+    }
+    return pow_cold(x, y);
+#else
+    return m_pow(x, y);
+#endif
+}
+// mitsnl/catgrating.py:147-161  params: factor, log(factor) hi, lo
 template <typename PP>
 MXB_DEV void op_qfactor(unsigned long long* st_sm, Photon& ph, PP p) {
-    mul_prob(st_sm, ph, m_pow(p[0], ph.last_order * ph.last_order));
+    mul_prob(st_sm, ph, pow_loghost(p[0], p[1], p[2], ph.last_order * ph.last_order));
 }
 
 // mitsnl/catgrating.py:222-259  params: openfraction, bardepth * innerfree, totalarea ; n = e_x of the geometry
@@ -541,8 +575,15 @@ template <typename PP, typename GP>
 MXB_DEV void op_l2abs(unsigned long long* st_sm, Photon& ph, PP p, GP geom) {
     const V3 p3 = normalize_unless(ph.unit, ph.dir);
     const V3 en = ld3(geom + 3);
+#ifdef MXB_OWN_ASIN
+    // sin(arccos(c)) = sqrt((1 - c)(1 + c)) (1 - c is exact for c >= 1/2); NaN above 1 like the reference
+    const double c = fabs(dot(p3, en));
+    const double sn = sqrt_nn((1.0 - c) * (1.0 + c));
+#else
     const double angle = m_acos(fabs(dot(p3, en)));   // no clip in the reference: NaN above 1
-    mul_prob(st_sm, ph, p[0] - div(p[1] * m_sin(angle), p[2]));
+    const double sn = m_sin(angle);
+#endif
+    mul_prob(st_sm, ph, p[0] - div(p[1] * sn, p[2]));
 }
 
 // multiLayerMirror.py:44-91  params: Pinv[9] P[9] ex[3]
@@ -556,9 +597,7 @@ MXB_DEV void op_brewster(unsigned long long* st_sm, Photon& ph, PP p) {
     const V3 nd{q[0] * loc.x + q[1] * loc.y + q[2] * loc.z, q[3] * loc.x + q[4] * loc.y + q[5] * loc.z,
                 q[6] * loc.x + q[7] * loc.y + q[8] * loc.z};
     const V3 ex = ld3(p + 18);
-    V3 v_s = cross(dh, ex);
-    const double nvs = sqrt(dot(v_s, v_s));
-    v_s = V3{v_s.x / nvs, v_s.y / nvs, v_s.z / nvs};
+    const V3 v_s = normalize(cross(dh, ex));
     const V3 v_p = cross(dh, v_s);
     const double pvs = dot(ph.pol, v_s), pvp = dot(ph.pol, v_p);
     const double Es2 = 1. * (pvs * pvs), Ep2 = 0. * (pvp * pvp);
@@ -566,8 +605,7 @@ MXB_DEV void op_brewster(unsigned long long* st_sm, Photon& ph, PP p) {
     if (inten > 1.001) count_status(st_sm, MXB_ST_INTENSITY);
     const V3 nvp = cross(nd, v_s);
     const V3 np_{-Es2 * v_s.x + Ep2 * nvp.x, -Es2 * v_s.y + Ep2 * nvp.y, -Es2 * v_s.z + Ep2 * nvp.z};
-    const double nn = sqrt(dot(np_, np_));
-    ph.pol = V3{np_.x / nn, np_.y / nn, np_.z / nn};
+    ph.pol = normalize(np_);
     ph.dir = nd;
     ph.unit = false;   // pos4d may carry zoom / shear: renormalise at the next use
     mul_prob(st_sm, ph, clip01(inten));
@@ -584,19 +622,19 @@ MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
     PP fw = pk + nr;
     PP pe = fw + nr;
     PP pf = pe + npol;
-    const double wavelength = kHcMultilayer / ph.energy;
+    const double wavelength = div(kHcMultilayer, ph.energy);
     const double tested = interp_clamped(pe, pf, npol, ph.energy);
-    const double local_x = ph.l0 / Ly;
+    const double local_x = div(ph.l0, Ly);
     const double peak_w = interp_clamped(xs, pl, nr, local_x);
-    const double max_refl = interp_clamped(xs, pk, nr, local_x) / tested;
+    const double max_refl = div(interp_clamped(xs, pk, nr, local_x), tested);
     const double spread = interp_clamped(xs, fw, nr, local_x);
-    const double c2 = (spread * spread) / (8. * 0.6931471805599453);
+    const double c2 = div(spread * spread, 8. * 0.6931471805599453);
     double refl = 0.0;
     if (c2 != 0.0) {
         const double dw = wavelength - peak_w;
-        refl = max_refl * m_exp(-(dw * dw) / (2 * c2));
+        refl = max_refl * m_exp(div(-(dw * dw), 2 * c2));
     }
-    mul_prob(st_sm, ph, refl / 100);
+    mul_prob(st_sm, ph, div(refl, 100));
 }
 
 // detector.py:73-75  pr: pixsize cp0 cp1
@@ -628,15 +666,15 @@ MXB_DEV bool cylinder_intersect(P g, const V3& pos, const V3& dir, V3& ip, doubl
     for (int r = 0; r < 3; ++r) dl[r] = g[4 * r] * dir.x + g[4 * r + 1] * dir.y + g[4 * r + 2] * dir.z;
 #pragma unroll
     for (int r = 0; r < 4; ++r) pl[r] = g[4 * r] * pos.x + g[4 * r + 1] * pos.y + g[4 * r + 2] * pos.z + g[4 * r + 3];
-    const double x = pl[0] / pl[3], y = pl[1] / pl[3], z = pl[2] / pl[3];
+    const double x = div(pl[0], pl[3]), y = div(pl[1], pl[3]), z = div(pl[2], pl[3]);
     const double c = (x * x + y * y) - 1.;
     const double b = 2 * (x * dl[0] + y * dl[1]);
     const double a = dl[0] * dl[0] + dl[1] * dl[1];
     const double underroot = b * b - 4 * a * c;
     const bool real = underroot >= 0;
-    const double sq = sqrt(underroot);
+    const double sq = m_sqrt(underroot);
     const double denom = 2 * a;
-    const double a1 = (-b + sq) / denom, a2 = (-b - sq) / denom;
+    const double a1 = div(-b + sq, denom), a2 = div(-b - sq, denom);
     const double x1 = x + a1 * dl[0], y1 = y + a1 * dl[1], z1 = z + a1 * dl[2];
     const double x2 = x + a2 * dl[0], y2 = y + a2 * dl[1], z2 = z + a2 * dl[2];
     const double phi1 = m_atan2(y1, x1), phi2 = m_atan2(y2, x2);
@@ -681,7 +719,7 @@ MXB_DEV void op_aperture(unsigned long long* st_sm, Photon& ph, PP pr, int flags
     double x, y;
     if (flags & 1) {  // CircleAperture :138-146
         const double phi = pr[12] + pr[13] * u0;
-        const double r = sqrt(pr[14] + (1. - pr[14]) * u1);
+        const double r = m_sqrt(pr[14] + (1. - pr[14]) * u1);
         double sn, cs;
         m_sincos(phi, &sn, &cs);
         x = r * cs;
@@ -720,13 +758,11 @@ MXB_DEV double arbitrary_pdf(const double* t, double u0, double u1) {
 
 // math/polarization.py:12-62 polarization_vectors
 MXB_DEV V3 polarization_vector(const V3& dir, double angle) {
-    const double nr = sqrt(dot(dir, dir));
-    const V3 r{dir.x / nr, dir.y / nr, dir.z / nr};
+    const V3 r = normalize(dir);
     const bool conv_x = (fabs(r.x) <= 1e-8) && (fabs(r.z) <= 1e-8);     // np.isclose(., 0.)
     const double rp = conv_x ? r.x : r.y;
     V3 v1{(conv_x ? 1. : 0.) - r.x * rp, (conv_x ? 0. : 1.) - r.y * rp, 0. - r.z * rp};
-    const double n1 = sqrt(dot(v1, v1));
-    v1 = V3{v1.x / n1, v1.y / n1, v1.z / n1};
+    v1 = normalize(v1);
     const V3 v2 = cross(r, v1);
     double s, c;
     m_sincos(angle, &s, &c);
@@ -771,16 +807,14 @@ MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_
     const V3 o{p[0] * v.x + p[1] * v.y + p[2] * v.z, p[3] * v.x + p[4] * v.y + p[5] * v.z,
                p[6] * v.x + p[7] * v.y + p[8] * v.z};
     const V3 m{-o.x, -o.y, -o.z};
-    const double nm = sqrt(dot(m, m));
-    const V3 d0{m.x / nm, m.y / nm, m.z / nm};
+    const V3 d0 = normalize(m);
     PP T = p + 9;
     V3 d{T[0] * d0.x + T[1] * d0.y + T[2] * d0.z, T[3] * d0.x + T[4] * d0.y + T[5] * d0.z,
          T[6] * d0.x + T[7] * d0.y + T[8] * d0.z};
     const V3 north = ld3(p + 18);
     const double proj = d.x * north.x + d.y * north.y + d.z * north.z;
     V3 nin{north.x - d.x * proj, north.y - d.y * proj, north.z - d.z * proj};
-    const double nn = sqrt(dot(nin, nin));
-    nin = V3{nin.x / nn, nin.y / nn, nin.z / nn};
+    nin = normalize(nin);
     const V3 ein = cross(d, nin);
     double sp, cp;
     m_sincos(polangle, &sp, &cp);
@@ -894,6 +928,19 @@ MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int
 #else
 #define MXB_SCAN_ATTR __device__ __forceinline__   // measured (C2, r01): a call site in the search loop costs 18 %
 #endif
+// -DMXB_SCAN_CHEAP (experiment, measured r02: C3 34.2 vs 34.7 ms, but 121 instead of 96 registers for C2, which never
+// scans): the scan only asks WHETHER a facet is hit, so it could use the division-free test (a superset of the exact
+// one by 1e-12; the caller confirms)
+#ifdef MXB_SCAN_CHEAP
+#define MXB_SCAN_TEST(row) plane_maybe_hit(row, pos, dir)
+#else
+#define MXB_SCAN_TEST(row) plane_intersect(row, pos, dir, false, ipt, a0, a1)
+#endif
+#ifdef MXB_SCAN_UNROLL1
+#define MXB_SCAN_PRAGMA _Pragma("unroll 1")
+#else
+#define MXB_SCAN_PRAGMA
+#endif
 template <typename BP, typename HP, typename IP>
 MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int rows_off, int stride, int F,
                                                int nu, int nv, V3 pos, V3 dir, int after) {
@@ -906,7 +953,7 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
     if (dn == 0.0) {
         if (fabs(h0) > Hs) return -1;          // parallel to the slab and outside of it
     } else {
-        const double ta = (-Hs - h0) / dn, tb = (Hs - h0) / dn;
+        const double ta = div(-Hs - h0, dn), tb = div(Hs - h0, dn);
         const double t_lo = fmax(fmin(ta, tb), 0.0), t_hi = fmax(ta, tb);
         if (t_hi < 0.0) return -1;             // the slab lies behind the photon
         const V3 uu = ld3(H + 6), vv = ld3(H + 9);
@@ -924,23 +971,28 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
             iv1 = (int)fmin(vhi, (double)(nv - 1));
         }
     }
+#ifndef MXB_SCAN_CHEAP
     V3 ipt;
     double a0, a1;
+#endif
     if ((long long)(iu1 - iu0 + 1) * (iv1 - iv0 + 1) > 256) {
         // a footprint this long touches most of the array: one ordered pass over the facets is cheaper
+        MXB_SCAN_PRAGMA
         for (int j = after + 1; j < F; ++j)
-            if (plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1)) return j;
+            if (MXB_SCAN_TEST(B + (rows_off + j * stride))) return j;
         return -1;
     }
     int best = 0x7fffffff;
+    MXB_SCAN_PRAGMA
     for (int iv = iv0; iv <= iv1; ++iv)
+        MXB_SCAN_PRAGMA
         for (int iu = iu0; iu <= iu1; ++iu) {
             const int cell = iv * nu + iu;
             const int k1 = cell_start.i32(cell + 1);
+            MXB_SCAN_PRAGMA
             for (int k = cell_start.i32(cell); k < k1; ++k) {
                 const int j = cand.i32(k);
-                if (j > after && j < best && plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1))
-                    best = j;
+                if (j > after && j < best && MXB_SCAN_TEST(B + (rows_off + j * stride))) best = j;
             }
         }
     return best == 0x7fffffff ? -1 : best;
@@ -950,7 +1002,19 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
 template <typename BP, typename HP, typename IP>
 MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int rows_off, int stride, int F, int nu,
                           int nv, Photon& ph, int& row) {
-    if (it.seg) {
+    if (MXB_UNLIKELY(it.seg)) {
+#ifdef MXB_SCAN_CHEAP
+        while (it.cur < it.end) {
+            const int j = array_scan_segment(B, H, cell_start, cand, rows_off, stride, F, nu, nv, ph.pos, ph.dir, it.cur - 1);
+            if (j < 0) break;
+            row = rows_off + j * stride;
+            it.cur = j + 1;
+            // the exact test decides (the scan's test is a superset of it by rounding) and yields ip / l0 / l1
+            if (plane_intersect(B + row, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1)) return true;
+        }
+        it.cur = it.end;
+        return false;
+#else
         if (it.cur >= it.end) return false;
         const int j = array_scan_segment(B, H, cell_start, cand, rows_off, stride, F, nu, nv, ph.pos, ph.dir, it.cur - 1);
         if (j < 0) {
@@ -961,6 +1025,7 @@ MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int
         it.cur = j + 1;
         plane_intersect(B + row, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1);
         return true;
+#endif
     }
     while (it.cur < it.end) {
         const int j = it.brute ? it.cur : cand.i32(it.cur);

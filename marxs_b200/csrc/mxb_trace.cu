@@ -1016,6 +1016,31 @@ int mxb_debug_draws(uint64_t seed, int64_t photon_id0, int64_t n, int slot, int 
     return MXB_OK;
 }
 
+// device math routines of this build, exported for verification (tests): out[i] = f(x[i], y[i])
+__global__ void debug_math_kernel(int kind, const double* x, const double* y, double* out, int64_t n, double log_hi, double log_lo) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        double r;
+        switch (kind) {
+        case 0: r = mxb::m_acos(a); break;
+        case 1: r = mxb::m_asin(a); break;
+        case 2: r = mxb::pow_loghost(a, log_hi, log_lo, b); break;
+        case 3: r = mxb::div(a, b); break;
+        case 4: case 5: { double s, c; mxb::sincos_small(a, &s, &c); r = (kind == 4) ? s : c; break; }
+        default: { double s, c; mxb::sincos_turn(a, &s, &c); r = (kind == 6) ? s : c; }
+        }
+        out[i] = r;
+    }
+}
+
+int mxb_debug_math(int kind, const double* x, const double* y, double* out, int64_t n, double log_hi, double log_lo, void* stream) {
+    if (!x || !out || kind < 0 || kind > 7 || ((kind == 2 || kind == 3) && !y)) return fail(MXB_EINVAL, "mxb_debug_math: bad argument");
+    if (n <= 0) return n == 0 ? MXB_OK : fail(MXB_EINVAL, "negative n");
+    debug_math_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(kind, x, y, out, n, log_hi, log_lo);
+    CUDA_TRY(cudaGetLastError());
+    return MXB_OK;
+}
+
 int mxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -106,6 +106,22 @@ class NonParallelCATGrating(CATGrating):
         return (self.blaze_center, self.d_blaze_mm)
 
 
+def log_double_double(x):
+    """ln(x) as an unevaluated sum of two doubles (40-digit arithmetic): the fast kernel build forms
+    ``x ** y = exp(y * ln x)`` from it without losing the digits a double logarithm would (csrc/mxb_ops.cuh
+    pow_loghost).  NaN, NaN when x is not a positive finite number (the kernel then calls libm's pow)."""
+    import decimal
+    x = float(x)
+    if not (x > 0.0 and np.isfinite(x)):
+        return float('nan'), float('nan')
+    with decimal.localcontext() as ctx:
+        ctx.prec = 40
+        ln = decimal.Decimal(x).ln()
+        hi = float(ln)
+        lo = float(ln - decimal.Decimal(hi))
+    return hi, lo
+
+
 class QualityFactor(FlatOpticalElement):
     """Scale probabilities of theoretical curves to measured values:
     ``probability *= factor ** order**2`` (reference :147-161)."""
@@ -121,7 +137,7 @@ class QualityFactor(FlatOpticalElement):
     def _lower_specific(self, lw):
         if lw.last_order_col != 'order':
             raise NotFusable('QualityFactor needs the order of a grating in the same stack')
-        lw.op('QFACTOR', pf=lw.eparams([self.factor]))
+        lw.op('QFACTOR', pf=lw.eparams([self.factor, *log_double_double(self.factor)]))
 
 
 class L1(CATGrating):

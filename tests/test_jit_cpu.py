@@ -58,7 +58,7 @@ def test_source_c2_structure():
     src = _lib.jit_source(prog, fake_columns(prog))
     assert src.count('array_open(') == 2 and src.count('array_search(') == 2
     assert 'select_order_fixed<7>' in src              # HETG: 7 equally likely orders, unrolled
-    assert 'op_acis(' in src and 'op_grating(' in src and 'op_rscatter(' in src
+    assert 'op_acis(' in src and 'op_grating(' in src and 'op_rscatter<1, 1>(' in src   # both scatter widths non-zero: baked
     assert '#define JIT_STAGE_WORDS {0}'.format(prog.stage_words) in src
     # FlatStack layers repeat the loc-coos commit of their stack: emitted once per column
     assert src.count('ph.pos = ph.ip') == 3

@@ -429,3 +429,123 @@ def test_paralleltransport_matrix_jones_gpu():
                     ('gen_nan', {'jones': g['jones'], 'replace_nans': False})):
         got = polarization.paralleltransport_matrix(d1, d2, **kw).cpu().numpy()
         np.testing.assert_allclose(got, g[key], rtol=1e-12, atol=1e-13, equal_nan=True, err_msg=key)
+
+
+# ---------------------------------------------------------------------------
+# device math of the fast build (own arccos / arcsin / integer power / small-angle sincos) against numpy
+# ---------------------------------------------------------------------------
+def _device_math(kind, x, y=None, log_hi=0., log_lo=0.):
+    from marxs_b200 import _lib
+    lib = _lib.load()
+    tx = torch.tensor(x, dtype=torch.float64, device='cuda')
+    ty = torch.tensor(y, dtype=torch.float64, device='cuda') if y is not None else None
+    out = torch.empty_like(tx)
+    rc = lib.mxb_debug_math(kind, tx.data_ptr(), ty.data_ptr() if ty is not None else None, out.data_ptr(), tx.numel(),
+                            log_hi, log_lo, None)
+    assert rc == 0, lib.mxb_last_error()
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_device_math_vs_numpy(mode):
+    """optics/grating.py:262 (arccos of the blaze angle), mitsnl/catgrating.py:147-161 (factor ** order^2), :251-256
+    (arccos / sin of L2 absorption), :280-285 (arcsin of the L2 diffraction width), math/rotations.py:50-87 (sin / cos):
+    the fast build evaluates these with its own routines (csrc/mxb_device.cuh).  Bars: 4 ulp for arccos / arcsin over
+    the whole domain incl. the ends, exact special values, 16 ulp for the integer power."""
+    rng = np.random.default_rng(SEED + 140)
+    eps = 2.0 ** -52
+    x = np.concatenate([np.linspace(-1, 1, 200001), 1 - np.logspace(-16, -1, 4000), np.logspace(-300, -1, 4000),
+                        -np.logspace(-300, -1, 4000), rng.uniform(-1, 1, 100000), [0., 1., -1., 0.5, -0.5, 0.5000000000000001]])
+    with np.errstate(invalid='ignore'):
+        for kind, f in ((0, np.arccos), (1, np.arcsin)):
+            got, want = _device_math(kind, x), f(x)
+            err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+            ok = want != 0
+            assert err[ok].max() <= 4 * eps, (kind, err[ok].max() / eps)
+            assert np.all(got[~ok] == 0)
+            bad = np.array([1.0000000000000002, -1.5, np.nan, np.inf])
+            assert np.all(np.isnan(_device_math(kind, bad)))       # like numpy outside [-1, 1]
+    assert _device_math(0, np.array([1.0]))[0] == 0.0 and _device_math(0, np.array([-1.0]))[0] == np.pi
+    assert _device_math(1, np.array([1.0]))[0] == np.pi / 2
+    # factor ** order^2 against 40-digit arithmetic (QualityFactor: one factor per element, its logarithm lowered as a
+    # double-double by the host)
+    import mpmath
+    from marxs_b200.missions.mitsnl.catgrating import log_double_double
+    mpmath.mp.dps = 40
+    order = np.arange(-45, 46).astype(float)
+    for f in (0.9, 0.98765, 0.5, 1.0, 0.9999999, 1.25):
+        hi, lo = log_double_double(f)
+        got = _device_math(2, np.full(len(order), f), order * order, hi, lo)
+        want = np.array([float(mpmath.mpf(f) ** int(b * b)) for b in order])
+        ok = want > 1e-300
+        assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= 4 * eps, f
+    hi, lo = log_double_double(0.98)
+    odd = np.array([2.5, 0.0, np.nan, 1e6, 2047.0, 0.5])
+    np.testing.assert_allclose(_device_math(2, np.full(len(odd), 0.98), odd, hi, lo), np.power(0.98, odd), rtol=8 * eps, equal_nan=True)
+    nan = float('nan')       # factor the host cannot take the logarithm of: libm's pow
+    np.testing.assert_allclose(_device_math(2, np.zeros(3), np.array([0., 1., 4.]), nan, nan), [1., 0., 0.])
+    # sin / cos of scatter angles: tiny (Taylor branch in the fast build) and large
+    a = np.concatenate([rng.normal(0, 1e-5, 50000), rng.uniform(-0.0078, 0.0078, 50000), rng.uniform(-7, 7, 20000), [0.]])
+    np.testing.assert_allclose(_device_math(4, a), np.sin(a), rtol=4 * eps, atol=0)
+    np.testing.assert_allclose(_device_math(5, a), np.cos(a), rtol=4 * eps, atol=0)
+    u = np.concatenate([rng.uniform(0, 1, 100000), np.arange(0, 1.0001, 0.125), [1e-300, 1 - 2.0 ** -53, 0.1249999999999999]])
+    ang = u * 2 * 3.141592653589793
+    # (the fast build reduces in turns: it does not see the rounding of ang)
+    tol = 2.3e-16 if mode == 'strict' else 8e-16     # strict: libm's sincos of the same rounded angle (1 ulp vs numpy)
+    assert np.max(np.abs(_device_math(6, u) - np.sin(ang))) <= tol
+    assert np.max(np.abs(_device_math(7, u) - np.cos(ang))) <= tol
+    q = rng.uniform(-5, 5, 10000)
+    d = rng.uniform(0.1, 5, 10000) * rng.choice([-1., 1.], 10000)
+    np.testing.assert_allclose(_device_math(3, q, d), q / d, rtol=(0 if mode == 'strict' else 2 * eps))
+
+
+# ---------------------------------------------------------------------------
+# sigma_clipped_stats as a kernel (reference analysis/analysis.py:9-25 -> astropy.stats.sigma_clipped_stats)
+# ---------------------------------------------------------------------------
+def _clip_np(a, sigma=3., maxiters=5):
+    """astropy's algorithm with its defaults, restated in numpy (median centre, std width, non-finite masked)."""
+    a = np.asarray(a, dtype=float)
+    a = a[np.isfinite(a)]
+    for _ in range(maxiters):
+        if a.size == 0:
+            break
+        med, std = np.median(a), a.std()
+        keep = (a >= med - sigma * std) & (a <= med + sigma * std)
+        if keep.all():
+            break
+        a = a[keep]
+    if a.size == 0:
+        return (np.nan, np.nan, np.nan)
+    return a.mean(), np.median(a), a.std()
+
+
+def test_sigma_clip_kernel_vs_numpy():
+    from marxs_b200 import analysis
+    rng = np.random.default_rng(SEED + 150)
+    cases = {
+        'gauss+outliers': np.concatenate([rng.normal(3., 0.5, 20001), rng.uniform(-50, 50, 300), [np.nan] * 5, [np.inf, -np.inf]]),
+        'even count': np.concatenate([rng.normal(-7., 2., 10000), rng.uniform(-500, 500, 100)]),
+        'negative and positive': rng.normal(0., 1e-3, 4097),
+        'heavy duplicates': np.round(rng.normal(0, 3, 50000)),
+        'all equal': np.full(1000, 2.5),
+        'two values': np.array([1., 2.]),
+        'one value': np.array([-4.25]),
+        'only nan': np.array([np.nan, np.inf]),
+        'empty': np.zeros(0),
+        'wide range': np.concatenate([10. ** rng.uniform(-300, 300, 5000), -10. ** rng.uniform(-300, 300, 5000)]),
+        'signed zeros': np.array([0., -0., 0., -0., 1e-320, -1e-320]),
+        'det_x like': np.concatenate([rng.normal(512.3, 0.02, 300000), rng.normal(600., 30., 3000)]),
+    }
+    for name, x in cases.items():
+        for kw in (dict(), dict(sigma=2., maxiters=1), dict(sigma=5., maxiters=0), dict(sigma=1.5, maxiters=20)):
+            got = analysis.sigma_clipped_stats(torch.as_tensor(x, device='cuda'), **kw)
+            want = _clip_np(x, **{'sigma': 3., 'maxiters': 5, **kw})
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300, equal_nan=True, err_msg='{0} {1}'.format(name, kw))
+            assert got[1] == want[1] or (np.isnan(got[1]) and np.isnan(want[1])), (name, kw)      # the median is exact
+    # column-sized input, and a host array (copied to the device: there is no CPU path)
+    big = np.concatenate([rng.normal(0., 1., 10_000_000), rng.uniform(-100, 100, 100_000)])
+    got = analysis.sigma_clipped_stats(torch.as_tensor(big, device='cuda'))
+    want = _clip_np(big)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert got[1] == want[1]
+    np.testing.assert_allclose(analysis.sigma_clipped_stats(cases['gauss+outliers']), _clip_np(cases['gauss+outliers']), rtol=1e-12)
