@@ -139,7 +139,9 @@ class _Events(dict):
         return len(self['order'])
 
 
+@pytest.mark.gpu
 def test_capture_res_aeff_matches_the_reference():
+    """(GPU: the statistics behind it are a kernel, mxb_sigma_clip_stats - there is no CPU path)"""
     ev = _Events(_events())
     orders = GOLD['ev_orders']
     for tag, cap in (('cap', analysis.CaptureResAeff(A_geom=5., orders=orders)),
@@ -166,6 +168,9 @@ def test_capture_res_aeff_matches_the_reference():
     np.testing.assert_allclose(r2[:7], np.min(both, axis=0)[:7], rtol=1e-10)
     with pytest.raises(ValueError):
         analysis.resolvingpower_from_photonlist_robust([ev], orders, ['det_x', 'det_x'], [None, 0.3])
+
+
+def test_analysis_host_helpers():
     res_avg, aeff_sum = analysis.average_R_Aeff(np.array([1., np.nan, 3.]), np.array([1., 5., 3.]))
     assert aeff_sum == 9. and np.isclose(res_avg, (1. + 9.) / 4.)
     ang = np.deg2rad(np.array([80., 100., 120., 260., 290., 10.]))
