@@ -12,11 +12,6 @@
 #endif
 
 #define MXB_DEV __device__ __forceinline__
-#ifdef MXB_NO_EXPECT
-#define MXB_UNLIKELY(x) (x)
-#else
-#define MXB_UNLIKELY(x) __builtin_expect(!!(x), 0)
-#endif
 // -DMXB_SHARE_CODE turns parallel transport / Rodrigues rotation into real functions (one copy, called)
 // for very large programs; measured slower on C3 (r01: 5.9 -> 6.9 ms), so it is off by default.
 #ifdef MXB_SHARE_CODE
@@ -230,25 +225,6 @@ MXB_DEV bool plane_intersect(P g, const V3& pos, const V3& dir, bool circular, V
     return hit;
 }
 
-// Division-free form of the same test for SEARCHES that only need to know whether a facet is hit (the steep-ray
-// footprint scan): with pc = c - pos, k = (pc.ex) / (dir.ex) and l = (k dir - pc).e = ((pc.ex)(dir.e) - (pc.e)(dir.ex)) / (dir.ex)
-// the conditions k >= 0, |l0| <= Ly, |l1| <= Lz become sign and magnitude tests on products.  The bounds are inflated
-// by 1e-12 so that rounding can never reject a facet the exact test accepts; callers confirm a hit with
-// plane_intersect (which also yields ip / l0 / l1) and go on searching when it disagrees.
-template <typename P>
-MXB_DEV bool plane_maybe_hit(P g, const V3& pos, const V3& dir) {
-    const double2 g01 = g.ld2(0), g23 = g.ld2(1), g45 = g.ld2(2), g67 = g.ld2(3), g89 = g.ld2(4),
-                  gab = g.ld2(5), gcd = g.ld2(6);
-    const double px = g01.x - pos.x, py = g01.y - pos.y, pz = g23.x - pos.z;
-    const double kn = px * g23.y + py * g45.x + pz * g45.y;
-    const double kd = dir.x * g23.y + dir.y * g45.x + dir.z * g45.y;
-    const double a0 = px * g67.x + py * g67.y + pz * g89.x, b0 = dir.x * g67.x + dir.y * g67.y + dir.z * g89.x;
-    const double a1 = px * g89.y + py * gab.x + pz * gab.y, b1 = dir.x * g89.y + dir.y * gab.x + dir.z * gab.y;
-    const double lim = fabs(kd) * 1.000000000001;
-    const bool fwd = (kn * kd >= 0.0) || (kn == 0.0);       // k >= 0 (k = -0 passes, like the IEEE comparison)
-    return (kd != 0.0) & fwd & (fabs(kn * b0 - a0 * kd) <= gcd.x * lim) & (fabs(kn * b1 - a1 * kd) <= gcd.y * lim);
-}
-
 // Unit-length tracking (fast build only).  The reference re-normalises directions in every
 // routine; a vector this kernel has just produced by normalisation, rotation or the grating
 // equation already has |v| = 1 to rounding, and normalising it again changes it by <= 1 ulp.  The
@@ -427,30 +403,8 @@ MXB_DEV int bracket(P xk, int n, double x) {
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = (photon id lo, hi, slot, 0)
 // ---------------------------------------------------------------------------
-#ifdef MXB_SHARE_PHILOX
-__device__ __noinline__ uint4 philox_shared(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
-    uint32_t c3 = 0u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-#endif
 MXB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                            uint32_t k1, uint32_t out[4]) {
-#ifdef MXB_SHARE_PHILOX
-    if (c3 == 0u) {       // (always: the counter's last word is unused)
-        const uint4 r = philox_shared(c0, c1, c2, k0, k1);
-        out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
-        return;
-    }
-#endif
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;

@@ -617,6 +617,22 @@ struct Gen {
         body.swap(src);         // body holds the op code; src receives the preamble
         if ((17 + fmap.size() + imap.size() + dmap.size() + smap.size()) * 8 > 32000) return fail("program has too many scalar parameters");
         out("// generated by libmxb (mxb_jit.cpp): specialised driver of one element program");
+        {
+            // array bodies that redirect photons more than once (two gratings, grating + scatter ...) make steep rays
+            // common: every warp then walks the footprint scan with a lane or two, and its code should stay small
+            bool compact_scan = false;
+            for (int pc = 0; pc < n_ops; ++pc) {
+                if (ops[pc].type != MXB_OP_ARRAY_BEGIN) continue;
+                int redirecting = 0;
+                for (int k = pc + 1; k < n_ops && k < ops[pc].w14; ++k) {
+                    const int t = ops[k].type;
+                    redirecting += (t == MXB_OP_GRATING || t == MXB_OP_GSCATTER || t == MXB_OP_RSCATTER || t == MXB_OP_LENS ||
+                                    t == MXB_OP_BREWSTER) ? 1 : 0;
+                }
+                compact_scan |= redirecting >= 2;
+            }
+            if (compact_scan) out("#define MXB_SCAN_UNROLL1 1");
+        }
         out("#include \"mxb_ops.cuh\"");
         out("using namespace mxb;");
         out("#ifndef JIT_THREADS\n#define JIT_THREADS 640\n#endif");

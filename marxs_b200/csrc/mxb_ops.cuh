@@ -928,14 +928,10 @@ MXB_DEV void array_open(ArrayIter& it, HP H, IP cell_start, int F, int mode, int
 #else
 #define MXB_SCAN_ATTR __device__ __forceinline__   // measured (C2, r01): a call site in the search loop costs 18 %
 #endif
-// -DMXB_SCAN_CHEAP (experiment, measured r02: C3 34.2 vs 34.7 ms, but 121 instead of 96 registers for C2, which never
-// scans): the scan only asks WHETHER a facet is hit, so it could use the division-free test (a superset of the exact
-// one by 1e-12; the caller confirms)
-#ifdef MXB_SCAN_CHEAP
-#define MXB_SCAN_TEST(row) plane_maybe_hit(row, pos, dir)
-#else
-#define MXB_SCAN_TEST(row) plane_intersect(row, pos, dir, false, ipt, a0, a1)
-#endif
+// MXB_SCAN_UNROLL1 (set by the kernel generator for programs whose array bodies redirect photons more than once, i.e.
+// where steep rays are common and every warp walks this scan with one or two lanes): do not unroll the scan loops -
+// smaller code in an instruction-cache-bound kernel (measured r02: C3 34.0 -> 32.3 ms; C2, which never scans, loses 1 %
+// to the changed register allocation, so it is not the default)
 #ifdef MXB_SCAN_UNROLL1
 #define MXB_SCAN_PRAGMA _Pragma("unroll 1")
 #else
@@ -971,15 +967,13 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
             iv1 = (int)fmin(vhi, (double)(nv - 1));
         }
     }
-#ifndef MXB_SCAN_CHEAP
     V3 ipt;
     double a0, a1;
-#endif
     if ((long long)(iu1 - iu0 + 1) * (iv1 - iv0 + 1) > 256) {
         // a footprint this long touches most of the array: one ordered pass over the facets is cheaper
         MXB_SCAN_PRAGMA
         for (int j = after + 1; j < F; ++j)
-            if (MXB_SCAN_TEST(B + (rows_off + j * stride))) return j;
+            if (plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1)) return j;
         return -1;
     }
     int best = 0x7fffffff;
@@ -992,7 +986,7 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
             MXB_SCAN_PRAGMA
             for (int k = cell_start.i32(cell); k < k1; ++k) {
                 const int j = cand.i32(k);
-                if (j > after && j < best && MXB_SCAN_TEST(B + (rows_off + j * stride))) best = j;
+                if (j > after && j < best && plane_intersect(B + (rows_off + j * stride), pos, dir, false, ipt, a0, a1)) best = j;
             }
         }
     return best == 0x7fffffff ? -1 : best;
@@ -1002,19 +996,7 @@ MXB_SCAN_ATTR int array_scan_segment(BP B, HP H, IP cell_start, IP cand, int row
 template <typename BP, typename HP, typename IP>
 MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int rows_off, int stride, int F, int nu,
                           int nv, Photon& ph, int& row) {
-    if (MXB_UNLIKELY(it.seg)) {
-#ifdef MXB_SCAN_CHEAP
-        while (it.cur < it.end) {
-            const int j = array_scan_segment(B, H, cell_start, cand, rows_off, stride, F, nu, nv, ph.pos, ph.dir, it.cur - 1);
-            if (j < 0) break;
-            row = rows_off + j * stride;
-            it.cur = j + 1;
-            // the exact test decides (the scan's test is a superset of it by rounding) and yields ip / l0 / l1
-            if (plane_intersect(B + row, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1)) return true;
-        }
-        it.cur = it.end;
-        return false;
-#else
+    if (it.seg) {
         if (it.cur >= it.end) return false;
         const int j = array_scan_segment(B, H, cell_start, cand, rows_off, stride, F, nu, nv, ph.pos, ph.dir, it.cur - 1);
         if (j < 0) {
@@ -1025,7 +1007,6 @@ MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int
         it.cur = j + 1;
         plane_intersect(B + row, ph.pos, ph.dir, false, ph.ip, ph.l0, ph.l1);
         return true;
-#endif
     }
     while (it.cur < it.end) {
         const int j = it.brute ? it.cur : cand.i32(it.cur);

@@ -50,6 +50,12 @@ for jit in (2, 0):
     o = lens(mb.PhotonBatch(ph, device='cuda')).to_numpy()
     assert (o['probability'] < 1).sum() > 100
 _lib.load().mxb_set_jit(-1)
+# sigma clipping kernels (radix-select median) and the exported device math
+from marxs_b200 import analysis
+import torch
+x = np.concatenate([rng.normal(0., 1., 20001), rng.uniform(-40, 40, 200), [np.nan, np.inf]])
+m = analysis.sigma_clipped_stats(torch.as_tensor(x, device='cuda'))
+assert abs(m[1]) < 0.1 and 0.9 < m[2] < 1.1
 print('sanitizer workload ok')
 PY
 done
