@@ -137,6 +137,19 @@ MXB_DEV double div(double a, double b) {
 #endif
 }
 
+// two quotients by the same divisor: one reciprocal (fast build), each quotient corrected like div()
+MXB_DEV void div2(double a0, double a1, double b, double& q0, double& q1) {
+#ifdef MXB_FAST
+    const double r = fast_rcp(b);
+    const double t0 = a0 * r, t1 = a1 * r;
+    q0 = fma(fma(-b, t0, a0), r, t0);
+    q1 = fma(fma(-b, t1, a1), r, t1);
+#else
+    q0 = a0 / b;
+    q1 = a1 / b;
+#endif
+}
+
 MXB_DEV double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 MXB_DEV V3 cross(const V3& a, const V3& b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};

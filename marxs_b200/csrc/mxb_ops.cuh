@@ -640,9 +640,10 @@ MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
 // detector.py:73-75  pr: pixsize cp0 cp1
 template <typename PP>
 MXB_DEV void op_detpix(const Photon& ph, PP pr, int flags, double& px, double& py) {
-    if (flags & 2) px = div(ph.l0 * pr[3], pr[0]) + pr[1];   // CircularDetector: phi * R / pixsize (detector.py:114)
-    else px = div(ph.l0, pr[0]) + pr[1];
-    py = div(ph.l1, pr[0]) + pr[2];
+    double qx, qy;
+    div2((flags & 2) ? ph.l0 * pr[3] : ph.l0, ph.l1, pr[0], qx, qy);   // CircularDetector: phi * R / pixsize (detector.py:114)
+    px = qx + pr[1];
+    py = qy + pr[2];
 }
 
 // ---------------------------------------------------------------------------
@@ -696,13 +697,15 @@ MXB_DEV bool cylinder_intersect(P g, const V3& pos, const V3& dir, V3& ip, doubl
 // global gp: f pixrad odet0 odet1 cosr sinr.  out: chipx chipy tdetx tdety detx dety x y
 template <typename PP, typename GP>
 MXB_DEV void op_acis(const Photon& ph, PP pr, GP gp, double out[8]) {
-    const double chipx = div(ph.l0, pr[0]) + pr[1] + 1;
-    const double chipy = div(ph.l1, pr[0]) + pr[2] + 1;
+    double cx, cy, xm, ym, x, y;
+    div2(ph.l0, ph.l1, pr[0], cx, cy);
+    const double chipx = cx + pr[1] + 1;
+    const double chipy = cy + pr[2] + 1;
     const double tx = pr[3] * (pr[4] * (chipx - 0.5) + pr[5] * (chipy - 0.5)) + pr[6];
     const double ty = pr[3] * (-pr[5] * (chipx - 0.5) + pr[4] * (chipy - 0.5)) + pr[7];
     const double mn0 = ph.ip.x - gp[0];
-    const double x = div(div(ph.ip.y, mn0), gp[1]);
-    const double y = div(div(ph.ip.z, mn0), gp[1]);
+    div2(ph.ip.y, ph.ip.z, mn0, xm, ym);
+    div2(xm, ym, gp[1], x, y);
     out[0] = chipx;
     out[1] = chipy;
     out[2] = tx;
