@@ -533,7 +533,11 @@ struct Gen {
         if (nF < 0 || stride < 14 || !range_ok(rows_off, (long long)std::max(nF, 1) * stride)) return fail("array rows outside the blob");
         if (mode == 1 && (!range_ok(cs_off, ((long long)nu * nv + 2) / 2) || !range_ok(cand_off, 0))) return fail("culling grid outside the blob");
         need_blob = true;
-        const std::string H = S(o.pg, 17);
+        const std::string H = S(o.pg, 18);
+        // disjointness certificate (mxb_ops.cuh array_revalidate): mode and table offset are structure
+        const int lim_mode = (mode == 1 && range_ok(o.pg, 20)) ? baked(o.pg + 19) : 0;
+        const int lim_off = lim_mode == 2 ? baked(o.pg + 18) : 0;
+        if (lim_mode == 2 && !range_ok(lim_off, (nF + 1) / 2)) return fail("certificate table outside the blob");
         out("            // ---- ops %d..%d: array of %d facets, stride %d, mode %d (%d x %d cells)", pc, end_pc, nF, stride, mode, nu, nv);
         out("            {");
         out("            ArrayIter it;");
@@ -581,8 +585,9 @@ struct Gen {
                 redirects |= (t == MXB_OP_LENS || t == MXB_OP_RSCATTER || t == MXB_OP_GSCATTER || t == MXB_OP_GRATING ||
                               t == MXB_OP_BREWSTER);
             }
-            if (redirects)
-                out("            array_revalidate(it, %s, ph, nhit, row, %d, %d, %d, st_sm);", H.c_str(), rows_off, stride, nF);
+            if (redirects || lim_mode)
+                out("            array_revalidate<%s>(it, %s, (B + %d), %d, ph, nhit, row, %d, %d, %d, st_sm);", redirects ? "true" : "false",
+                    H.c_str(), lim_off, lim_mode, rows_off, stride, nF);
             else
                 out("            // (body does not redirect photons: the candidate list stays valid)");
         }

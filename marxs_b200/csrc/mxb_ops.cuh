@@ -70,6 +70,10 @@ struct PRef {
         if (STAGED) return reinterpret_cast<const double2*>(g_smem + off)[k];
         return __ldg(reinterpret_cast<const double2*>(g + off) + k);
     }
+    MXB_DEV float f32(int k) const {  // packed float32 view of the words at off
+        if (STAGED) return reinterpret_cast<const float*>(g_smem)[2 * off + k];
+        return __ldg(reinterpret_cast<const float*>(g) + 2 * (long long)off + k);
+    }
     MXB_DEV int i32(int k) const {  // packed int32 view of the words at off
         if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
         return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
@@ -1024,15 +1028,39 @@ MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int
     return false;
 }
 
-// after the body: photons that hit re-validate the culling cone for their NEW direction.  The cell
-// list covers ONE redirection inside the cone (H t + 2 H t' <= margin); a second hit or a steep new
-// direction falls back to brute force over the remaining facets
-template <typename HP>
-MXB_DEV void array_revalidate(ArrayIter& it, HP H, const Photon& ph, int nhit, int row, int rows_off, int stride,
-                              int F, unsigned long long* st_sm) {
-    if (ph.hit && !it.brute) {
-        double dn;
-        const bool ok = cull_cone_ok(H, ph.dir, ph.unit, dn);
+// after the body, for photons that hit:
+// (1) DISJOINTNESS CERTIFICATE.  The lowering computes for every facet A the largest tangent t_A (angle to the array's
+//     mean normal) below which a ray that starts anywhere on A cannot reach any OTHER facet of the array: for each pair
+//     the footprints on the mean plane are separated by gap_AB (separating-axis test), the facets' heights differ by at
+//     most h_AB, and a ray travels at most h_AB tan(theta) sideways while it changes height by h_AB, so
+//     t_A = min_B gap_AB / h_AB (0 when A overlaps a neighbour).  A photon that leaves A inside that cone is DONE with
+//     the array: the reference's remaining facets (simulator.py:42-49) would all miss it, so they are not tested, and a
+//     steep diffraction order does not have to walk the footprint scan.  lim_mode 1: H[17] = min_A t_A^2 (every facet);
+//     2: per-facet t_A^2 as float32 (rounded down) at `limits`; 0: no certificate (overlapping arrays).
+// (2) otherwise, when the body can redirect photons, the culling cone is re-validated for the NEW direction: the cell
+//     list covers ONE redirection inside the cone (H t + 2 H t' <= margin); a second hit or a steep new direction
+//     falls back to the footprint scan over the remaining facets
+template <bool REDIRECTS = true, typename HP, typename LP>
+MXB_DEV void array_revalidate(ArrayIter& it, HP H, LP limits, int lim_mode, const Photon& ph, int nhit, int row,
+                              int rows_off, int stride, int F, unsigned long long* st_sm) {
+    if (!ph.hit) return;
+#ifdef MXB_NO_CERT      // A/B switch of the certificate
+    lim_mode = 0;
+#endif
+    if (!lim_mode && (!REDIRECTS || it.brute)) return;
+    const V3 nb = ld3(H + 3);
+    const double dn = dot(ph.dir, nb);
+    const double d2 = (kTrackUnit && ph.unit) ? 1.0 : dot(ph.dir, ph.dir);
+    const double c2 = dn * dn, s2 = d2 - c2;          // tan^2 = s2 / c2; NaN fails every comparison below
+    if (lim_mode) {
+        const double t2 = (lim_mode == 2) ? (double)limits.f32((row - rows_off) / stride) : H[17];
+        if (s2 <= t2 * c2) {
+            it.cur = it.end;      // no other facet can be hit from here
+            return;
+        }
+    }
+    if (REDIRECTS && !it.brute) {
+        const bool ok = dn != 0.0 && s2 <= H[15] * c2;
         if (nhit >= 2 || (dn == dn && !ok)) {
             const int j = (row - rows_off) / stride;
             it.brute = true;

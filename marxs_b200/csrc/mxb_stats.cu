@@ -18,7 +18,8 @@
 
 namespace {
 
-constexpr int kBlocks = 592;      // 148 SMs x 4
+constexpr int kBlocks = 1184;     // 148 SMs x 8 CTAs of 256 threads: full occupancy
+constexpr int kUnroll = 4;        // independent 8-byte loads in flight per thread (the passes are latency bound otherwise)
 constexpr int kThreads = 256;
 
 struct ClipState {
@@ -80,12 +81,17 @@ __global__ void __launch_bounds__(kThreads) clip_count_sum(const double* __restr
     const double lo = st->lo, hi = st->hi;
     double s = 0.0;
     unsigned long long c = 0;
-    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        const double v = x[i];
-        if (alive(v, lo, hi)) {
-            s += v;
-            ++c;
-        }
+    const long long T = (long long)gridDim.x * kThreads;
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += kUnroll * T) {
+        double v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = (i + u * T < n) ? __ldg(x + i + u * T) : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (alive(v[u], lo, hi)) {
+                s += v[u];
+                ++c;
+            }
     }
     const double bs = block_sum(s, sm);
     const double bc = block_sum((double)c, sm);      // < 2^53 values per block: exact
@@ -96,14 +102,20 @@ __global__ void __launch_bounds__(kThreads) clip_count_sum(const double* __restr
 }
 
 // one block: mean, convergence test, ranks of the middle element(s)
-__global__ void clip_after_sum(ClipState* st) {
-    if (st->done || threadIdx.x) return;
+// (one warp: lane l adds the partials l, l + 32, ... in order, then a fixed shuffle tree: deterministic)
+__device__ __forceinline__ double warp_reduce_partials(const double* p) {
     double s = 0.0;
+    for (int b = threadIdx.x; b < kBlocks; b += 32) s += p[b];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    return __shfl_sync(0xffffffffu, s, 0);
+}
+__global__ void clip_after_sum(ClipState* st) {
+    if (st->done) return;
+    const double s = warp_reduce_partials(st->part_sum);
     unsigned long long c = 0;
-    for (int b = 0; b < kBlocks; ++b) {
-        s += st->part_sum[b];
-        c += st->part_cnt[b];
-    }
+    for (int b = threadIdx.x; b < kBlocks; b += 32) c += st->part_cnt[b];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (threadIdx.x) return;
     st->cnt = c;
     if (c == 0 || c == st->prev_cnt) {      // everything clipped, or the last round clipped nothing: out[] is final
         if (c == 0) {
@@ -118,7 +130,7 @@ __global__ void clip_after_sum(ClipState* st) {
     st->key[0] = st->key[1] = 0ULL;
     st->rank[0] = (c - 1) / 2;
     st->rank[1] = c / 2;
-    for (int k = 0; k < 256; ++k) st->hist[0][k] = st->hist[1][k] = 0u;
+    for (int k = 0; k < 256; ++k) st->hist[0][k] = st->hist[1][k] = 0u;      // (also zeroed by every clip_pick)
 }
 
 // pass 2: sum of squared deviations from the mean
@@ -127,12 +139,17 @@ __global__ void __launch_bounds__(kThreads) clip_m2(const double* __restrict__ x
     if (st->done) return;
     const double lo = st->lo, hi = st->hi, mean = st->mean;
     double s = 0.0;
-    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        const double v = x[i];
-        if (alive(v, lo, hi)) {
-            const double d = v - mean;
-            s = fma(d, d, s);
-        }
+    const long long T = (long long)gridDim.x * kThreads;
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += kUnroll * T) {
+        double v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = (i + u * T < n) ? __ldg(x + i + u * T) : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (alive(v[u], lo, hi)) {
+                const double d = v[u] - mean;
+                s = fma(d, d, s);
+            }
     }
     const double bs = block_sum(s, sm);
     if (threadIdx.x == 0) st->part_sum[blockIdx.x] = bs;
@@ -151,47 +168,75 @@ __global__ void __launch_bounds__(kThreads) clip_hist(const double* __restrict__
     // (shift == 56: no prefix yet; a 64-bit shift by 64 is undefined, so the mask form is used)
     const unsigned long long mask = (shift == 56) ? 0ULL : (~0ULL << (shift + 8));
     const long long n_up = (n + 31) & ~31LL;      // whole warps stay in the loop (match_any needs the full mask)
-    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n_up; i += (long long)gridDim.x * kThreads) {
-        const double v = (i < n) ? x[i] : __longlong_as_double(0x7ff8000000000000LL);
-        const bool ok = alive(v, lo, hi);
-        const unsigned long long key = order_key(v);
-        const unsigned d = (unsigned)(key >> shift) & 255u;
-        const bool in_a = ok && ((key & mask) == ka);
-        const bool in_b = ok && !same && ((key & mask) == kb);
-        // lanes of a warp that count the same bin are combined: a narrow distribution puts the whole column into one
-        // or two bins of the leading bytes
-        const unsigned tag = in_a ? d : (in_b ? 256u + d : 512u);
-        const unsigned peers = __match_any_sync(0xffffffffu, tag);
-        if (tag < 512u && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[tag >> 8][tag & 255u], (unsigned)__popc(peers));
+    const long long T = (long long)gridDim.x * kThreads;
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n_up; i += kUnroll * T) {
+        double v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = (i + u * T < n) ? __ldg(x + i + u * T) : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool ok = alive(v[u], lo, hi);
+            const unsigned long long key = order_key(v[u]);
+            const unsigned d = (unsigned)(key >> shift) & 255u;
+            const bool in_a = ok && ((key & mask) == ka);
+            const bool in_b = ok && !same && ((key & mask) == kb);
+            // lanes of a warp that count the same bin are combined: a narrow distribution puts the whole column into
+            // one or two bins of the leading bytes
+            const unsigned tag = in_a ? d : (in_b ? 256u + d : 512u);
+            const unsigned peers = __match_any_sync(0xffffffffu, tag);
+            if (tag < 512u && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
+                atomicAdd(&h[tag >> 8][tag & 255u], (unsigned)__popc(peers));
+        }
     }
     __syncthreads();
     if (h[0][threadIdx.x]) atomicAdd(&st->hist[0][threadIdx.x], h[0][threadIdx.x]);
     if (h[1][threadIdx.x]) atomicAdd(&st->hist[1][threadIdx.x], h[1][threadIdx.x]);
 }
 
-// one block: descend one byte for both middle elements
+// one warp: descend one byte for both middle elements (lane l owns bins 8l .. 8l+7; a warp scan finds the owner)
 __global__ void clip_pick(ClipState* st, int shift) {
-    if (st->done || threadIdx.x) return;
+    if (st->done) return;
+    const int lane = threadIdx.x;
     const bool same = (st->key[0] == st->key[1]);
     for (int m = 0; m < 2; ++m) {
         const unsigned* h = st->hist[(m == 1 && !same) ? 1 : 0];
-        unsigned long long r = st->rank[m], cum = 0;
-        int d = 0;
-        for (; d < 255; ++d) {
-            if (r < cum + h[d]) break;
-            cum += h[d];
+        unsigned v[8];
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = h[lane * 8 + k];
+            tot += v[k];
         }
-        st->rank[m] = r - cum;
-        st->key[m] |= (unsigned long long)d << shift;
+        unsigned long long inc = tot;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const unsigned long long exc = inc - tot, r = st->rank[m];
+        const unsigned ball = __ballot_sync(0xffffffffu, (r >= exc) && (r < inc));
+        const int owner = ball ? __ffs(ball) - 1 : 31;
+        __syncwarp();
+        if (lane == owner) {
+            unsigned long long cum = exc;
+            int d = lane * 8;
+            for (int k = 0; k < 8; ++k) {
+                d = lane * 8 + k;
+                if (r < cum + v[k] || d == 255) break;
+                cum += v[k];
+            }
+            st->rank[m] = r - cum;
+            st->key[m] |= (unsigned long long)d << shift;
+        }
+        __syncwarp();
     }
-    for (int k = 0; k < 256; ++k) st->hist[0][k] = st->hist[1][k] = 0u;
+    for (int k = lane; k < 256; k += 32) st->hist[0][k] = st->hist[1][k] = 0u;
 }
 
 // one block: results of the round, next window
 __global__ void clip_after_round(ClipState* st) {
-    if (st->done || threadIdx.x) return;
-    double m2 = 0.0;
-    for (int b = 0; b < kBlocks; ++b) m2 += st->part_sum[b];
+    if (st->done) return;
+    const double m2 = warp_reduce_partials(st->part_sum);
+    if (threadIdx.x) return;
     const double std = sqrt(m2 / (double)st->cnt);
     const double med = 0.5 * (key_value(st->key[0]) + key_value(st->key[1]));
     st->out[0] = st->mean;

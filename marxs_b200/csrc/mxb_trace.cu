@@ -497,7 +497,10 @@ mxb_trace_kernel(const __grid_constant__ TraceParams P) {
                 // after the body: photons that hit re-validate the culling cone for their NEW direction
                 const int bpc = arr_pc;
                 const OpCold& c = opc[bpc];
-                array_revalidate(arr, B + oph[bpc].pg, ph, arr_nhit, row, c.c[2], c.c[1], c.c[0], st_sm);
+                {
+                    const Ref H = B + oph[bpc].pg;      // H[18]: offset of the per-facet limit table, H[19]: certificate mode
+                    array_revalidate<true>(arr, H, B + (int)H[18], (int)H[19], ph, arr_nhit, row, c.c[2], c.c[1], c.c[0], st_sm);
+                }
                 // another search round only if some lane that hit still has facets to test
                 ctx.init_round = false;               // later rounds only store for photons that hit
                 if (__any_sync(0xffffffffu, ph.hit && arr.cur < arr.end)) {

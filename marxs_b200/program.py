@@ -130,6 +130,62 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
                 mean_candidates=float(np.mean([len(l) for l in lists if l])) if len(cand) else 0.)
 
 
+def single_hit_limits(G, grid):
+    """Per-facet disjointness certificate of a facet array (kernel side: csrc/mxb_ops.cuh array_revalidate).
+
+    t[A] = largest tangent of the angle to the array's mean normal below which a ray that starts anywhere on facet A
+    cannot reach any OTHER facet: for every pair the footprints on the mean plane are separated by gap_AB (the best of
+    the eight edge-normal axes of the two quadrilaterals: a lower bound of their distance) and their heights above the
+    plane differ by at most h_AB; a ray moves h tan(theta) sideways per height h, so it needs tan(theta) >= gap_AB / h_AB
+    to get from A to B.  t[A] = min_B gap_AB / h_AB, shrunk by 1e-9 for rounding; 0 for a facet whose footprint overlaps
+    a neighbour's (the reference's sequential "last hit wins" loop then matters and nothing is certified).
+    Returns the (F,) array of SQUARED tangents, capped at 1e6."""
+    F = G.shape[0]
+    c, ey, ez = G[:, 0:3], G[:, 6:9], G[:, 9:12]
+    Ly, Lz = G[:, 12], G[:, 13]
+    corners = np.stack([c + sy * Ly[:, None] * ey + sz * Lz[:, None] * ez
+                        for sy, sz in ((-1, -1), (1, -1), (1, 1), (-1, 1))], axis=1)          # cyclic order
+    rel = corners - grid['O']
+    h = rel @ grid['nbar']
+    q = np.stack([rel @ grid['u'], rel @ grid['v']], axis=2)                                  # (F, 4, 2)
+    edges = np.roll(q, -1, axis=1) - q
+    nrm = np.stack([edges[..., 1], -edges[..., 0]], axis=2)
+    length = np.linalg.norm(nrm, axis=2, keepdims=True)
+    if not np.all(length > 0):
+        return np.zeros(F)                                    # degenerate footprint (facet edge-on): certify nothing
+    nrm = nrm / length
+    hlo, hhi = h.min(axis=1), h.max(axis=1)
+    t = np.full(F, np.inf)
+    idx = np.arange(F)
+    for a0 in range(0, F, 256):                               # blocks of facets: (256, 4, F, 4) projections at a time
+        a1 = min(F, a0 + 256)
+        proj = np.einsum('akx,bmx->akbm', nrm[a0:a1], q)
+        lo, hi = proj.min(axis=3), proj.max(axis=3)           # (A, 4, F)
+        own = np.einsum('akx,amx->akm', nrm[a0:a1], q[a0:a1])
+        own_lo, own_hi = own.min(axis=2), own.max(axis=2)     # (A, 4)
+        sep = np.maximum(lo - own_hi[:, :, None], own_lo[:, :, None] - hi).max(axis=1)        # axes of A: (A, F)
+        gap = np.maximum(sep, 0.)
+        hd = np.maximum(hhi[a0:a1, None] - hlo[None, :], hhi[None, :] - hlo[a0:a1, None])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            lim = np.where(hd > 0, gap / hd, np.inf)
+        lim[idx[a0:a1] - a0, idx[a0:a1]] = np.inf             # a facet against itself
+        # the pair's separation is the better of both facets' axes: lim_AB = max(lim via A's axes, via B's axes)
+        # (kept conservative here: each facet uses only its own axes for its row and the pair minimum below)
+        t[a0:a1] = np.minimum(t[a0:a1], lim.min(axis=1))
+    t = np.where(np.isfinite(t), t, 1e3) * (1. - 1e-9)
+    return np.minimum(t * t, 1e6)
+
+
+def _pack_f32_down(a):
+    """float32 values not larger than the float64 ones, packed into float64 words"""
+    a = np.asarray(a, dtype=np.float64)
+    f = a.astype(np.float32)
+    f = np.where(f.astype(np.float64) > a, np.nextafter(f, np.float32(0)), f).astype(np.float32)
+    if len(f) % 2:
+        f = np.concatenate([f, np.zeros(1, np.float32)])
+    return f.view(np.float64)
+
+
 def _pack_i32(a):
     a = np.ascontiguousarray(a, dtype=np.int32)
     if len(a) % 2:
@@ -494,6 +550,13 @@ class Lowering:
             ints[4], ints[5] = grid['nu'], grid['nv']
             ints[6] = self.params(_pack_i32(grid['start']))
             ints[7] = self.params(_pack_i32(grid['cand']))
+            # disjointness certificate: head[17] array-wide limit, head[18] per-facet table, head[19] mode
+            lim2 = single_hit_limits(G, grid)
+            if lim2.min() > 0.:
+                head[17], head[19] = float(lim2.min()), 1.
+            elif (lim2 > 0.).any():
+                head[18], head[19] = float(self.params(_pack_f32_down(lim2))), 2.
+            grid['single_hit_limit2'] = lim2
         init = a['init']
         init_off = self.params(_pack_i32(init)) if init else 0
         begin = self.ops[a['begin']]

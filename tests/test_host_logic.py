@@ -272,6 +272,54 @@ def test_cull_grid_is_conservative(case):
     assert g['mean_candidates'] < 6
 
 
+@pytest.mark.parametrize('case', ['hetg', 'random', 'staggered', 'overlapping'])
+def test_single_hit_certificate_is_conservative(case):
+    """program.single_hit_limits: a ray that starts ON facet A with tan(angle to the mean normal) below t[A] hits no
+    other facet (oracle arithmetic, rays in both directions); facets that overlap a neighbour are certified nothing."""
+    rng = np.random.default_rng(7)
+    if case == 'hetg':
+        elems = chandra.HETG().elements
+    elif case == 'random':
+        elems = [optics.FlatDetector(position=[rng.uniform(-5, 5), 25. * (k % 8) + rng.uniform(-2, 2), 25. * (k // 8) + rng.uniform(-2, 2)],
+                                     orientation=affines.axangle2mat(rng.normal(size=3), rng.uniform(0, 0.08)),
+                                     zoom=[1, rng.uniform(3, 9), rng.uniform(3, 9)]) for k in range(48)]
+    elif case == 'staggered':      # two layers 30 mm apart, laterally interleaved: small gaps against large height steps
+        elems = [optics.FlatDetector(position=[30. * (k % 2), 11. * k, 0.], zoom=[1, 5., 20.]) for k in range(12)]
+    else:
+        elems = [optics.FlatDetector(position=[2. * k, 8. * k, 0.], zoom=[1, 5., 20.]) for k in range(6)]
+    G = np.array([program.geom14(e.pos4d) for e in elems])
+    g = program.build_cull_grid(G)
+    assert g is not None
+    t2 = program.single_hit_limits(G, g)
+    if case == 'overlapping':
+        assert np.all(t2 == 0.)
+        return
+    assert (t2 > 0).all() and np.all(np.isfinite(t2))
+    if case == 'staggered':
+        assert np.sqrt(t2.max()) < 0.05          # 1 mm gaps / 30 mm steps
+    per = 400
+    F = len(G)
+    a = np.repeat(np.arange(F), per)
+    n = len(a)
+    ly, lz = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    start = G[a, 0:3] + (ly * G[a, 12])[:, None] * G[a, 6:9] + (lz * G[a, 13])[:, None] * G[a, 9:12]
+    t = np.sqrt(t2[a]) * rng.uniform(0, 1, n) ** 0.25 * 0.999999           # biased towards the limit
+    t = np.minimum(t, 50.)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    d = g['nbar'] + t[:, None] * (np.cos(phi)[:, None] * g['u'] + np.sin(phi)[:, None] * g['v'])
+    d *= rng.choice([-1., 1.], n)[:, None] * rng.uniform(0.5, 2, n)[:, None]
+    pos = np.ones((n, 4))
+    pos[:, :3] = start
+    dirs = np.zeros((n, 4))
+    dirs[:, :3] = d
+    for j in range(F):
+        hit, _, _ = mo.plane_intersect(mo.PlaneConsts(elems[j].pos4d), dirs, pos)
+        assert not np.any(hit & (a != j)), (case, j)
+    # the packed float32 table never exceeds the float64 limits
+    packed = program._pack_f32_down(t2).view(np.float32)[:F].astype(np.float64)
+    assert np.all(packed <= t2) and np.all(packed >= t2 * (1 - 1e-6))
+
+
 # ---------------------------------------------------------------------------
 # later additions: row hoisting, plan-cache digest, sources / pointing host logic
 # ---------------------------------------------------------------------------
