@@ -537,7 +537,7 @@ struct Gen {
         // disjointness certificate (mxb_ops.cuh array_revalidate): mode and table offset are structure
         const int lim_mode = (mode == 1 && range_ok(o.pg, 20)) ? baked(o.pg + 19) : 0;
         const int lim_off = lim_mode == 2 ? baked(o.pg + 18) : 0;
-        if (lim_mode == 2 && !range_ok(lim_off, (nF + 1) / 2)) return fail("certificate table outside the blob");
+        if (lim_mode == 2 && !range_ok(lim_off, (nF + 2) / 2)) return fail("certificate table outside the blob");
         out("            // ---- ops %d..%d: array of %d facets, stride %d, mode %d (%d x %d cells)", pc, end_pc, nF, stride, mode, nu, nv);
         out("            {");
         out("            ArrayIter it;");

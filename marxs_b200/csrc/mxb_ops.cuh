@@ -70,10 +70,6 @@ struct PRef {
         if (STAGED) return reinterpret_cast<const double2*>(g_smem + off)[k];
         return __ldg(reinterpret_cast<const double2*>(g + off) + k);
     }
-    MXB_DEV float f32(int k) const {  // packed float32 view of the words at off
-        if (STAGED) return reinterpret_cast<const float*>(g_smem)[2 * off + k];
-        return __ldg(reinterpret_cast<const float*>(g) + 2 * (long long)off + k);
-    }
     MXB_DEV int i32(int k) const {  // packed int32 view of the words at off
         if (STAGED) return reinterpret_cast<const int*>(g_smem)[2 * off + k];
         return __ldg(reinterpret_cast<const int*>(g) + 2 * (long long)off + k);
@@ -1029,14 +1025,16 @@ MXB_DEV bool array_search(ArrayIter& it, BP B, HP H, IP cell_start, IP cand, int
 }
 
 // after the body, for photons that hit:
-// (1) DISJOINTNESS CERTIFICATE.  The lowering computes for every facet A the largest tangent t_A (angle to the array's
-//     mean normal) below which a ray that starts anywhere on A cannot reach any OTHER facet of the array: for each pair
-//     the footprints on the mean plane are separated by gap_AB (separating-axis test), the facets' heights differ by at
-//     most h_AB, and a ray travels at most h_AB tan(theta) sideways while it changes height by h_AB, so
-//     t_A = min_B gap_AB / h_AB (0 when A overlaps a neighbour).  A photon that leaves A inside that cone is DONE with
-//     the array: the reference's remaining facets (simulator.py:42-49) would all miss it, so they are not tested, and a
-//     steep diffraction order does not have to walk the footprint scan.  lim_mode 1: H[17] = min_A t_A^2 (every facet);
-//     2: per-facet t_A^2 as float32 (rounded down) at `limits`; 0: no certificate (overlapping arrays).
+// (1) DISJOINTNESS CERTIFICATE (program.py single_hit_successors).  The lowering computes for every pair of facets
+//     A < B the smallest tangent (angle to the array's mean normal) a ray needs to get from any point of A to B: the
+//     footprints on the mean plane are separated by gap_AB (separating-axis test), the heights differ by at most h_AB,
+//     and a ray travels h tan(theta) sideways per height h, so it needs tan(theta) >= gap_AB / h_AB.  Inside the cone
+//     tan^2 <= H[17] a photon that leaves facet A can therefore only reach A's short SUCCESSOR list (later facets with
+//     a smaller limit: none for the facets of a tiled array, the overlapping diagonal neighbours of a ring-placed
+//     one).  lim_mode 1: every list is empty - the photon is DONE with the array; 2: the search continues over the
+//     successors only (`limits`: int32 list starts per facet, indexing into the candidate array).  Either way the
+//     reference's remaining facets (simulator.py:42-49) would all miss, so they are not tested and a steep diffraction
+//     order does not walk the footprint scan.  0: no certificate.
 // (2) otherwise, when the body can redirect photons, the culling cone is re-validated for the NEW direction: the cell
 //     list covers ONE redirection inside the cone (H t + 2 H t' <= margin); a second hit or a steep new direction
 //     falls back to the footprint scan over the remaining facets
@@ -1052,12 +1050,17 @@ MXB_DEV void array_revalidate(ArrayIter& it, HP H, LP limits, int lim_mode, cons
     const double dn = dot(ph.dir, nb);
     const double d2 = (kTrackUnit && ph.unit) ? 1.0 : dot(ph.dir, ph.dir);
     const double c2 = dn * dn, s2 = d2 - c2;          // tan^2 = s2 / c2; NaN fails every comparison below
-    if (lim_mode) {
-        const double t2 = (lim_mode == 2) ? (double)limits.f32((row - rows_off) / stride) : H[17];
-        if (s2 <= t2 * c2) {
+    if (lim_mode && s2 <= H[17] * c2) {
+        if (lim_mode == 2) {      // only this facet's successors can still be hit: an ordinary (short) candidate list
+            const int j = (row - rows_off) / stride;
+            it.brute = false;
+            it.seg = false;
+            it.cur = limits.i32(j);
+            it.end = limits.i32(j + 1);
+        } else {
             it.cur = it.end;      // no other facet can be hit from here
-            return;
         }
+        return;
     }
     if (REDIRECTS && !it.brute) {
         const bool ok = dn != 0.0 && s2 <= H[15] * c2;

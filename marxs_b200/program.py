@@ -63,7 +63,7 @@ def geom14(pos4d):
     return out
 
 
-def build_cull_grid(G, tan_max=0.12, max_cells=4096):
+def build_cull_grid(G, tan_max=0.12, max_cells=4096, hops=2):
     """Conservative 2-D culling grid for an array of rectangles.
 
     G : (F, 14) facet geometry rows.  Returns None when a grid is not worthwhile
@@ -74,7 +74,11 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
     With H = max height of any facet point above the plane, a ray inside the cone
     tan(theta) <= margin / (3 H) cannot hit a facet that is not listed in its
     cell, even after ONE redirection inside the same cone (H t + 2 H t' <= margin).
-    The kernel checks the cone per photon and falls back to brute force outside.
+    The kernel checks the cone per photon and falls back to the footprint scan outside.
+
+    ``hops`` = 2 covers that redirection (margin = 3 H tan_max); ``hops`` = 0 (margin = H tan_max, a third of the
+    inflation) is valid for the INCOMING ray only and is used when the disjointness certificate guarantees that a photon
+    never continues through its cell list after a hit (``single_hit_successors`` with a cone at least this wide).
     """
     F = G.shape[0]
     if F < 3:
@@ -100,8 +104,8 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
     H = float(np.abs(h).max())
     extent = float(max(np.ptp(pu), np.ptp(pv), 1e-12))
     slack = 1e-6 + 1e-9 * extent
-    margin = 3.0 * H * tan_max + slack
-    T2 = min(((margin - slack) / (3.0 * H)) ** 2, 1e12) if H > 0 else 1e12
+    margin = (1.0 + hops) * H * tan_max + slack
+    T2 = min(((margin - slack) / ((1.0 + hops) * H)) ** 2, 1e12) if H > 0 else 1e12
     lo_u, hi_u = pu.min(axis=1) - margin, pu.max(axis=1) + margin
     lo_v, hi_v = pv.min(axis=1) - margin, pv.max(axis=1) + margin
     u0, v0 = float(lo_u.min()), float(lo_v.min())
@@ -130,16 +134,15 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096):
                 mean_candidates=float(np.mean([len(l) for l in lists if l])) if len(cand) else 0.)
 
 
-def single_hit_limits(G, grid):
-    """Per-facet disjointness certificate of a facet array (kernel side: csrc/mxb_ops.cuh array_revalidate).
+def facet_reach_limits(G, grid):
+    """(F, F) matrix L of a facet array: L[A, B] (B > A) = smallest tangent of the angle to the array's mean normal a
+    ray needs to get from ANY point of facet A to facet B; inf for B <= A (the reference loops the facets in order and
+    never returns to an earlier one, simulator.py:42-49).
 
-    t[A] = largest tangent of the angle to the array's mean normal below which a ray that starts anywhere on facet A
-    cannot reach any OTHER facet: for every pair the footprints on the mean plane are separated by gap_AB (the best of
-    the eight edge-normal axes of the two quadrilaterals: a lower bound of their distance) and their heights above the
-    plane differ by at most h_AB; a ray moves h tan(theta) sideways per height h, so it needs tan(theta) >= gap_AB / h_AB
-    to get from A to B.  t[A] = min_B gap_AB / h_AB, shrunk by 1e-9 for rounding; 0 for a facet whose footprint overlaps
-    a neighbour's (the reference's sequential "last hit wins" loop then matters and nothing is certified).
-    Returns the (F,) array of SQUARED tangents, capped at 1e6."""
+    The footprints of A and B on the mean plane are separated by gap_AB (the best of the four edge-normal axes of A's
+    quadrilateral: a lower bound of their distance), their heights above the plane differ by at most h_AB, and a ray
+    moves h tan(theta) sideways per height h: L = gap_AB / h_AB, shrunk by 1e-9 for rounding; 0 where the footprints
+    overlap.  Kernel side: csrc/mxb_ops.cuh array_revalidate (successor lists / single-hit stop)."""
     F = G.shape[0]
     c, ey, ez = G[:, 0:3], G[:, 6:9], G[:, 9:12]
     Ly, Lz = G[:, 12], G[:, 13]
@@ -151,39 +154,52 @@ def single_hit_limits(G, grid):
     edges = np.roll(q, -1, axis=1) - q
     nrm = np.stack([edges[..., 1], -edges[..., 0]], axis=2)
     length = np.linalg.norm(nrm, axis=2, keepdims=True)
+    idx = np.arange(F)
+    later = idx[None, :] > idx[:, None]
     if not np.all(length > 0):
-        return np.zeros(F)                                    # degenerate footprint (facet edge-on): certify nothing
+        return np.where(later, 0., np.inf)                    # degenerate footprint (facet edge-on): nothing is known
     nrm = nrm / length
     hlo, hhi = h.min(axis=1), h.max(axis=1)
-    t = np.full(F, np.inf)
-    idx = np.arange(F)
+    L = np.empty((F, F))
     for a0 in range(0, F, 256):                               # blocks of facets: (256, 4, F, 4) projections at a time
         a1 = min(F, a0 + 256)
         proj = np.einsum('akx,bmx->akbm', nrm[a0:a1], q)
         lo, hi = proj.min(axis=3), proj.max(axis=3)           # (A, 4, F)
         own = np.einsum('akx,amx->akm', nrm[a0:a1], q[a0:a1])
         own_lo, own_hi = own.min(axis=2), own.max(axis=2)     # (A, 4)
-        sep = np.maximum(lo - own_hi[:, :, None], own_lo[:, :, None] - hi).max(axis=1)        # axes of A: (A, F)
+        sep = np.maximum(lo - own_hi[:, :, None], own_lo[:, :, None] - hi).max(axis=1)        # (A, F)
         gap = np.maximum(sep, 0.)
         hd = np.maximum(hhi[a0:a1, None] - hlo[None, :], hhi[None, :] - hlo[a0:a1, None])
         with np.errstate(divide='ignore', invalid='ignore'):
-            lim = np.where(hd > 0, gap / hd, np.inf)
-        lim[idx[a0:a1] - a0, idx[a0:a1]] = np.inf             # a facet against itself
-        # the pair's separation is the better of both facets' axes: lim_AB = max(lim via A's axes, via B's axes)
-        # (kept conservative here: each facet uses only its own axes for its row and the pair minimum below)
-        t[a0:a1] = np.minimum(t[a0:a1], lim.min(axis=1))
-    t = np.where(np.isfinite(t), t, 1e3) * (1. - 1e-9)
-    return np.minimum(t * t, 1e6)
+            L[a0:a1] = np.where(hd > 0, gap / hd, np.inf)
+    L = np.where(np.isfinite(L), L * (1. - 1e-9), L)
+    L[~later] = np.inf
+    return L
 
 
-def _pack_f32_down(a):
-    """float32 values not larger than the float64 ones, packed into float64 words"""
-    a = np.asarray(a, dtype=np.float64)
-    f = a.astype(np.float32)
-    f = np.where(f.astype(np.float64) > a, np.nextafter(f, np.float32(0)), f).astype(np.float32)
-    if len(f) % 2:
-        f = np.concatenate([f, np.zeros(1, np.float32)])
-    return f.view(np.float64)
+def single_hit_successors(G, grid, t_big=1.0, max_succ=8):
+    """Disjointness certificate of a facet array.  Returns (t2, start, succ):
+
+    * within the cone tan^2 <= t2 around the mean normal, a photon that leaves facet A can only reach the LATER facets
+      succ[start[A]:start[A + 1]] (ascending) - none for most facets of a tiled array, the overlapping diagonal
+      neighbours of a ring-placed one.  The kernel tests exactly those instead of the rest of the candidate list or the
+      footprint scan; results equal the reference's loop over all facets by construction.
+    * succ is None when no facet has a successor inside the cone (then t2 is as large as the geometry allows).
+    * (0., None, None): nothing can be certified."""
+    L = facet_reach_limits(G, grid)
+    F = G.shape[0]
+    finite = L[np.isfinite(L)]
+    t_min = float(finite.min()) if finite.size else 1e3
+    if t_min >= 0.3:                        # no pair closer than 17 degrees: one number for the array, no lists
+        return min(t_min, 1e3) ** 2, None, None
+    for t in (t_big, 0.3):
+        within = L <= t
+        if within.sum(axis=1).max() <= max_succ:
+            start = np.zeros(F + 1, dtype=np.int64)
+            start[1:] = np.cumsum(within.sum(axis=1))
+            succ = np.nonzero(within)[1]                      # row-major: ascending within each facet
+            return t * t, start, succ
+    return 0., None, None
 
 
 def _pack_i32(a):
@@ -548,15 +564,25 @@ class Lowering:
             head[16] = grid['H'] * (1. + 1e-9) + 1e-6      # half thickness of the slab that holds every facet point
             ints[3] = 1
             ints[4], ints[5] = grid['nu'], grid['nv']
+            # disjointness certificate: head[17] = tan^2 of its cone, head[19] mode (1: every facet is the last one a
+            # photon can hit; 2: successor lists), head[18] = offset of the per-facet list starts (int32, F + 1), which
+            # index into the candidate array (the lists are appended to the grid's)
+            t2, sstart, succ = single_hit_successors(G, grid)
+            if t2 >= grid['T2']:
+                # after a hit the photon is either inside the certified cone (done / successors) or outside the culling
+                # cone (footprint scan): it never walks on through its cell list, so the list only has to be complete
+                # for the incoming ray
+                grid = build_cull_grid(G, hops=0)
+            cand_all = grid['cand']
+            if t2 > 0. and succ is None:
+                head[17], head[19] = t2, 1.
+            elif t2 > 0.:
+                head[17], head[19] = t2, 2.
+                head[18] = float(self.params(_pack_i32(sstart + len(cand_all))))
+                cand_all = np.concatenate([cand_all, succ])
             ints[6] = self.params(_pack_i32(grid['start']))
-            ints[7] = self.params(_pack_i32(grid['cand']))
-            # disjointness certificate: head[17] array-wide limit, head[18] per-facet table, head[19] mode
-            lim2 = single_hit_limits(G, grid)
-            if lim2.min() > 0.:
-                head[17], head[19] = float(lim2.min()), 1.
-            elif (lim2 > 0.).any():
-                head[18], head[19] = float(self.params(_pack_f32_down(lim2))), 2.
-            grid['single_hit_limit2'] = lim2
+            ints[7] = self.params(_pack_i32(cand_all))
+            grid['single_hit'] = (t2, sstart, succ)
         init = a['init']
         init_off = self.params(_pack_i32(init)) if init else 0
         begin = self.ops[a['begin']]

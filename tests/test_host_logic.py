@@ -228,11 +228,13 @@ def test_selector_tables():
 
 
 # ---- culling grid ---------------------------------------------------------------------
-@pytest.mark.parametrize('case', ['hetg', 'random'])
+@pytest.mark.parametrize('case', ['hetg', 'random', 'hetg-incoming-only'])
 def test_cull_grid_is_conservative(case):
-    """Every facet a ray inside the validity cone hits (oracle arithmetic) is listed in its cell."""
+    """Every facet a ray inside the validity cone hits (oracle arithmetic) is listed in its cell (also for the tighter
+    grid that only has to serve the incoming ray, hops=0)."""
     rng = np.random.default_rng(5)
-    if case == 'hetg':
+    hops = 0 if case == 'hetg-incoming-only' else 2
+    if case.startswith('hetg'):
         elems = chandra.HETG().elements
     else:
         F = 60
@@ -240,8 +242,10 @@ def test_cull_grid_is_conservative(case):
                                      orientation=affines.axangle2mat(rng.normal(size=3), rng.uniform(0, 0.08)),
                                      zoom=[1, rng.uniform(3, 9), rng.uniform(3, 9)]) for _ in range(F)]
     G = np.array([program.geom14(e.pos4d) for e in elems])
-    g = program.build_cull_grid(G)
+    g = program.build_cull_grid(G, hops=hops)
     assert g is not None
+    if hops == 0:
+        assert g['margin'] < 0.4 * program.build_cull_grid(G)['margin'] and np.isclose(g['T2'], 0.12 ** 2)
     n = 60000
     # rays through random points of the array, directions inside the cone around nbar
     target = G[rng.integers(0, len(G), n), :3] + rng.uniform(-20, 20, (n, 3))
@@ -272,10 +276,11 @@ def test_cull_grid_is_conservative(case):
     assert g['mean_candidates'] < 6
 
 
-@pytest.mark.parametrize('case', ['hetg', 'random', 'staggered', 'overlapping'])
+@pytest.mark.parametrize('case', ['hetg', 'random', 'staggered', 'overlapping', 'rowland'])
 def test_single_hit_certificate_is_conservative(case):
-    """program.single_hit_limits: a ray that starts ON facet A with tan(angle to the mean normal) below t[A] hits no
-    other facet (oracle arithmetic, rays in both directions); facets that overlap a neighbour are certified nothing."""
+    """program.single_hit_successors: inside the certified cone a ray that starts ON facet A hits no LATER facet that
+    is not in A's successor list (oracle arithmetic, rays in both directions; earlier facets are never revisited by
+    the reference's loop).  Tiled arrays get empty lists and a wide cone, overlapping neighbours become successors."""
     rng = np.random.default_rng(7)
     if case == 'hetg':
         elems = chandra.HETG().elements
@@ -285,39 +290,53 @@ def test_single_hit_certificate_is_conservative(case):
                                      zoom=[1, rng.uniform(3, 9), rng.uniform(3, 9)]) for k in range(48)]
     elif case == 'staggered':      # two layers 30 mm apart, laterally interleaved: small gaps against large height steps
         elems = [optics.FlatDetector(position=[30. * (k % 2), 11. * k, 0.], zoom=[1, 5., 20.]) for k in range(12)]
-    else:
+    elif case == 'overlapping':
         elems = [optics.FlatDetector(position=[2. * k, 8. * k, 0.], zoom=[1, 5., 20.]) for k in range(6)]
+    else:                          # ring-placed facets of a Rowland array: diagonal neighbours overlap in projection
+        from marxs_b200.design import RowlandTorus, GratingArrayStructure
+        gas = GratingArrayStructure(rowland=RowlandTorus(6000., 6000.), d_element=[30., 30.], radius=[300., 420.],
+                                    elem_class=optics.FlatGrating,
+                                    elem_args={'zoom': [1, 13.5, 13.5], 'd': 2e-4, 'order_selector': optics.OrderSelector([0])})
+        elems = gas.elements
     G = np.array([program.geom14(e.pos4d) for e in elems])
     g = program.build_cull_grid(G)
     assert g is not None
-    t2 = program.single_hit_limits(G, g)
-    if case == 'overlapping':
-        assert np.all(t2 == 0.)
-        return
-    assert (t2 > 0).all() and np.all(np.isfinite(t2))
-    if case == 'staggered':
-        assert np.sqrt(t2.max()) < 0.05          # 1 mm gaps / 30 mm steps
-    per = 400
+    t2, start, succ = program.single_hit_successors(G, g)
     F = len(G)
+    assert t2 > 0.
+    if case in ('hetg', 'random'):
+        assert succ is None and t2 > 0.09                  # tiled: every facet is the last one a photon can hit
+    else:
+        assert succ is not None and len(start) == F + 1 and start[-1] == len(succ)
+        for a in range(F):
+            lst = succ[start[a]:start[a + 1]]
+            assert np.all(lst > a) and np.all(np.diff(lst) > 0)
+        if case == 'overlapping':
+            assert [list(succ[start[a]:start[a + 1]]) for a in range(F)][:2] == [[1], [2]]
+        if case == 'rowland':
+            assert 0 < (np.diff(start) > 0).sum() < F and np.diff(start).max() <= 4
+    lists = [set() if succ is None else set(int(x) for x in succ[start[a]:start[a + 1]]) for a in range(F)]
+    per = 400 if F < 100 else 120
     a = np.repeat(np.arange(F), per)
     n = len(a)
     ly, lz = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
-    start = G[a, 0:3] + (ly * G[a, 12])[:, None] * G[a, 6:9] + (lz * G[a, 13])[:, None] * G[a, 9:12]
-    t = np.sqrt(t2[a]) * rng.uniform(0, 1, n) ** 0.25 * 0.999999           # biased towards the limit
-    t = np.minimum(t, 50.)
+    start_pt = G[a, 0:3] + (ly * G[a, 12])[:, None] * G[a, 6:9] + (lz * G[a, 13])[:, None] * G[a, 9:12]
+    t = np.sqrt(t2) * rng.uniform(0, 1, n) ** 0.25 * 0.999999             # biased towards the edge of the cone
     phi = rng.uniform(0, 2 * np.pi, n)
     d = g['nbar'] + t[:, None] * (np.cos(phi)[:, None] * g['u'] + np.sin(phi)[:, None] * g['v'])
     d *= rng.choice([-1., 1.], n)[:, None] * rng.uniform(0.5, 2, n)[:, None]
     pos = np.ones((n, 4))
-    pos[:, :3] = start
+    pos[:, :3] = start_pt
     dirs = np.zeros((n, 4))
     dirs[:, :3] = d
+    later_hits = 0
     for j in range(F):
         hit, _, _ = mo.plane_intersect(mo.PlaneConsts(elems[j].pos4d), dirs, pos)
-        assert not np.any(hit & (a != j)), (case, j)
-    # the packed float32 table never exceeds the float64 limits
-    packed = program._pack_f32_down(t2).view(np.float32)[:F].astype(np.float64)
-    assert np.all(packed <= t2) and np.all(packed >= t2 * (1 - 1e-6))
+        for i in np.nonzero(hit & (a < j))[0]:
+            assert j in lists[a[i]], (case, int(a[i]), j)
+            later_hits += 1
+    if case in ('overlapping', 'rowland', 'staggered'):
+        assert later_hits > 0          # the lists are exercised, not vacuous
 
 
 # ---------------------------------------------------------------------------
