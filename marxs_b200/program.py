@@ -559,11 +559,6 @@ class Lowering:
         rows_off = self.params(rows)
         ints = [F, stride, rows_off, 0, 0, 0, 0, 0]
         if grid is not None:
-            head[0:3], head[3:6], head[6:9], head[9:12] = grid['O'], grid['nbar'], grid['u'], grid['v']
-            head[12], head[13], head[14], head[15] = grid['u0'], grid['v0'], grid['inv_cell'], grid['T2']
-            head[16] = grid['H'] * (1. + 1e-9) + 1e-6      # half thickness of the slab that holds every facet point
-            ints[3] = 1
-            ints[4], ints[5] = grid['nu'], grid['nv']
             # disjointness certificate: head[17] = tan^2 of its cone, head[19] mode (1: every facet is the last one a
             # photon can hit; 2: successor lists), head[18] = offset of the per-facet list starts (int32, F + 1), which
             # index into the candidate array (the lists are appended to the grid's)
@@ -571,8 +566,13 @@ class Lowering:
             if t2 >= grid['T2']:
                 # after a hit the photon is either inside the certified cone (done / successors) or outside the culling
                 # cone (footprint scan): it never walks on through its cell list, so the list only has to be complete
-                # for the incoming ray
+                # for the incoming ray (same frame O, nbar, u, v; finer inflation, hence other cells)
                 grid = build_cull_grid(G, hops=0)
+            head[0:3], head[3:6], head[6:9], head[9:12] = grid['O'], grid['nbar'], grid['u'], grid['v']
+            head[12], head[13], head[14], head[15] = grid['u0'], grid['v0'], grid['inv_cell'], grid['T2']
+            head[16] = grid['H'] * (1. + 1e-9) + 1e-6      # half thickness of the slab that holds every facet point
+            ints[3] = 1
+            ints[4], ints[5] = grid['nu'], grid['nv']
             cand_all = grid['cand']
             if t2 > 0. and succ is None:
                 head[17], head[19] = t2, 1.

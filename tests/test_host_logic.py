@@ -160,6 +160,21 @@ def test_program_encoding_c2():
     rows = b[rows_off:rows_off + F * stride].reshape(F, stride)
     np.testing.assert_array_equal(rows[:, :14], np.array([program.geom14(e.pos4d) for e in chandra.HETG().elements]))
     assert list(rows[:, prog.ops[5]['w15']].astype(int)) == list(range(336))       # facet id_num per row
+    # the array header describes the SAME grid the cell lists were built for (the certificate makes the lowering
+    # rebuild the grid with a smaller margin: frame, origin, cell size and lists must come from one build), and the
+    # blob's lists are that grid's
+    for pc, n_fac in ((4, 336), (7, 6)):
+        o = prog.ops[pc]
+        H = b[o['pg']:o['pg'] + program.ARRAY_HEADER_WORDS]
+        G = b[o['cols'][2]:o['cols'][2] + n_fac * o['cols'][1]].reshape(n_fac, o['cols'][1])[:, :14]
+        ref_grid = program.build_cull_grid(G, hops=0)           # both arrays are certified beyond the culling cone
+        assert H[19] == 1. and H[17] > H[15] == ref_grid['T2']
+        assert (o['cols'][4], o['cols'][5]) == (ref_grid['nu'], ref_grid['nv'])
+        np.testing.assert_array_equal(H[12:15], [ref_grid['u0'], ref_grid['v0'], ref_grid['inv_cell']])
+        start = b[o['cols'][6]:o['cols'][6] + (ref_grid['nu'] * ref_grid['nv'] + 2) // 2].view(np.int32)[:ref_grid['nu'] * ref_grid['nv'] + 1]
+        np.testing.assert_array_equal(start, ref_grid['start'])
+        cand = b[o['cols'][7]:o['cols'][7] + (len(ref_grid['cand']) + 1) // 2].view(np.int32)[:len(ref_grid['cand'])]
+        np.testing.assert_array_equal(cand, ref_grid['cand'])
     # 'y' is first written (and initialised) by the HRMA stack, later overwritten by ACIS sky y
     ycol = prog.out_f64.index('y') + program.FIRST_OUT
     assert prog.ops[0]['cols'][5] == ycol + COL_INIT and prog.ops[8]['cols'][7] == ycol
