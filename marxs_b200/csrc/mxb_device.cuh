@@ -395,7 +395,12 @@ MXB_DEV double interp_clamped(P xp, P fp, int n, double x) {
     if (x <= x_lo) return fp[0];
     int lo = 0, hi = n - 1;  // invariant xp[lo] <= x < xp[hi]
     bool found = false;
-    if (GUESS && n >= 8) {
+#ifdef MXB_NO_INTERP_SEARCH
+    constexpr bool kGuess = false;
+#else
+    constexpr bool kGuess = GUESS;
+#endif
+    if (kGuess && n >= 8) {
         int g = (int)((x - x_lo) * fast_rcp(x_hi - x_lo) * (double)(n - 1));
         g = g < 1 ? 1 : (g > n - 3 ? n - 3 : g);
         const double k0 = xp[g - 1], k1 = xp[g], k2 = xp[g + 1], k3 = xp[g + 2];      // independent loads

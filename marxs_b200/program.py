@@ -14,6 +14,8 @@ so programs are re-lowered per call and cached by the hash of their blob.
 import ctypes
 from collections import OrderedDict
 
+import os
+
 import numpy as np
 import torch
 
@@ -61,6 +63,12 @@ def geom14(pos4d):
     out[12] = np.linalg.norm(p[:, 1])
     out[13] = np.linalg.norm(p[:, 2])
     return out
+
+
+# Verification switch (tests): lower every facet array WITHOUT culling grid and disjointness certificate, i.e. every
+# photon is tested against every facet in order like the reference's loop.  Same arithmetic per facet, so the results
+# must equal the culled search bit for bit.  Part of the plan-cache key (simulator._lower_run, source._run_born).
+EXHAUSTIVE_SEARCH = False
 
 
 def build_cull_grid(G, tan_max=0.12, max_cells=4096, hops=2):
@@ -518,6 +526,7 @@ class Lowering:
         a['ids'].append(a['id_num'])
 
     def end_array(self, cull=True):
+        cull = cull and not EXHAUSTIVE_SEARCH
         a = self.array
         F = len(a['rows'])
         nper = len(a['rows'][0]) if F else 0
@@ -563,7 +572,7 @@ class Lowering:
             # photon can hit; 2: successor lists), head[18] = offset of the per-facet list starts (int32, F + 1), which
             # index into the candidate array (the lists are appended to the grid's)
             t2, sstart, succ = single_hit_successors(G, grid)
-            if t2 >= grid['T2']:
+            if t2 >= grid['T2'] and os.environ.get('MXB_GRID_HOPS', '0') == '0':      # (env: A/B switch)
                 # after a hit the photon is either inside the certified cone (done / successors) or outside the culling
                 # cone (footprint scan): it never walks on through its cell list, so the list only has to be complete
                 # for the incoming ray (same frame O, nbar, u, v; finer inflation, hence other cells)

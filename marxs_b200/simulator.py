@@ -14,6 +14,7 @@ from .affines import decompose44
 from .base import SimulationSequenceElement, _parse_position_keywords
 from .geometry import Geometry
 from .program import Lowering, NotFusable
+from . import program as _program
 from . import rng
 
 __all__ = ['SimulationSetupError', 'BaseContainer', 'Sequence', 'Parallel', 'ParallelCalculated',
@@ -162,7 +163,7 @@ def _lower_run(elements, i, photons):
     pins = []
     if use_cache:
         try:
-            key = fingerprint(elements[i:], (tuple(photons.colnames), photons.meta), pins)
+            key = fingerprint(elements[i:], (tuple(photons.colnames), photons.meta, _program.EXHAUSTIVE_SEARCH), pins)
         except Uncacheable:
             use_cache = False
     if use_cache:

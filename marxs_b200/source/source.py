@@ -14,6 +14,7 @@ import torch
 from ..base import SimulationSequenceElement, _parse_position_keywords
 from ..photons import PhotonBatch
 from ..program import Lowering, NotFusable
+from .. import program as _program
 from .. import rng as _rng
 
 __all__ = ['Source', 'PointSource', 'LabPointSourceCone', 'FarLabPointSource', 'FixedPointing', 'JitterPointing',
@@ -460,7 +461,7 @@ def _run_born(elements, photons, check=True, given=()):
     from ..simulator import fingerprint, Uncacheable
     pins = []
     try:
-        key = fingerprint(elements, ('born', photons.meta, tuple(given)), pins)
+        key = fingerprint(elements, ('born', photons.meta, tuple(given), _program.EXHAUSTIVE_SEARCH), pins)
     except Uncacheable:
         key = None
     prog = _born_cache.get(key, (None,))[0] if key is not None else None
