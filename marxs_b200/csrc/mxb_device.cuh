@@ -384,37 +384,15 @@ MXB_DEV_BIG V3 axangle_rotate_T(const V3& axis, double angle, const V3& v) {
     return rotate_T_sc<PERP, AXIS_UNIT>(axis, s, c, v);
 }
 
-// np.interp arithmetic, clamped ends (oracle interp1d_np).
-// GUESS (tables in GLOBAL memory, where every bisection level is a dependent L2 round trip): interpolation search - the
-// bracket is guessed from the end knots (exact for a uniform grid), confirmed against the knots around the guess, and
-// only a failed confirmation bisects.  The bracket found is the bisection's, so the result is bit-identical.
-template <bool GUESS = false, typename P>
+// np.interp arithmetic, clamped ends (oracle interp1d_np)
+template <typename P>
 MXB_DEV double interp_clamped(P xp, P fp, int n, double x) {
-    const double x_lo = xp[0], x_hi = xp[n - 1];
-    if (x >= x_hi) return fp[n - 1];
-    if (x <= x_lo) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    if (x <= xp[0]) return fp[0];
     int lo = 0, hi = n - 1;  // invariant xp[lo] <= x < xp[hi]
-    bool found = false;
-#ifdef MXB_NO_INTERP_SEARCH
-    constexpr bool kGuess = false;
-#else
-    constexpr bool kGuess = GUESS;
-#endif
-    if (kGuess && n >= 8) {
-        int g = (int)((x - x_lo) * fast_rcp(x_hi - x_lo) * (double)(n - 1));
-        g = g < 1 ? 1 : (g > n - 3 ? n - 3 : g);
-        const double k0 = xp[g - 1], k1 = xp[g], k2 = xp[g + 1], k3 = xp[g + 2];      // independent loads
-        if (k1 <= x && x < k2) { lo = g; found = true; }
-        else if (k2 <= x && x < k3) { lo = g + 1; found = true; }
-        else if (k0 <= x && x < k1) { lo = g - 1; found = true; }
-        else if (x < k0) hi = g - 1;
-        else lo = g + 2;
-    }
-    if (!found) {
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (xp[mid] <= x) lo = mid; else hi = mid;
-        }
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
     }
     if (lo > n - 2) lo = n - 2;
     const double slope = div(fp[lo + 1] - fp[lo], xp[lo + 1] - xp[lo]);

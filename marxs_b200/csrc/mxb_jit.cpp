@@ -734,14 +734,11 @@ struct Gen {
             out("#else");
             out("        {   // lanes past the end of the batch re-read the last photon (their results are never stored)");
             out("            const idx_t il = active ? i : n_ph - 1;");
-            // JIT_STREAM_IN (experiment): the photon planes are read once - cache-streaming loads keep them from
-            // evicting the table lines the selectors bisect over from the small L1 left beside a large staged program
-            out("#ifdef JIT_STREAM_IN\n#define JIT_LD(k) __ldcs(P.in[k] + il)\n#else\n#define JIT_LD(k) P.in[k][il]\n#endif");
-            out("            ph.pos = V3{JIT_LD(0), JIT_LD(1), JIT_LD(2)};");
-            out("            ph.dir = V3{JIT_LD(3), JIT_LD(4), JIT_LD(5)};");
-            out("            ph.pol = V3{JIT_LD(6), JIT_LD(7), JIT_LD(8)};");
-            out("            ph.energy = JIT_LD(9);");
-            out("            ph.prob = JIT_LD(10);");
+            out("            ph.pos = V3{P.in[0][il], P.in[1][il], P.in[2][il]};");
+            out("            ph.dir = V3{P.in[3][il], P.in[4][il], P.in[5][il]};");
+            out("            ph.pol = V3{P.in[6][il], P.in[7][il], P.in[8][il]};");
+            out("            ph.energy = P.in[9][il];");
+            out("            ph.prob = P.in[10][il];");
             out("        }");
             out("#endif");
         }

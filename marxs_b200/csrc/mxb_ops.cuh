@@ -76,9 +76,6 @@ struct PRef {
     }
 };
 
-template <typename P> struct RefIsGlobal { static constexpr bool value = false; };
-template <> struct RefIsGlobal<PRef<false>> { static constexpr bool value = true; };
-
 struct SRef {
     const double* s;
     MXB_DEV double operator[](int k) const { return s[k]; }
@@ -375,7 +372,7 @@ MXB_DEV double filter_value(unsigned long long* st_sm, PP p, double energy, int 
             return slope * (energy - xp[lo]) + fp[lo];
         }
     }
-    return interp_clamped<RefIsGlobal<PP>::value>(xp, fp, n, energy);
+    return interp_clamped(xp, fp, n, energy);
 }
 
 // grating.py:12-57 OrderSelector with a compile-time order count (specialised kernels):
