@@ -823,9 +823,8 @@ MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_
     m_sincos(polangle, &sp, &cp);
     V3 pol{cp * nin.x + sp * ein.x, cp * nin.y + sp * ein.y, cp * nin.z + sp * ein.z};
     if ((flags & 1) && p[21] > 0.0) {
-        const double randang = u_axis * 2. * 3.141592653589793;
         double sa, ca;
-        m_sincos(randang, &sa, &ca);
+        sincos_turn(u_axis, &sa, &ca);          // randang = u_axis * 2. * pi
         const V3 ax{0., sa, ca};
         const double ang = 0. + p[21] * z_jitter;
         d = axangle_rotate_T(ax, ang, d);
@@ -839,11 +838,10 @@ MXB_DEV void op_pointing(Photon& ph, PP p, int flags, double ra_deg, double dec_
 // source/labSource.py:62-137: p = position[3] R[9] fractional_area
 template <typename PP>
 MXB_DEV void op_labcone(Photon& ph, PP p, double u_theta, double u_v, double polangle) {
-    const double theta = 0. + (kTwoPi - 0.) * u_theta;
     const double v = 0. + (p[12] - 0.) * u_v;
     const double phi = m_acos(1 - 2 * v);
     double st, ct, sp, cp;
-    m_sincos(theta, &st, &ct);
+    sincos_turn(u_theta, &st, &ct);            // theta = 0. + (2 pi - 0.) * u_theta
     m_sincos(phi, &sp, &cp);
     const V3 d{ct * sp, st * sp, cp};
     PP R = p + 3;
