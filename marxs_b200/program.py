@@ -142,15 +142,18 @@ def build_cull_grid(G, tan_max=0.12, max_cells=4096, hops=2):
                 mean_candidates=float(np.mean([len(l) for l in lists if l])) if len(cand) else 0.)
 
 
-def facet_reach_limits(G, grid):
-    """(F, F) matrix L of a facet array: L[A, B] (B > A) = smallest tangent of the angle to the array's mean normal a
-    ray needs to get from ANY point of facet A to facet B; inf for B <= A (the reference loops the facets in order and
-    never returns to an earlier one, simulator.py:42-49).
+def facet_reach_limits(G, grid, t_cap=1.0):
+    """Sparse reachability of a facet array: arrays (A, B, L) over the pairs A < B with L <= t_cap, where L[A, B] is a
+    lower bound of the tangent of the angle to the array's mean normal a ray needs to get from ANY point of facet A to
+    facet B.  (Only later facets matter: the reference loops the facets in order and never returns to an earlier one,
+    simulator.py:42-49.)
 
     The footprints of A and B on the mean plane are separated by gap_AB (the best of the four edge-normal axes of A's
     quadrilateral: a lower bound of their distance), their heights above the plane differ by at most h_AB, and a ray
     moves h tan(theta) sideways per height h: L = gap_AB / h_AB, shrunk by 1e-9 for rounding; 0 where the footprints
-    overlap.  Kernel side: csrc/mxb_ops.cuh array_revalidate (successor lists / single-hit stop)."""
+    overlap.  Pairs whose centres are further apart than the two half-diagonals plus t_cap times the array's height
+    range cannot have L <= t_cap and are never looked at (blocks of 512 facets against all centres).
+    Kernel side: csrc/mxb_ops.cuh array_revalidate (successor lists / single-hit stop)."""
     F = G.shape[0]
     c, ey, ez = G[:, 0:3], G[:, 6:9], G[:, 9:12]
     Ly, Lz = G[:, 12], G[:, 13]
@@ -162,27 +165,37 @@ def facet_reach_limits(G, grid):
     edges = np.roll(q, -1, axis=1) - q
     nrm = np.stack([edges[..., 1], -edges[..., 0]], axis=2)
     length = np.linalg.norm(nrm, axis=2, keepdims=True)
+    ctr = q.mean(axis=1)
+    rad = np.linalg.norm(q - ctr[:, None, :], axis=2).max(axis=1)
+    reach = 2. * rad.max() + t_cap * (h.max() - h.min())
     idx = np.arange(F)
-    later = idx[None, :] > idx[:, None]
+    pa, pb = [], []
+    for a0 in range(0, F, 512):
+        a1 = min(F, a0 + 512)
+        d2 = ((ctr[a0:a1, None, :] - ctr[None, :, :]) ** 2).sum(axis=2)
+        ia, ib = np.nonzero((d2 <= reach * reach) & (idx[None, :] > idx[a0:a1, None]))
+        pa.append(ia + a0)
+        pb.append(ib)
+    pa, pb = np.concatenate(pa), np.concatenate(pb)
+    if pa.size == 0:
+        return pa, pb, np.zeros(0)
     if not np.all(length > 0):
-        return np.where(later, 0., np.inf)                    # degenerate footprint (facet edge-on): nothing is known
+        return pa, pb, np.zeros(pa.size)                      # degenerate footprint (facet edge-on): nothing is known
     nrm = nrm / length
     hlo, hhi = h.min(axis=1), h.max(axis=1)
-    L = np.empty((F, F))
-    for a0 in range(0, F, 256):                               # blocks of facets: (256, 4, F, 4) projections at a time
-        a1 = min(F, a0 + 256)
-        proj = np.einsum('akx,bmx->akbm', nrm[a0:a1], q)
-        lo, hi = proj.min(axis=3), proj.max(axis=3)           # (A, 4, F)
-        own = np.einsum('akx,amx->akm', nrm[a0:a1], q[a0:a1])
-        own_lo, own_hi = own.min(axis=2), own.max(axis=2)     # (A, 4)
-        sep = np.maximum(lo - own_hi[:, :, None], own_lo[:, :, None] - hi).max(axis=1)        # (A, F)
+    L = np.empty(pa.size)
+    for p0 in range(0, pa.size, 65536):
+        A, B = pa[p0:p0 + 65536], pb[p0:p0 + 65536]
+        other = np.einsum('pkx,pmx->pkm', nrm[A], q[B])       # B's corners on A's four axes
+        own = np.einsum('pkx,pmx->pkm', nrm[A], q[A])
+        sep = np.maximum(other.min(axis=2) - own.max(axis=2), own.min(axis=2) - other.max(axis=2)).max(axis=1)
         gap = np.maximum(sep, 0.)
-        hd = np.maximum(hhi[a0:a1, None] - hlo[None, :], hhi[None, :] - hlo[a0:a1, None])
+        hd = np.maximum(hhi[A] - hlo[B], hhi[B] - hlo[A])
         with np.errstate(divide='ignore', invalid='ignore'):
-            L[a0:a1] = np.where(hd > 0, gap / hd, np.inf)
+            L[p0:p0 + 65536] = np.where(hd > 0, gap / hd, np.inf)
     L = np.where(np.isfinite(L), L * (1. - 1e-9), L)
-    L[~later] = np.inf
-    return L
+    keep = L <= t_cap
+    return pa[keep], pb[keep], L[keep]
 
 
 def single_hit_successors(G, grid, t_big=1.0, max_succ=8):
@@ -192,21 +205,21 @@ def single_hit_successors(G, grid, t_big=1.0, max_succ=8):
       succ[start[A]:start[A + 1]] (ascending) - none for most facets of a tiled array, the overlapping diagonal
       neighbours of a ring-placed one.  The kernel tests exactly those instead of the rest of the candidate list or the
       footprint scan; results equal the reference's loop over all facets by construction.
-    * succ is None when no facet has a successor inside the cone (then t2 is as large as the geometry allows).
+    * succ is None when no facet has a successor inside the cone (t2 is then the smallest pair limit, at most t_big^2).
     * (0., None, None): nothing can be certified."""
-    L = facet_reach_limits(G, grid)
     F = G.shape[0]
-    finite = L[np.isfinite(L)]
-    t_min = float(finite.min()) if finite.size else 1e3
+    A, B, L = facet_reach_limits(G, grid, t_cap=t_big)
+    t_min = float(L.min()) if L.size else t_big
     if t_min >= 0.3:                        # no pair closer than 17 degrees: one number for the array, no lists
-        return min(t_min, 1e3) ** 2, None, None
+        return min(t_min, t_big) ** 2, None, None
     for t in (t_big, 0.3):
-        within = L <= t
-        if within.sum(axis=1).max() <= max_succ:
+        sel = L <= t
+        count = np.bincount(A[sel], minlength=F)
+        if count.max() <= max_succ:
+            order = np.lexsort((B[sel], A[sel]))              # by facet, ascending successors
             start = np.zeros(F + 1, dtype=np.int64)
-            start[1:] = np.cumsum(within.sum(axis=1))
-            succ = np.nonzero(within)[1]                      # row-major: ascending within each facet
-            return t * t, start, succ
+            start[1:] = np.cumsum(count)
+            return t * t, start, B[sel][order]
     return 0., None, None
 
 
