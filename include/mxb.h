@@ -256,7 +256,8 @@ int mxb_debug_draws(uint64_t seed, int64_t photon_id0, int64_t n, int slot, int 
  * 2: x ** y as QualityFactor uses it (mitsnl/catgrating.py:147-161, y = order^2; x is ONE number for the call and
  *    log_hi + log_lo its natural logarithm as a double-double, the parameters the host lowers)  3: x / y
  * 4 / 5: sin(x) / cos(x) of the scatter rotations (math/rotations.py:50-87)  6 / 7: sin / cos of x turns, the
- * uniform azimuth x * 2 * pi of RandomGaussianScatter (optics/scatter.py:135-137).  Device pointers. */
+ * uniform azimuth x * 2 * pi of RandomGaussianScatter (optics/scatter.py:135-137)  8 / 9: sin / cos of a general angle
+ * (source/labSource.py:88-93, math/polarization.py:52-60, source/pointing.py:101-177).  Device pointers. */
 int mxb_debug_math(int kind, const double* x, const double* y, double* out, int64_t n, double log_hi, double log_lo, void* stream);
 
 /* sigma_clipped_stats of a device column (reference marxs/analysis/analysis.py:9-25 -> astropy.stats.sigma_clipped_stats

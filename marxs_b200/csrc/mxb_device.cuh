@@ -41,7 +41,10 @@ MXB_LIBM double m_log(double x) { return log(x); }
 MXB_LIBM double m_exp(double x) { return exp(x); }
 MXB_LIBM double m_pow(double x, double y) { return pow(x, y); }
 MXB_LIBM double m_atan2(double y, double x) { return atan2(y, x); }
+MXB_LIBM void libm_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+#if !defined(MXB_FAST) || defined(MXB_LIBM_SINCOS)
 MXB_LIBM void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+#endif                                                  // (fast build: m_sincos is defined below, after its tables)
 
 constexpr double kEnergy2Wave = 1.2398419292004202e-06;  // marxs/__init__.py:14 (keV -> mm)
 constexpr double kHcKevNm = 1.2398419843320026;          // astropy u.spectral(): keV -> nm
@@ -174,7 +177,7 @@ MXB_DEV V3 normalize(const V3& a) {
 // libm sincos for the (rare) large scatter angle: one out-of-line copy instead of ~110 inlined instructions per site
 __device__ __noinline__ double2 sincos_large(double x) {
     double s, c;
-    m_sincos(x, &s, &c);
+    libm_sincos(x, &s, &c);
     return make_double2(s, c);
 }
 #endif
@@ -344,6 +347,37 @@ MXB_DEV void sincos_turn(double u, double* s, double* c) {
 #endif
 }
 
+#if defined(MXB_FAST) && !defined(MXB_LIBM_SINCOS)
+// sin / cos of a general angle in the fast build: Cody-Waite reduction by pi/2 = hi + lo with two fma (exact products;
+// the remainder is good to 1e-28 |k| for |x| < 1e5), then the same constant-bank polynomials as sincos_turn: ~45
+// instead of libm's ~110 instructions per site, a third of which build coefficients with MOV pairs; <= 3 ulp
+// (test_device_math_vs_numpy).  Larger arguments take libm's routine out of line.
+MXB_DEV void m_sincos(double x, double* s, double* c) {
+    if (!(fabs(x) < 1e5)) {              // also NaN / inf
+        const double2 sc = sincos_large(x);
+        *s = sc.x;
+        *c = sc.y;
+        return;
+    }
+    const double q = rint(x * 0.63661977236758138);
+    double r = fma(-q, 1.5707963267948966, x);
+    r = fma(-q, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = kSinQ[5], pc = kCosQ[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        ps = fma(ps, z, kSinQ[k]);
+        pc = fma(pc, z, kCosQ[k]);
+    }
+    const double sn = fma(r * z, ps, r);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int k = (int)q;
+    const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+}
+#endif
+
 // math/rotations.py:50-87 axangle2mat applied TRANSPOSED (scatter.py:60,68), from sin / cos of the angle.
 // PERP: axis . v == 0 by construction (axis = v x something); AXIS_UNIT: |axis| == 1 already (fast build only)
 template <bool PERP = false, bool AXIS_UNIT = false>
@@ -397,6 +431,30 @@ MXB_DEV double interp_clamped(P xp, P fp, int n, double x) {
     if (lo > n - 2) lo = n - 2;
     const double slope = div(fp[lo + 1] - fp[lo], xp[lo + 1] - xp[lo]);
     return slope * (x - xp[lo]) + fp[lo];
+}
+
+// the bracket interp_clamped finds, for several value arrays over the SAME knots and query (MultiLayerEfficiency looks
+// three columns up at one position): mode 0 interior (segment lo), 1 clamped to the first value, 2 to the last
+template <typename P>
+MXB_DEV int interp_bracket(P xp, int n, double x, int& lo) {
+    lo = 0;
+    if (x >= xp[n - 1]) return 2;
+    if (x <= xp[0]) return 1;
+    int hi = n - 1;  // invariant xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (lo > n - 2) lo = n - 2;
+    return 0;
+}
+// value of one array on a bracket: the arithmetic of interp_clamped (x0 = xp[lo], dx = xp[lo + 1] - xp[lo])
+template <typename P>
+MXB_DEV double interp_on_bracket(P fp, int n, int mode, int lo, double x, double x0, double dx) {
+    if (mode == 2) return fp[n - 1];
+    if (mode == 1) return fp[0];
+    const double slope = div(fp[lo + 1] - fp[lo], dx);
+    return slope * (x - x0) + fp[lo];
 }
 
 // index i in [0, n-2] with xk[i] <= x < xk[i+1]  (searchsorted(side='right') - 1, clipped)

@@ -625,9 +625,13 @@ MXB_DEV void op_mleff(unsigned long long* st_sm, Photon& ph, PP p) {
     const double wavelength = div(kHcMultilayer, ph.energy);
     const double tested = interp_clamped(pe, pf, npol, ph.energy);
     const double local_x = div(ph.l0, Ly);
-    const double peak_w = interp_clamped(xs, pl, nr, local_x);
-    const double max_refl = div(interp_clamped(xs, pk, nr, local_x), tested);
-    const double spread = interp_clamped(xs, fw, nr, local_x);
+    // three columns at one position: one bisection (the values are interp_clamped's, bit for bit)
+    int lo;
+    const int mode = interp_bracket(xs, nr, local_x, lo);
+    const double x0 = mode ? 0.0 : xs[lo], dx = mode ? 1.0 : xs[lo + 1] - x0;      // (unused when clamped)
+    const double peak_w = interp_on_bracket(pl, nr, mode, lo, local_x, x0, dx);
+    const double max_refl = div(interp_on_bracket(pk, nr, mode, lo, local_x, x0, dx), tested);
+    const double spread = interp_on_bracket(fw, nr, mode, lo, local_x, x0, dx);
     const double c2 = div(spread * spread, 8. * 0.6931471805599453);
     double refl = 0.0;
     if (c2 != 0.0) {

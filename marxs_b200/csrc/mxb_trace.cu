@@ -1030,14 +1030,15 @@ __global__ void debug_math_kernel(int kind, const double* x, const double* y, do
         case 2: r = mxb::pow_loghost(a, log_hi, log_lo, b); break;
         case 3: r = mxb::div(a, b); break;
         case 4: case 5: { double s, c; mxb::sincos_small(a, &s, &c); r = (kind == 4) ? s : c; break; }
-        default: { double s, c; mxb::sincos_turn(a, &s, &c); r = (kind == 6) ? s : c; }
+        case 6: case 7: { double s, c; mxb::sincos_turn(a, &s, &c); r = (kind == 6) ? s : c; break; }
+        default: { double s, c; mxb::m_sincos(a, &s, &c); r = (kind == 8) ? s : c; }
         }
         out[i] = r;
     }
 }
 
 int mxb_debug_math(int kind, const double* x, const double* y, double* out, int64_t n, double log_hi, double log_lo, void* stream) {
-    if (!x || !out || kind < 0 || kind > 7 || ((kind == 2 || kind == 3) && !y)) return fail(MXB_EINVAL, "mxb_debug_math: bad argument");
+    if (!x || !out || kind < 0 || kind > 9 || ((kind == 2 || kind == 3) && !y)) return fail(MXB_EINVAL, "mxb_debug_math: bad argument");
     if (n <= 0) return n == 0 ? MXB_OK : fail(MXB_EINVAL, "negative n");
     debug_math_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(kind, x, y, out, n, log_hi, log_lo);
     CUDA_TRY(cudaGetLastError());

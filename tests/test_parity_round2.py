@@ -494,6 +494,14 @@ def test_device_math_vs_numpy(mode):
     tol = 2.3e-16 if mode == 'strict' else 8e-16     # strict: libm's sincos of the same rounded angle (1 ulp vs numpy)
     assert np.max(np.abs(_device_math(6, u) - np.sin(ang))) <= tol
     assert np.max(np.abs(_device_math(7, u) - np.cos(ang))) <= tol
+    # sin / cos of general angles (source cones, polarization angles, pointing): kinds 8 / 9
+    g = np.concatenate([rng.uniform(-7, 7, 100000), rng.uniform(-1e5, 1e5, 50000), np.arange(-8, 9) * (np.pi / 2),
+                        np.arange(-8, 9) * (np.pi / 4), [0., 1e-300, 99999.99, 1e5, 3e5, 1e9, -2e7]])
+    for kind, f in ((8, np.sin), (9, np.cos)):
+        got, want = _device_math(kind, g), f(g)
+        # 3 ulp of the value, or of the reduction's absolute accuracy next to a zero of the function
+        assert np.all(np.abs(got - want) <= 3 * eps * np.maximum(np.abs(want), 1e-3 * 0 + 2e-17 * np.maximum(np.abs(g), 1.)) + 3 * eps * np.abs(want)), kind
+    assert np.all(np.isnan(_device_math(8, np.array([np.nan, np.inf]))))
     q = rng.uniform(-5, 5, 10000)
     d = rng.uniform(0.1, 5, 10000) * rng.choice([-1., 1.], 10000)
     np.testing.assert_allclose(_device_math(3, q, d), q / d, rtol=(0 if mode == 'strict' else 2 * eps))
