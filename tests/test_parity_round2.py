@@ -604,3 +604,50 @@ def test_culled_search_equals_exhaustive_search(config):
     assert 0.5 < (full[idcol] >= 0).mean() < 0.95
     for c in full:
         assert np.array_equal(fast[c], full[c], equal_nan=True), c
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3, 4])
+def test_culled_search_equals_exhaustive_search_random_arrays(mode, seed):
+    """Random facet arrays - tiled, staggered in two layers, partly overlapping, strongly dispersing gratings or
+    detectors - hit by photons from inside and far outside the culling cone: the culled search (cell lists, certificate
+    with and without successor lists, footprint scan) must reproduce the exhaustive in-order search bit for bit in all
+    four build / kernel modes."""
+    mb = _mb()
+    from marxs_b200 import optics, simulator, program
+    rng = np.random.default_rng(SEED + 180 + seed)
+    n = 40000
+    layers = int(rng.integers(1, 3))
+    pitch = float(rng.choice([8.5, 10., 14.]))
+    half = float(rng.uniform(3.5, 0.62 * pitch))            # > pitch / 2: neighbours overlap
+    pos4ds = []
+    for layer in range(layers):
+        for y in np.arange(-40, 41, pitch):
+            for z in np.arange(-30, 31, pitch):
+                p = [-7. * layer + 0.003 * rng.uniform(0, 1) * (y * y + z * z), y + 0.4 * pitch * layer + rng.uniform(-1, 1),
+                     z - 0.3 * pitch * layer + rng.uniform(-1, 1)]
+                a, b = rng.uniform(-0.12, 0.12, 2)
+                Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+                Rz = np.array([[np.cos(b), -np.sin(b), 0], [np.sin(b), np.cos(b), 0], [0, 0, 1.]])
+                pos4ds.append(mo.compose(p, Rz @ Ry, [1., half * rng.uniform(0.8, 1.), half * rng.uniform(0.8, 1.)]))
+    order = rng.permutation(len(pos4ds))                     # list order is not spatial order
+    pos4ds = [pos4ds[k] for k in order]
+    if seed % 2:
+        sel = optics.OrderSelector(orderlist=np.array([-30, -12, 0, 9, 25]), p=np.full(5, 0.2))
+        make = lambda: simulator.Parallel(elem_class=optics.FlatGrating, elem_pos=pos4ds, id_col='facet',      # noqa: E731
+                                          elem_args=dict(d=2e-4, order_selector=sel))
+    else:
+        make = lambda: simulator.Parallel(elem_class=optics.FlatDetector, elem_pos=pos4ds, id_col='facet',     # noqa: E731
+                                          elem_args=dict(pixsize=0.05))
+    table = make_photons(rng, n, spread=float(rng.choice([0.05, 0.3, 1.2])), x0=40., lateral=45., e_lo=0.8, e_hi=1.6)
+    results = []
+    for exhaustive in (False, True):
+        program.EXHAUSTIVE_SEARCH = exhaustive
+        try:
+            mb.set_seed(5 + seed)
+            results.append(make()(mb.PhotonBatch(table, device='cuda')).to_numpy())
+        finally:
+            program.EXHAUSTIVE_SEARCH = False
+    culled, full = results
+    assert set(culled) == set(full) and 0.05 < (full['facet'] >= 0).mean()
+    for c in full:
+        assert np.array_equal(culled[c], full[c], equal_nan=True), c
