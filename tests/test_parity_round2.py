@@ -606,7 +606,7 @@ def test_culled_search_equals_exhaustive_search(config):
         assert np.array_equal(fast[c], full[c], equal_nan=True), c
 
 
-@pytest.mark.parametrize('seed', [1, 2, 3, 4])
+@pytest.mark.parametrize('seed', list(range(1, 1 + int(__import__('os').environ.get('MXB_TEST_SEEDS', '6')))))
 def test_culled_search_equals_exhaustive_search_random_arrays(mode, seed):
     """Random facet arrays - tiled, staggered in two layers, partly overlapping, strongly dispersing gratings or
     detectors - hit by photons from inside and far outside the culling cone: the culled search (cell lists, certificate
